@@ -1,0 +1,159 @@
+/* rsrx.h — C-ABI of librsrx.so, the B200 (sm_100a) batched Airbot stepper.
+ *
+ * The reference has no native boundary on this path: callers go through the
+ * brax `Env` API — `reset(rng) -> State`, `step(state, action) -> State`
+ * (reference test/airbot.py:102,165; cube_env.py:95,145; T_shape_env.py:98,139)
+ * wrapped by brax's VmapWrapper / DomainRandomizationVmapWrapper, EpisodeWrapper
+ * and AutoResetWrapper (twin: ppo_train/go2_training/mujoco_playground/_src/
+ * wrapper.py:117-165), and underneath `PipelineEnv.pipeline_init/pipeline_step`
+ * -> `mjx.forward` / n_frames x `mjx.step` (twin call site:
+ * mujoco_playground/_src/mjx_env.py:30-65).  The entry points below are what an
+ * FFI for that path binds; INTEGRATION.md shows the ctypes and XLA-FFI stubs.
+ *
+ * Conventions
+ *  - plain pointers and sizes; no torch / CUDA types in signatures.  `stream`
+ *    is a `cudaStream_t` passed as `void*` (NULL = default stream).
+ *  - every `float*` / `int32_t*` below is DEVICE memory owned by the caller,
+ *    unless the name ends in `_host`.
+ *  - functions return 0 on success, non-zero on error; rsrx_last_error() gives
+ *    the thread-local message.  Nothing throws across the ABI.  Launches are
+ *    asynchronous on `stream`; no allocation or host sync happens in
+ *    rsrx_env_reset / rsrx_env_step.
+ *  - batched natively: one call advances N environments; it *is* the
+ *    AutoReset(Episode(Vmap|DomainRandomizationVmap(env))) stack.
+ */
+#ifndef RSRX_H_
+#define RSRX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rsrx_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsrx_model rsrx_model; /* opaque; holds the device copy of the model */
+
+/* Offsets (in floats) of the fields inside one row of the `data` buffer — the
+ * mjx.Data subset that callers of the Airbot envs read.
+ * One row per env, `data_stride` floats apart. */
+typedef struct rsrx_layout {
+  int32_t data_stride; /* floats per env in data / first_data */
+  int32_t qpos, qvel, ctrl, qacc_warmstart, time;
+  int32_t xpos, xquat, site_xpos, geom_xpos;
+  int32_t obs_size;    /* 23 (sf, cube) or 16 (T) */
+  int32_t obs_stride;  /* floats per env in obs / first_obs */
+  int32_t info_stride; /* floats per env in info (RSRX_INFO_*) */
+  int32_t metrics_stride;
+  int32_t nq, nv, nu, nbody, nsite, ngeom;
+} rsrx_layout;
+
+/* info row (floats).  sf/cube: target_pos, new_cube_pos, site_pos, cube_pos,
+ * last_action.  T: target_base_pos, target_vertical_pos, target_w, new_T_pos,
+ * site_pos, T_pos, xita.  (reference test/airbot.py:153-159, T_shape_env.py:125-132) */
+#define RSRX_INFO_TARGET 0   /* [3] target_pos | target_base_pos */
+#define RSRX_INFO_TARGET2 3  /* [3] T: target_vertical_pos */
+#define RSRX_INFO_NEWPOS 6   /* [2] new_cube_pos | new_T_pos */
+#define RSRX_INFO_SITE 8     /* [3] site_pos */
+#define RSRX_INFO_OBJ 11     /* [3] cube_pos | T_pos */
+#define RSRX_INFO_LAST_ACTION 14
+#define RSRX_INFO_XITA 15
+#define RSRX_INFO_TARGET_W 16
+#define RSRX_INFO_STEPS 17      /* brax EpisodeWrapper info['steps'] */
+#define RSRX_INFO_TRUNCATION 18 /* brax EpisodeWrapper info['truncation'] */
+#define RSRX_INFO_STRIDE 20
+
+/* per-env status bits written by the kernels (no host sync needed to keep going) */
+#define RSRX_STATUS_NONFINITE 1      /* a non-finite value reached qpos/qvel */
+#define RSRX_STATUS_CONTACT_OVERFLOW 2 /* more active contacts than the kernel's cap */
+#define RSRX_STATUS_SOLVER_CAP 4     /* Newton hit opt.iterations */
+
+/* State of N wrapped envs; every pointer is a caller-owned device buffer. */
+typedef struct rsrx_state {
+  float* data;        /* [N][data_stride]  pipeline_state                 */
+  float* first_data;  /* [N][data_stride]  info['first_pipeline_state']   */
+  float* obs;         /* [N][obs_stride]                                   */
+  float* first_obs;   /* [N][obs_stride]   info['first_obs']               */
+  float* reward;      /* [N] */
+  float* done;        /* [N] */
+  float* info;        /* [N][RSRX_INFO_STRIDE] */
+  float* metrics;     /* [N][metrics_stride] */
+  int32_t* status;    /* [N] RSRX_STATUS_* (OR-accumulated) */
+} rsrx_state;
+
+/* Per-env model arrays = the four leaves the reference's domain_randomize gives a
+ * leading env axis (ppo_train/airbot_training/domain_randomize.py:71-90) — also
+ * used for the friction sweep (RSR/rsr_pipeline.py:125-136 sets
+ * geom_friction[-1,:]).  NULL = the nominal model value. */
+typedef struct rsrx_per_env {
+  const float* geom_friction;    /* [N][ngeom][3] */
+  const float* body_mass;        /* [N][nbody]    */
+  const float* dof_damping;      /* [N][nv]       */
+  const float* dof_frictionloss; /* [N][nv]       */
+} rsrx_per_env;
+
+/* ---- model ----------------------------------------------------------------
+ * replaces mujoco.MjModel.from_xml_path + brax.io.mjcf.load_model + mjx.put_model
+ * (test/airbot.py:43-47): the host compiles MJCF to an rsrx_model_blob
+ * (rsr_mjx_b200/mjcf.py) and hands it over here together with the env constants. */
+int rsrx_model_create(const void* blob_host, size_t blob_bytes, const rsrx_env_cfg* cfg_host, rsrx_model** out);
+void rsrx_model_destroy(rsrx_model* m);
+int rsrx_model_layout(const rsrx_model* m, rsrx_layout* out);
+size_t rsrx_model_blob_size(void);
+size_t rsrx_env_cfg_size(void);
+
+/* ---- env.reset -------------------------------------------------------------
+ * replaces jit(vmap(env.reset))(keys) (RSR/train.py:231) minus the sampling,
+ * which stays host-side Python (rsr_mjx_b200/airbot_spec.py::sample_reset restates
+ * jax.random): given sampled qpos[N][nq], qvel[N][nv], ctrl[N][nu] it runs
+ * pipeline_init (= mjx.make_data + mjx.forward, mjx_env.py:30-54), sets ctrl,
+ * builds info / metrics / obs (test/airbot.py:135-163) and the wrappers' reset
+ * state (first_pipeline_state, first_obs, steps, truncation). */
+int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, const float* qvel, const float* ctrl,
+                   const rsrx_per_env* per_env, rsrx_state st, void* stream);
+
+/* ---- env.step --------------------------------------------------------------
+ * replaces AutoResetWrapper(EpisodeWrapper(VmapWrapper(env))).step(state, action)
+ * (RSR/train.py:313 actor_step -> env.step): action[N][nu] in [-1,1]; one launch
+ * does action shaping, n_frames x mjx.step, reward/obs/done, episode bookkeeping
+ * and auto-reset for all N envs, in place on `st`. */
+int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const float* action, const rsrx_per_env* per_env,
+                  void* stream);
+
+/* ---- physics only (pipeline_step / mjx.step, mjx_env.py:55-65) ---------------
+ * advances data rows by nsteps x mjx.step with the ctrl stored in the rows. */
+int rsrx_physics_step(const rsrx_model* m, int N, float* data, int nsteps, const rsrx_per_env* per_env,
+                      int32_t* status, void* stream);
+
+/* Debug dump of the last forward() inside rsrx_physics_step(nsteps=1) for parity
+ * tests: per env M[nv*nv], qfrc_bias[nv], qacc_smooth[nv], qacc[nv],
+ * qfrc_constraint[nv], ncon, nefc, niter, contact dist[cap], contact pos[cap*3].
+ * `dump` is [N][rsrx_debug_stride()] floats. */
+int rsrx_debug_stride(void);
+int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, const rsrx_per_env* per_env, float* dump,
+                            void* stream);
+
+/* ---- RSR distribution loss (RSR/rsr_loss.py:122-175, dataset_processor.py:17-43)
+ * density[M] = softmax_m(logsumexp_n(-|grid_m - x_n|^2 / (2 h^2)) - log Ntot) over
+ * x = [reference_data (Nref rows); online batch (Nb rows)], both [.,D] row-major;
+ * distance = sum|cumsum(density) - cumsum(reference_density)|;
+ * loss = loss_scale * divergence * distance.
+ * out_host-free: out[0]=loss, out[1]=distance (device).  grad_batch may be NULL;
+ * otherwise it receives d loss / d batch [Nb][D] (callers slice the action
+ * columns, the only ones a policy gradient flows through). */
+int rsrx_rsr_loss(const float* grid, int M, int D, const float* reference_data, int Nref, const float* batch, int Nb,
+                  const float* reference_density, float bandwidth, float divergence, float loss_scale,
+                  float* density_out, float* out, float* grad_batch, void* stream);
+/* KDE density only (evaluate_kde) for build_rsr_data (rsr_loss.py:43-91) */
+int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, float bandwidth, float* density_out,
+             void* stream);
+
+const char* rsrx_last_error(void);
+const char* rsrx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSRX_H_ */

@@ -1,0 +1,332 @@
+// rsrx_api.cu — C-ABI of librsrx.so (include/rsrx.h): model upload and kernel
+// launches.  No torch types; the caller owns every state buffer.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "rsrx_env.cuh"
+#include "rsrx_loss.cuh"
+
+using namespace rsrx;
+
+struct rsrx_model {
+  DModel host;
+  DModel* dev;
+  int smem_bytes;
+};
+
+static thread_local std::string g_err;
+static int fail(const std::string& s) { g_err = s; return 1; }
+#define CUDA_OK(x)                                                                                   \
+  do {                                                                                               \
+    cudaError_t _e = (x);                                                                            \
+    if (_e != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+extern "C" const char* rsrx_last_error(void) { return g_err.c_str(); }
+extern "C" const char* rsrx_version(void) { return "rsrx 0.1 (sm_100a)"; }
+extern "C" size_t rsrx_model_blob_size(void) { return sizeof(rsrx_model_blob); }
+extern "C" size_t rsrx_env_cfg_size(void) { return sizeof(rsrx_env_cfg); }
+extern "C" int rsrx_debug_stride(void) { return dbg::STRIDE; }
+
+// ---- host-side double math for the static precomputation -----------------------
+namespace {
+void hq_mul(double* r, const double* u, const double* v) {
+  double a = u[0] * v[0] - u[1] * v[1] - u[2] * v[2] - u[3] * v[3];
+  double b = u[0] * v[1] + u[1] * v[0] + u[2] * v[3] - u[3] * v[2];
+  double c = u[0] * v[2] - u[1] * v[3] + u[2] * v[0] + u[3] * v[1];
+  double d = u[0] * v[3] + u[1] * v[2] - u[2] * v[1] + u[3] * v[0];
+  r[0] = a; r[1] = b; r[2] = c; r[3] = d;
+}
+void hq_mat(double* m, const double* q) {
+  m[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3]; m[1] = 2 * (q[1] * q[2] - q[0] * q[3]); m[2] = 2 * (q[1] * q[3] + q[0] * q[2]);
+  m[3] = 2 * (q[1] * q[2] + q[0] * q[3]); m[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3]; m[5] = 2 * (q[2] * q[3] - q[0] * q[1]);
+  m[6] = 2 * (q[1] * q[3] - q[0] * q[2]); m[7] = 2 * (q[2] * q[3] + q[0] * q[1]); m[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+}
+void hq_rot(double* r, const double* v, const double* q) {
+  double m[9];
+  hq_mat(m, q);
+  double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+}  // namespace
+
+static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel& d) {
+  memset(&d, 0, sizeof(d));
+  if (b.magic != RSRX_MAGIC || b.version != RSRX_VERSION) return fail("model blob: bad magic/version");
+  if (b.nbody > NB || b.njnt > NJ || b.nq > NQ || b.nv > NV || b.nu > NU || b.ngeom > NG || b.nsite > NS || b.npair > NP ||
+      b.neq > RSRX_MAXEQ)
+    return fail("model blob exceeds compiled capacities");
+  if (b.neq + b.nv > 32 || b.njnt > 32) return fail("too many constraint candidates for one warp");
+  d.nbody = b.nbody; d.njnt = b.njnt; d.nq = b.nq; d.nv = b.nv; d.nu = b.nu; d.ngeom = b.ngeom; d.nsite = b.nsite;
+  d.npair = b.npair; d.neq = b.neq;
+  d.iterations = b.iterations; d.ls_iterations = b.ls_iterations;
+  d.timestep = (float)b.timestep;
+  for (int i = 0; i < 3; i++) d.gravity[i] = (float)b.gravity[i];
+  d.tolerance = (float)b.tolerance; d.ls_tolerance = (float)b.ls_tolerance; d.impratio = (float)b.impratio;
+  d.meaninertia = (float)b.meaninertia;
+  int maxdepth = 0;
+  double sx[NB][3] = {{0}}, sq[NB][4] = {{0}};
+  sq[0][0] = 1;
+  for (int i = 0; i < b.nbody; i++) {
+    d.body_parentid[i] = b.body_parentid[i]; d.body_rootid[i] = b.body_rootid[i]; d.body_jntadr[i] = b.body_jntadr[i];
+    d.body_jntnum[i] = b.body_jntnum[i]; d.body_dofadr[i] = b.body_dofadr[i]; d.body_dofnum[i] = b.body_dofnum[i];
+    d.body_depth[i] = b.body_depth[i];
+    d.body_static[i] = (b.body_weldid[i] == 0);
+    if (b.body_depth[i] > maxdepth) maxdepth = b.body_depth[i];
+    for (int k = 0; k < 3; k++) { d.body_pos[i][k] = (float)b.body_pos[i][k]; d.body_ipos[i][k] = (float)b.body_ipos[i][k]; d.body_inertia[i][k] = (float)b.body_inertia[i][k]; }
+    for (int k = 0; k < 4; k++) { d.body_quat[i][k] = (float)b.body_quat[i][k]; d.body_iquat[i][k] = (float)b.body_iquat[i][k]; }
+    d.body_mass[i] = (float)b.body_mass[i];
+    d.body_invweight0[i] = (float)b.body_invweight0[i][0];
+    if (i > 0 && i <= b.body_parentid[i]) return fail("bodies must be in depth-first order");
+    // subtree end (bodies are in DFS pre-order)
+    int end = i + 1;
+    while (end < b.nbody && b.body_depth[end] > b.body_depth[i]) end++;
+    d.body_subtree_end[i] = end;
+    // dof mask along the path to the world
+    uint32_t mask = 0;
+    for (int a = i; a > 0; a = b.body_parentid[a])
+      for (int k = 0; k < b.body_dofnum[a]; k++) mask |= 1u << (b.body_dofadr[a] + k);
+    d.body_dofmask[i] = mask;
+    // static world pose
+    if (i > 0 && d.body_static[i]) {
+      int p = b.body_parentid[i];
+      double t[3];
+      hq_rot(t, b.body_pos[i], sq[p]);
+      for (int k = 0; k < 3; k++) sx[i][k] = sx[p][k] + t[k];
+      hq_mul(sq[i], sq[p], b.body_quat[i]);
+    }
+    for (int k = 0; k < 3; k++) d.static_xpos[i][k] = (float)sx[i][k];
+    for (int k = 0; k < 4; k++) d.static_xquat[i][k] = (float)sq[i][k];
+  }
+  d.nlevel = maxdepth + 1;
+  for (int j = 0; j < b.njnt; j++) {
+    d.jnt_type[j] = b.jnt_type[j]; d.jnt_qposadr[j] = b.jnt_qposadr[j]; d.jnt_dofadr[j] = b.jnt_dofadr[j];
+    d.jnt_bodyid[j] = b.jnt_bodyid[j]; d.jnt_limited[j] = b.jnt_limited[j];
+    if (b.jnt_type[j] != RSRX_JNT_FREE && b.jnt_type[j] != RSRX_JNT_HINGE && b.jnt_type[j] != RSRX_JNT_SLIDE)
+      return fail("unsupported joint type");
+    for (int k = 0; k < 3; k++) { d.jnt_pos[j][k] = (float)b.jnt_pos[j][k]; d.jnt_axis[j][k] = (float)b.jnt_axis[j][k]; }
+    for (int k = 0; k < 2; k++) { d.jnt_range[j][k] = (float)b.jnt_range[j][k]; d.jnt_solref[j][k] = (float)b.jnt_solref[j][k]; }
+    for (int k = 0; k < 5; k++) d.jnt_solimp[j][k] = (float)b.jnt_solimp[j][k];
+    d.jnt_margin[j] = (float)b.jnt_margin[j];
+  }
+  for (int i = 0; i < b.nq; i++) d.qpos0[i] = (float)b.qpos0[i];
+  d.nment = 0;
+  for (int i = 0; i < b.nv; i++) {
+    d.dof_bodyid[i] = b.dof_bodyid[i]; d.dof_jntid[i] = b.dof_jntid[i]; d.dof_parentid[i] = b.dof_parentid[i];
+    int j = b.dof_jntid[i];
+    d.dof_actfrclimited[i] = b.jnt_actfrclimited[j];
+    d.dof_actfrcrange[i][0] = (float)b.jnt_actfrcrange[j][0]; d.dof_actfrcrange[i][1] = (float)b.jnt_actfrcrange[j][1];
+    d.dof_hasfriction[i] = b.dof_frictionloss[i] > 0;
+    d.dof_damping[i] = (float)b.dof_damping[i]; d.dof_frictionloss[i] = (float)b.dof_frictionloss[i];
+    d.dof_armature[i] = (float)b.dof_armature[i]; d.dof_invweight0[i] = (float)b.dof_invweight0[i];
+    for (int k = 0; k < 2; k++) d.dof_solref[i][k] = (float)b.dof_solref[i][k];
+    for (int k = 0; k < 5; k++) d.dof_solimp[i][k] = (float)b.dof_solimp[i][k];
+    for (int a = i; a >= 0; a = b.dof_parentid[a]) {
+      if (d.nment >= MAXMENT) return fail("mass-matrix entry list overflow");
+      d.ment_i[d.nment] = (unsigned char)i; d.ment_j[d.nment] = (unsigned char)a; d.nment++;
+    }
+  }
+  d.ntri = 0;
+  for (int i = 0; i < b.nv; i++)
+    for (int j = 0; j <= i; j++) { d.tri_i[d.ntri] = (unsigned char)i; d.tri_j[d.ntri] = (unsigned char)j; d.ntri++; }
+  for (int g = 0; g < b.ngeom; g++) {
+    d.geom_type[g] = b.geom_type[g]; d.geom_bodyid[g] = b.geom_bodyid[g];
+    int bd = b.geom_bodyid[g];
+    d.geom_static[g] = d.body_static[bd];
+    for (int k = 0; k < 3; k++) { d.geom_pos[g][k] = (float)b.geom_pos[g][k]; d.geom_size[g][k] = (float)b.geom_size[g][k]; d.geom_friction[g][k] = (float)b.geom_friction[g][k]; }
+    for (int k = 0; k < 4; k++) d.geom_quat[g][k] = (float)b.geom_quat[g][k];
+    if (d.geom_static[g]) {
+      double t[3], q[4], m[9];
+      hq_rot(t, b.geom_pos[g], sq[bd]);
+      hq_mul(q, sq[bd], b.geom_quat[g]);
+      hq_mat(m, q);
+      for (int k = 0; k < 3; k++) d.geom_static_xpos[g][k] = (float)(sx[bd][k] + t[k]);
+      for (int k = 0; k < 9; k++) d.geom_static_xmat[g][k] = (float)m[k];
+    }
+  }
+  for (int s = 0; s < b.nsite; s++) {
+    d.site_bodyid[s] = b.site_bodyid[s];
+    for (int k = 0; k < 3; k++) d.site_pos[s][k] = (float)b.site_pos[s][k];
+  }
+  for (int p = 0; p < b.npair; p++) {
+    int g1 = b.pair_geom1[p], g2 = b.pair_geom2[p];
+    d.pair_g1[p] = g1; d.pair_g2[p] = g2;
+    int t1 = b.geom_type[g1], t2 = b.geom_type[g2];
+    if (!((t1 == RSRX_GEOM_PLANE || t1 == RSRX_GEOM_BOX) && t2 == RSRX_GEOM_BOX)) return fail("only plane-box and box-box pairs are supported");
+    int condim = b.geom_condim[g1] > b.geom_condim[g2] ? b.geom_condim[g1] : b.geom_condim[g2];
+    if (condim != 4) return fail("only condim 4 contacts are supported (all Airbot pairs are condim 4)");
+    // float32 mixing, like MJX does at run time
+    float mix1 = (float)b.geom_solmix[g1], mix2 = (float)b.geom_solmix[g2];
+    float mix = mix1 / (mix1 + mix2);
+    if (mix1 < MJ_MINVAL && mix2 < MJ_MINVAL) mix = 0.5f;
+    else if (mix1 < MJ_MINVAL) mix = 0.f;
+    else if (mix2 < MJ_MINVAL) mix = 1.f;
+    float r1[2] = {(float)b.geom_solref[g1][0], (float)b.geom_solref[g1][1]}, r2[2] = {(float)b.geom_solref[g2][0], (float)b.geom_solref[g2][1]};
+    bool standard = r1[0] > 0 && r2[0] > 0;
+    for (int k = 0; k < 2; k++) d.pair_solref[p][k] = standard ? mix * r1[k] + (1.f - mix) * r2[k] : (r1[k] < r2[k] ? r1[k] : r2[k]);
+    for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = mix * (float)b.geom_solimp[g1][k] + (1.f - mix) * (float)b.geom_solimp[g2][k];
+    d.pair_margin[p] = (float)(b.geom_margin[g1] > b.geom_margin[g2] ? b.geom_margin[g1] : b.geom_margin[g2]);
+    d.pair_tran[p] = (float)b.body_invweight0[b.geom_bodyid[g1]][0] + (float)b.body_invweight0[b.geom_bodyid[g2]][0];
+  }
+  for (int u = 0; u < b.nu; u++) {
+    int j = b.act_trnid[u];
+    d.act_qadr[u] = b.jnt_qposadr[j]; d.act_dof[u] = b.jnt_dofadr[j];
+    d.act_ctrllimited[u] = b.act_ctrllimited[u]; d.act_forcelimited[u] = b.act_forcelimited[u];
+    d.act_gear[u] = (float)b.act_gear[u]; d.act_gain[u] = (float)b.act_gainprm[u][0];
+    for (int k = 0; k < 3; k++) d.act_bias[u][k] = (float)b.act_biasprm[u][k];
+    for (int k = 0; k < 2; k++) { d.act_ctrlrange[u][k] = (float)b.act_ctrlrange[u][k]; d.act_forcerange[u][k] = (float)b.act_forcerange[u][k]; }
+  }
+  for (int e = 0; e < b.neq; e++) {
+    int j1 = b.eq_obj1id[e], j2 = b.eq_obj2id[e];
+    d.eq_q1[e] = b.jnt_qposadr[j1]; d.eq_d1[e] = b.jnt_dofadr[j1];
+    d.eq_q2[e] = j2 >= 0 ? b.jnt_qposadr[j2] : -1; d.eq_d2[e] = j2 >= 0 ? b.jnt_dofadr[j2] : -1;
+    float invw = (float)b.dof_invweight0[b.jnt_dofadr[j1]];
+    if (j2 >= 0) invw += (float)b.dof_invweight0[b.jnt_dofadr[j2]];
+    d.eq_invweight[e] = invw;
+    for (int k = 0; k < 5; k++) { d.eq_data[e][k] = (float)b.eq_data[e][k]; d.eq_solimp[e][k] = (float)b.eq_solimp[e][k]; }
+    for (int k = 0; k < 2; k++) d.eq_solref[e][k] = (float)b.eq_solref[e][k];
+  }
+  // env
+  d.env_kind = c.env_kind; d.episode_length = c.episode_length; d.action_repeat = c.action_repeat; d.n_frames = c.n_frames;
+  d.cube_body = c.cube_body; d.target_body = c.target_body; d.site_endpoint = c.site_endpoint; d.site_tail = c.site_tail;
+  d.site_target_tail = c.site_target_tail; d.geom_base = c.geom_base; d.geom_vertical = c.geom_vertical;
+  d.geom_target_base = c.geom_target_base; d.geom_target_vertical = c.geom_target_vertical;
+  for (int i = 0; i < 6; i++) d.joint_qadr[i] = c.joint_qadr[i];
+  for (int i = 0; i < NU; i++) d.action_scale[i] = (float)c.action_scale[i];
+  d.push_reward_weight = (float)c.push_reward_weight; d.siet_to_box_reward_weight = (float)c.siet_to_box_reward_weight;
+  d.healthy_reward = (float)c.healthy_reward; d.endpoint_min_z_pos = (float)c.endpoint_min_z_pos;
+  if (c.env_kind < 0 || c.env_kind > 2) return fail("bad env_kind");
+  if (b.nu < 5) return fail("Airbot envs need 5 actuators");
+  // layout
+  rsrx_layout& L = d.lay;
+  int o = 0;
+  L.qpos = o; o += b.nq;
+  L.qvel = o; o += b.nv;
+  L.ctrl = o; o += b.nu;
+  L.qacc_warmstart = o; o += b.nv;
+  L.time = o; o += 1;
+  L.xpos = o; o += b.nbody * 3;
+  L.xquat = o; o += b.nbody * 4;
+  L.site_xpos = o; o += b.nsite * 3;
+  L.geom_xpos = o; o += b.ngeom * 3;
+  L.data_stride = (o + 3) / 4 * 4;
+  L.obs_size = c.env_kind == RSRX_ENV_T ? 16 : 23;
+  L.obs_stride = OBS_STRIDE;
+  L.info_stride = RSRX_INFO_STRIDE;
+  L.metrics_stride = METRICS_STRIDE;
+  L.nq = b.nq; L.nv = b.nv; L.nu = b.nu; L.nbody = b.nbody; L.nsite = b.nsite; L.ngeom = b.ngeom;
+  return 0;
+}
+
+extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const rsrx_env_cfg* cfg_host, rsrx_model** out) {
+  if (!blob_host || !cfg_host || !out) return fail("rsrx_model_create: null argument");
+  if (blob_bytes != sizeof(rsrx_model_blob)) return fail("rsrx_model_create: blob size mismatch (host/lib out of sync)");
+  rsrx_model* m = new rsrx_model();
+  if (build_dmodel(*reinterpret_cast<const rsrx_model_blob*>(blob_host), *cfg_host, m->host)) { delete m; return 1; }
+  m->smem_bytes = ar::TOTAL * (int)sizeof(float);
+  cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
+  if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("rsrx_model_create: ") + cudaGetErrorString(e);
+    if (m->dev) cudaFree(m->dev);
+    delete m;
+    return fail(msg);
+  }
+  *out = m;
+  return 0;
+}
+
+extern "C" void rsrx_model_destroy(rsrx_model* m) {
+  if (!m) return;
+  if (m->dev) cudaFree(m->dev);
+  delete m;
+}
+
+extern "C" int rsrx_model_layout(const rsrx_model* m, rsrx_layout* out) {
+  if (!m || !out) return fail("rsrx_model_layout: null argument");
+  *out = m->host.lay;
+  return 0;
+}
+
+static PerEnv to_pe(const rsrx_per_env* p) {
+  PerEnv pe = {nullptr, nullptr, nullptr, nullptr};
+  if (p) { pe.geom_friction = p->geom_friction; pe.body_mass = p->body_mass; pe.dof_damping = p->dof_damping; pe.dof_frictionloss = p->dof_frictionloss; }
+  return pe;
+}
+static StatePtrs to_sp(const rsrx_state& s) {
+  StatePtrs p;
+  p.data = s.data; p.first_data = s.first_data; p.obs = s.obs; p.first_obs = s.first_obs; p.reward = s.reward; p.done = s.done;
+  p.info = s.info; p.metrics = s.metrics; p.status = s.status;
+  return p;
+}
+static int check_state(const rsrx_state& s) {
+  if (!s.data || !s.first_data || !s.obs || !s.first_obs || !s.reward || !s.done || !s.info || !s.metrics || !s.status)
+    return fail("rsrx_state: every buffer must be non-null");
+  return 0;
+}
+
+extern "C" int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, const float* qvel, const float* ctrl,
+                              const rsrx_per_env* per_env, rsrx_state st, void* stream) {
+  if (!m || !qpos || !qvel || !ctrl) return fail("rsrx_env_reset: null argument");
+  if (N <= 0) return fail("rsrx_env_reset: N must be positive");
+  if (check_state(st)) return 1;
+  reset_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(per_env), to_sp(st));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const float* action, const rsrx_per_env* per_env,
+                             void* stream) {
+  if (!m || !action) return fail("rsrx_env_step: null argument");
+  if (N <= 0) return fail("rsrx_env_step: N must be positive");
+  if (check_state(st)) return 1;
+  step_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(per_env), to_sp(st));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rsrx_physics_step(const rsrx_model* m, int N, float* data, int nsteps, const rsrx_per_env* per_env,
+                                 int32_t* status, void* stream) {
+  if (!m || !data) return fail("rsrx_physics_step: null argument");
+  if (N <= 0 || nsteps < 0) return fail("rsrx_physics_step: bad N / nsteps");
+  physics_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(per_env), status, nullptr);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, const rsrx_per_env* per_env, float* dump,
+                                       void* stream) {
+  if (!m || !data || !dump) return fail("rsrx_physics_step_debug: null argument");
+  if (N <= 0) return fail("rsrx_physics_step_debug: bad N");
+  physics_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, 1, to_pe(per_env), nullptr, dump);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- RSR loss -------------------------------------------------------------------
+extern "C" int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, float bandwidth, float* density_out,
+                        void* stream) {
+  if (!grid || !data || !density_out) return fail("rsrx_kde: null argument");
+  if (M <= 0 || M > loss::MAXM || D <= 0 || Ndata <= 0 || !(bandwidth > 0.f)) return fail("rsrx_kde: bad sizes (M <= 64)");
+  return loss::launch(grid, M, D, nullptr, 0, data, Ndata, nullptr, bandwidth, 0.f, 0.f, density_out, nullptr, nullptr,
+                      (cudaStream_t)stream)
+             ? fail(std::string("rsrx_kde: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+
+extern "C" int rsrx_rsr_loss(const float* grid, int M, int D, const float* reference_data, int Nref, const float* batch,
+                             int Nb, const float* reference_density, float bandwidth, float divergence, float loss_scale,
+                             float* density_out, float* out, float* grad_batch, void* stream) {
+  if (!grid || !batch || !reference_density || !out) return fail("rsrx_rsr_loss: null argument");
+  if (Nref > 0 && !reference_data) return fail("rsrx_rsr_loss: reference_data is null");
+  if (M <= 0 || M > loss::MAXM || D <= 0 || Nb <= 0 || Nref < 0 || !(bandwidth > 0.f)) return fail("rsrx_rsr_loss: bad sizes (M <= 64)");
+  return loss::launch(grid, M, D, reference_data, Nref, batch, Nb, reference_density, bandwidth, divergence, loss_scale,
+                      density_out, out, grad_batch, (cudaStream_t)stream)
+             ? fail(std::string("rsrx_rsr_loss: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}

@@ -1,0 +1,346 @@
+// rsrx_env.cuh — fused environment kernels: one launch = one brax
+// AutoResetWrapper(EpisodeWrapper(VmapWrapper(env))).step for N envs.
+//   reference env code: test/airbot.py:165-268, cube_env.py:145-229,
+//   T_shape_env.py:139-234; wrappers: mujoco_playground/_src/wrapper.py:117-138.
+#pragma once
+#include "rsrx_physics.cuh"
+
+namespace rsrx {
+
+struct PerEnv {
+  const float* geom_friction;
+  const float* body_mass;
+  const float* dof_damping;
+  const float* dof_frictionloss;
+};
+
+// load per-env model arrays + the dynamic state of env `e` into the arena
+__device__ void load_env(const DModel* __restrict__ dm, float* sm, int lane, int e, const float* __restrict__ row,
+                         const PerEnv& pe) {
+  const rsrx_layout& L = dm->lay;
+  for (int i = lane; i < dm->nq; i += 32) sm[ar::QPOS + i] = row[L.qpos + i];
+  for (int i = lane; i < dm->nv; i += 32) {
+    sm[ar::QVEL + i] = row[L.qvel + i];
+    sm[ar::WARM + i] = row[L.qacc_warmstart + i];
+    sm[ar::DAMP + i] = pe.dof_damping ? pe.dof_damping[(size_t)e * dm->nv + i] : dm->dof_damping[i];
+    sm[ar::FLOSS + i] = pe.dof_frictionloss ? pe.dof_frictionloss[(size_t)e * dm->nv + i] : dm->dof_frictionloss[i];
+  }
+  for (int i = lane; i < dm->nu; i += 32) sm[ar::CTRL + i] = row[L.ctrl + i];
+  for (int i = lane; i < dm->nbody; i += 32) sm[ar::BMASS + i] = pe.body_mass ? pe.body_mass[(size_t)e * dm->nbody + i] : dm->body_mass[i];
+  for (int i = lane; i < dm->ngeom * 3; i += 32)
+    sm[ar::GFRIC + i] = pe.geom_friction ? pe.geom_friction[(size_t)e * dm->ngeom * 3 + i] : dm->geom_friction[i / 3][i % 3];
+  RSRX_SYNC();
+}
+
+// write the pipeline_state row (qpos/qvel/ctrl/warmstart/time + lagged kinematics)
+__device__ void store_env(const DModel* __restrict__ dm, const float* sm, int lane, float* __restrict__ row, float time) {
+  const rsrx_layout& L = dm->lay;
+  for (int i = lane; i < dm->nq; i += 32) row[L.qpos + i] = sm[ar::QPOS + i];
+  for (int i = lane; i < dm->nv; i += 32) { row[L.qvel + i] = sm[ar::QVEL + i]; row[L.qacc_warmstart + i] = sm[ar::WARM + i]; }
+  for (int i = lane; i < dm->nu; i += 32) row[L.ctrl + i] = sm[ar::CTRL + i];
+  if (lane == 0) row[L.time] = time;
+  for (int i = lane; i < dm->nbody * 3; i += 32) row[L.xpos + i] = sm[ar::XPOS + i];
+  for (int i = lane; i < dm->nbody * 4; i += 32) row[L.xquat + i] = sm[ar::XQUAT + i];
+  for (int i = lane; i < dm->nsite * 3; i += 32) row[L.site_xpos + i] = sm[ar::SXPOS + i];
+  for (int i = lane; i < dm->ngeom * 3; i += 32) row[L.geom_xpos + i] = sm[ar::GXPOS + i];
+}
+
+// _get_obs into the arena's OBSBUF (lane 0); info = this env's info row
+__device__ void get_obs(const DModel* __restrict__ dm, float* sm, const float* info) {
+  float* obs = sm + ar::OBSBUF;
+  int n = 0;
+  for (int i = 0; i < 6; i++) obs[n++] = sm[ar::QPOS + dm->joint_qadr[i]];
+  const float* site = sm + ar::SXPOS + dm->site_endpoint * 3;
+  if (dm->env_kind == RSRX_ENV_T) {
+    obs[n++] = site[2];
+    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET + i] - sm[ar::GXPOS + dm->geom_base * 3 + i];
+    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET2 + i] - sm[ar::GXPOS + dm->geom_vertical * 3 + i];
+    obs[n++] = info[RSRX_INFO_XITA];
+    for (int i = 0; i < 2; i++) obs[n++] = info[RSRX_INFO_NEWPOS + i] - site[i];
+  } else {
+    const float* cube = sm + ar::XPOS + dm->cube_body * 3;
+    for (int i = 0; i < 3; i++) obs[n++] = site[i];
+    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET + i];
+    for (int i = 0; i < 3; i++) obs[n++] = cube[i];
+    for (int i = 0; i < 2; i++) obs[n++] = info[RSRX_INFO_NEWPOS + i];
+    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET + i] - cube[i];
+    for (int i = 0; i < 3; i++) obs[n++] = cube[i] - site[i];
+  }
+  for (; n < OBS_STRIDE; n++) obs[n] = 0.f;
+}
+
+struct StatePtrs {
+  float *data, *first_data, *obs, *first_obs, *reward, *done, *info, *metrics;
+  int* status;
+};
+
+// ---------------------------------------------------------------- reset kernel
+// pipeline_init (make_data + mjx.forward with ctrl = 0, warmstart = 0), then
+// data.replace(ctrl), info / metrics / obs, wrappers' reset bookkeeping.
+__global__ void __launch_bounds__(32) reset_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ qpos,
+                                                  const float* __restrict__ qvel, const float* __restrict__ ctrl,
+                                                  PerEnv pe, StatePtrs st) {
+  extern __shared__ float smem[];
+  float* sm = smem;
+  const int lane = threadIdx.x, e = blockIdx.x;
+  if (e >= N) return;
+  const rsrx_layout& L = dm->lay;
+  float* row = st.data + (size_t)e * L.data_stride;
+  // stage a row: qpos, qvel, ctrl = 0, warm = 0
+  for (int i = lane; i < L.data_stride; i += 32) row[i] = 0.f;
+  RSRX_SYNC();
+  for (int i = lane; i < dm->nq; i += 32) row[L.qpos + i] = qpos[(size_t)e * dm->nq + i];
+  for (int i = lane; i < dm->nv; i += 32) row[L.qvel + i] = qvel[(size_t)e * dm->nv + i];
+  RSRX_SYNC();
+  load_env(dm, sm, lane, e, row, pe);
+  SolverDims sd;
+  int status = 0;
+  forward(dm, sm, lane, &sd, &status);
+  for (int i = lane; i < dm->nu; i += 32) sm[ar::CTRL + i] = ctrl[(size_t)e * dm->nu + i];
+  RSRX_SYNC();
+  store_env(dm, sm, lane, row, 0.f);
+  float* info = st.info + (size_t)e * RSRX_INFO_STRIDE;
+  if (lane == 0) {
+    for (int i = 0; i < RSRX_INFO_STRIDE; i++) info[i] = 0.f;
+    const float* site = sm + ar::SXPOS + dm->site_endpoint * 3;
+    for (int i = 0; i < 3; i++) { info[RSRX_INFO_SITE + i] = site[i]; info[RSRX_INFO_OBJ + i] = sm[ar::XPOS + dm->cube_body * 3 + i]; }
+    if (dm->env_kind == RSRX_ENV_T) {
+      info[RSRX_INFO_NEWPOS] = 0.24739072f; info[RSRX_INFO_NEWPOS + 1] = -0.00496255f;
+      for (int i = 0; i < 3; i++) {
+        info[RSRX_INFO_TARGET + i] = sm[ar::GXPOS + dm->geom_target_base * 3 + i];
+        info[RSRX_INFO_TARGET2 + i] = sm[ar::GXPOS + dm->geom_target_vertical * 3 + i];
+      }
+      info[RSRX_INFO_TARGET_W] = sm[ar::XQUAT + dm->target_body * 4] * 10.f;
+      info[RSRX_INFO_XITA] = 0.2876f;
+    } else {
+      info[RSRX_INFO_NEWPOS] = 0.37342f; info[RSRX_INFO_NEWPOS + 1] = -0.07989f;
+      for (int i = 0; i < 3; i++) info[RSRX_INFO_TARGET + i] = sm[ar::XPOS + dm->target_body * 3 + i];
+    }
+    get_obs(dm, sm, info);
+    st.reward[e] = 0.f;
+    st.done[e] = 0.f;
+    for (int i = 0; i < METRICS_STRIDE; i++) st.metrics[(size_t)e * METRICS_STRIDE + i] = 0.f;
+  }
+  status = __reduce_or_sync(0xffffffffu, status);
+  if (lane == 0) st.status[e] = status;
+  RSRX_SYNC();
+  for (int i = lane; i < OBS_STRIDE; i += 32) {
+    st.obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
+    st.first_obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
+  }
+  __threadfence_block();
+  RSRX_SYNC();
+  float* frow = st.first_data + (size_t)e * L.data_stride;
+  for (int i = lane; i < L.data_stride; i += 32) frow[i] = row[i];
+}
+
+// ----------------------------------------------------------------- step kernel
+__global__ void __launch_bounds__(32) step_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ action,
+                                                 PerEnv pe, StatePtrs st) {
+  extern __shared__ float smem[];
+  float* sm = smem;
+  const int lane = threadIdx.x, e = blockIdx.x;
+  if (e >= N) return;
+  const rsrx_layout& L = dm->lay;
+  const int kind = dm->env_kind;
+  float* row = st.data + (size_t)e * L.data_stride;
+  float* info = st.info + (size_t)e * RSRX_INFO_STRIDE;
+  load_env(dm, sm, lane, e, row, pe);
+  float time = row[L.time];
+  // ---- AutoReset pre + action shaping (lane 0; reads the *lagged* kinematics of the row)
+  if (lane == 0) {
+    float steps = info[RSRX_INFO_STEPS];
+    if (st.done[e] != 0.f) steps = 0.f;
+    info[RSRX_INFO_STEPS] = steps;
+    float act[NU];
+    const int nu = dm->nu;
+    for (int i = 0; i < nu; i++) act[i] = sm[ar::CTRL + i] + dm->action_scale[i] * action[(size_t)e * nu + i];
+    act[3] = -(1.57f + sm[ar::QPOS + dm->joint_qadr[1]] + sm[ar::QPOS + dm->joint_qadr[2]]);
+    if (kind == RSRX_ENV_T) {
+      const float px = row[L.site_xpos + dm->site_endpoint * 3], py = row[L.site_xpos + dm->site_endpoint * 3 + 1];
+      const float dx = row[L.site_xpos + dm->site_tail * 3] - px, dy = row[L.site_xpos + dm->site_tail * 3 + 1] - py;
+      act[4] = -atan2f(dy, dx + 0.00001f) + act[0] + 1.5708f;
+    } else {
+      const float* cube = row + L.xpos + dm->cube_body * 3;
+      const float dx = info[RSRX_INFO_TARGET] - cube[0], dy = info[RSRX_INFO_TARGET + 1] - cube[1];
+      float a4 = -atan2f(dy, dx + 0.00001f) + act[0] + 1.5708f;
+      if (kind == RSRX_ENV_SF) {
+        float df[3] = {info[RSRX_INFO_TARGET] - cube[0], info[RSRX_INFO_TARGET + 1] - cube[1], info[RSRX_INFO_TARGET + 2] - cube[2]};
+        if (sqrtf(dot3(df, df)) < 0.03f) a4 = info[RSRX_INFO_LAST_ACTION];
+        info[RSRX_INFO_LAST_ACTION] = a4;
+      }
+      act[4] = a4;
+    }
+    for (int i = 0; i < nu; i++) sm[ar::CTRL + i] = clipf(act[i], dm->act_ctrlrange[i][0], dm->act_ctrlrange[i][1]);
+  }
+  RSRX_SYNC();
+  // ---- pipeline_step: n_frames x mjx.step
+  int status = 0;
+  SolverDims sd;
+  for (int f = 0; f < dm->n_frames; ++f) {
+    forward(dm, sm, lane, &sd, &status);
+    implicit_advance(dm, sm, lane);
+    time += dm->timestep;
+  }
+  // ---- post-physics (lane 0)
+  float done = 0.f;
+  if (lane == 0) {
+    float reward;
+    const float* site = sm + ar::SXPOS + dm->site_endpoint * 3;
+    const float W = dm->siet_to_box_reward_weight;
+    float* met = st.metrics + (size_t)e * METRICS_STRIDE;
+    if (kind == RSRX_ENV_T) {
+      float db[3], dv[3], box[3], tgt[3];
+      for (int i = 0; i < 3; i++) {
+        db[i] = info[RSRX_INFO_TARGET + i] - sm[ar::GXPOS + dm->geom_base * 3 + i];
+        dv[i] = info[RSRX_INFO_TARGET2 + i] - sm[ar::GXPOS + dm->geom_vertical * 3 + i];
+        box[i] = sm[ar::GXPOS + dm->geom_vertical * 3 + i] - sm[ar::GXPOS + dm->geom_base * 3 + i];
+        tgt[i] = info[RSRX_INFO_TARGET2 + i] - info[RSRX_INFO_TARGET + i];
+      }
+      float disb = sqrtf(dot3(db, db)), disv = sqrtf(dot3(dv, dv));
+      if (disb < 0.005f) disb = 0.f;
+      if (disv < 0.005f) disv = 0.f;
+      const float prb = 1.f / (1.f + 10.f * disb), prv = 1.f / (1.f + 10.f * disv);
+      const float cosx = dot3(box, tgt) / (sqrtf(dot3(box, box)) * sqrtf(dot3(tgt, tgt)));
+      const float xita = acosf(clipf(cosx, -1.f, 1.f));
+      info[RSRX_INFO_XITA] = xita;
+      const float pwr = 1.f / (1.f + 6.f * xita);
+      const float push = (0.1515f * prb + 0.1515f * prv + 0.66f * pwr) * dm->push_reward_weight;
+      const float tail0 = sm[ar::SXPOS + dm->site_tail * 3], tail1 = sm[ar::SXPOS + dm->site_tail * 3 + 1];
+      const float old0 = info[RSRX_INFO_NEWPOS], old1 = info[RSRX_INFO_NEWPOS + 1];
+      float site_z_reward = site[2] < 0.83f ? 1.f : 0.f;
+      site_z_reward += 4.f / (1.f + 3.f * fabsf(site[2] - 0.805f));
+      const float dx = sm[ar::SXPOS + dm->site_target_tail * 3] - tail0, dy = sm[ar::SXPOS + dm->site_target_tail * 3 + 1] - tail1;
+      const float ang = atan2f(dy, dx + 0.00001f);
+      const float distance = sqrtf(dx * dx + dy * dy) + 0.025f;
+      const float y_ = distance * sinf(ang), x_ = distance * cosf(ang);
+      info[RSRX_INFO_NEWPOS] = dx - x_ + tail0;
+      info[RSRX_INFO_NEWPOS + 1] = dy - y_ + tail1;
+      const float e0 = site[0] - old0, e1 = site[1] - old1;
+      float sdis = sqrtf(e0 * e0 + e1 * e1);
+      sdis = sdis < 0.02f ? 0.f : sdis - 0.02f;
+      const float s2c = (1.f - tanhf(5.f * sdis)) * W;
+      const float health = dm->healthy_reward * fabsf((site[2] < dm->endpoint_min_z_pos ? 1.f : 0.f) - 1.f);
+      reward = push + s2c + health + site_z_reward;
+      done = sm[ar::XPOS + dm->cube_body * 3 + 2] < 0.6f ? 1.f : 0.f;
+      met[0] = push; met[1] = s2c; met[2] = health; met[4] = site_z_reward;
+    } else {
+      const float* cube = sm + ar::XPOS + dm->cube_body * 3;
+      float df[3] = {info[RSRX_INFO_TARGET] - cube[0], info[RSRX_INFO_TARGET + 1] - cube[1], info[RSRX_INFO_TARGET + 2] - cube[2]};
+      float dis = sqrtf(dot3(df, df));
+      const float thr = kind == RSRX_ENV_SF ? 0.003f : 0.005f;
+      if (dis < thr) dis = 0.f;
+      const float push = (1.f / (1.f + 3.f * dis)) * dm->push_reward_weight;
+      const float task_complete = (kind == RSRX_ENV_SF && dis < 0.003f) ? 5.f : 0.f;
+      const float old0 = info[RSRX_INFO_NEWPOS], old1 = info[RSRX_INFO_NEWPOS + 1];
+      const float site_z_reward = site[2] < 0.82f ? 1.f : 0.f;
+      const float dx = info[RSRX_INFO_TARGET] - cube[0], dy = info[RSRX_INFO_TARGET + 1] - cube[1];
+      const float ang = atan2f(dy, dx + 0.00001f);
+      const float distance = sqrtf(dx * dx + dy * dy) + 0.04f;
+      const float y_ = distance * sinf(ang), x_ = distance * cosf(ang);
+      info[RSRX_INFO_NEWPOS] = dx - x_ + cube[0];
+      info[RSRX_INFO_NEWPOS + 1] = dy - y_ + cube[1];
+      const float e0 = site[0] - old0, e1 = site[1] - old1;
+      float sdis = sqrtf(e0 * e0 + e1 * e1);
+      sdis = sdis < 0.042f ? 0.f : sdis - 0.042f;
+      float s2c = (1.f - tanhf(5.f * sdis)) * W;
+      if (dis < 0.005f) s2c = W;
+      if (kind == RSRX_ENV_SF) {
+        float dn = 0.f;
+        if (site[2] < dm->endpoint_min_z_pos) dn = 1.f;
+        if (site[0] > 1.0f) dn = 1.f;
+        if (site[0] < -0.6f) dn = 1.f;
+        if (site[1] > 0.3f) dn = 1.f;
+        if (site[1] < -0.3f) dn = 1.f;
+        if (cube[2] < 0.6f) dn = 1.f;
+        const float health = dm->healthy_reward * fabsf(dn - 1.f);
+        reward = push + s2c + health + task_complete + site_z_reward;
+        done = dis < 0.003f ? 1.f : 0.f;
+        met[0] = push; met[1] = 0.f; met[2] = s2c;
+      } else {
+        const float health = dm->healthy_reward * fabsf((site[2] < dm->endpoint_min_z_pos ? 1.f : 0.f) - 1.f);
+        reward = push + s2c + health + site_z_reward;
+        done = cube[2] < 0.6f ? 1.f : 0.f;
+        met[0] = push; met[2] = s2c;
+      }
+    }
+    reward = clipf(reward, -1e2f, 1e2f);
+    get_obs(dm, sm, info);
+    for (int i = 0; i < 3; i++) { info[RSRX_INFO_SITE + i] = site[i]; info[RSRX_INFO_OBJ + i] = sm[ar::XPOS + dm->cube_body * 3 + i]; }
+    // EpisodeWrapper
+    float steps = info[RSRX_INFO_STEPS] + (float)dm->action_repeat;
+    float trunc = 0.f;
+    if (steps >= (float)dm->episode_length) { trunc = 1.f - done; done = 1.f; }
+    info[RSRX_INFO_STEPS] = steps;
+    info[RSRX_INFO_TRUNCATION] = trunc;
+    st.reward[e] = reward;
+    st.done[e] = done;
+  }
+  done = __shfl_sync(0xffffffffu, done, 0);
+  // non-finite guard
+  bool bad = false;
+  for (int i = lane; i < dm->nq; i += 32) bad |= !isfinite(sm[ar::QPOS + i]);
+  for (int i = lane; i < dm->nv; i += 32) bad |= !isfinite(sm[ar::QVEL + i]);
+  if (bad) status |= RSRX_STATUS_NONFINITE;
+  status = __reduce_or_sync(0xffffffffu, status);
+  if (lane == 0 && status) st.status[e] |= status;
+  RSRX_SYNC();
+  // ---- AutoReset post: pipeline_state and obs only
+  if (done != 0.f) {
+    const float* frow = st.first_data + (size_t)e * L.data_stride;
+    for (int i = lane; i < L.data_stride; i += 32) row[i] = frow[i];
+    for (int i = lane; i < OBS_STRIDE; i += 32) st.obs[(size_t)e * OBS_STRIDE + i] = st.first_obs[(size_t)e * OBS_STRIDE + i];
+  } else {
+    store_env(dm, sm, lane, row, time);
+    for (int i = lane; i < OBS_STRIDE; i += 32) st.obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
+  }
+}
+
+// ------------------------------------------------------------ physics-only kernel
+__global__ void __launch_bounds__(32) physics_kernel(const DModel* __restrict__ dm, int N, float* __restrict__ data,
+                                                    int nsteps, PerEnv pe, int* __restrict__ status_out,
+                                                    float* __restrict__ dump) {
+  extern __shared__ float smem[];
+  float* sm = smem;
+  const int lane = threadIdx.x, e = blockIdx.x;
+  if (e >= N) return;
+  const rsrx_layout& L = dm->lay;
+  float* row = data + (size_t)e * L.data_stride;
+  load_env(dm, sm, lane, e, row, pe);
+  float time = row[L.time];
+  int status = 0;
+  SolverDims sd;
+  sd.nsr = sd.ncon = sd.nrow = 0;
+  int niter = 0;
+  for (int f = 0; f < nsteps; ++f) {
+    niter = forward(dm, sm, lane, &sd, &status);
+    if (dump) {
+      float* dp = dump + (size_t)e * dbg::STRIDE;
+      const int nv = dm->nv;
+      for (int i = lane; i < nv * nv; i += 32) dp[dbg::M + i] = sm[ar::MM + (i / nv) * LD + (i % nv)];
+      for (int i = lane; i < nv; i += 32) {
+        dp[dbg::BIAS + i] = sm[ar::V_BIAS + i];
+        dp[dbg::QACC_SMOOTH + i] = sm[ar::V_QACCS + i];
+        dp[dbg::QACC + i] = sm[ar::V_QACC + i];
+        dp[dbg::QFRC_C + i] = sm[ar::V_QFRCC + i];
+        dp[dbg::QFRC_ACT + i] = sm[ar::V_ACT + i];
+      }
+      if (lane == 0) { dp[dbg::NCON] = (float)sd.ncon; dp[dbg::NEFC] = (float)sd.nrow; dp[dbg::NITER] = (float)niter; }
+      for (int c = lane; c < MAXC; c += 32) {
+        const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+        const bool v = c < sd.ncon;
+        dp[dbg::CDIST + c] = v ? cr[cf::DIST] : 0.f;
+        for (int i = 0; i < 3; i++) dp[dbg::CPOS + c * 3 + i] = v ? cr[cf::POS + i] : 0.f;
+        const int bodies = __float_as_int(cr[cf::BODIES]);
+        dp[dbg::CGEOM + c] = v ? (float)(((bodies >> 16) & 0xff) * 64 + ((bodies >> 24) & 0xff)) : -1.f;
+      }
+    }
+    implicit_advance(dm, sm, lane);
+    time += dm->timestep;
+  }
+  store_env(dm, sm, lane, row, time);
+  status = __reduce_or_sync(0xffffffffu, status);
+  if (lane == 0 && status_out) status_out[e] |= status;
+}
+
+}  // namespace rsrx

@@ -1,0 +1,1171 @@
+// rsrx_physics.cuh — one warp = one environment.  Every stage of mjx.step
+// (mujoco-mjx 3.2.4 forward.py::step) as a warp-cooperative
+// device function over the per-warp shared-memory arena (rsrx_device.cuh).
+// Lanes map to bodies / dofs / geoms / geom pairs / constraint rows; tree
+// recursions run level by level; reductions use xor-shuffles.
+#pragma once
+#include "rsrx_device.cuh"
+
+namespace rsrx {
+
+#define RSRX_SYNC() __syncwarp()
+
+// ------------------------------------------------------------------ kinematics
+// smooth.py::kinematics — static bodies/geoms come precomputed from the host.
+__device__ void kinematics(const DModel* __restrict__ dm, float* sm, int lane) {
+  const int nbody = dm->nbody;
+  if (lane < nbody && dm->body_static[lane]) {
+    for (int i = 0; i < 3; i++) sm[ar::XPOS + lane * 3 + i] = dm->static_xpos[lane][i];
+    for (int i = 0; i < 4; i++) sm[ar::XQUAT + lane * 4 + i] = dm->static_xquat[lane][i];
+  }
+  RSRX_SYNC();
+  for (int lev = 1; lev < dm->nlevel; ++lev) {
+    const int b = lane;
+    if (b < nbody && dm->body_depth[b] == lev && !dm->body_static[b]) {
+      const int p = dm->body_parentid[b];
+      float pq[4] = {sm[ar::XQUAT + p * 4], sm[ar::XQUAT + p * 4 + 1], sm[ar::XQUAT + p * 4 + 2], sm[ar::XQUAT + p * 4 + 3]};
+      float bp[3] = {dm->body_pos[b][0], dm->body_pos[b][1], dm->body_pos[b][2]};
+      float bq[4] = {dm->body_quat[b][0], dm->body_quat[b][1], dm->body_quat[b][2], dm->body_quat[b][3]};
+      float pos[3], quat[4], t[3];
+      rotate(t, bp, pq);
+      for (int i = 0; i < 3; i++) pos[i] = sm[ar::XPOS + p * 3 + i] + t[i];
+      quat_mul(quat, pq, bq);
+      const int jn = dm->body_jntnum[b], ja0 = dm->body_jntadr[b];
+      for (int k = 0; k < jn; k++) {
+        const int j = ja0 + k, qa = dm->jnt_qposadr[j];
+        const int jt = dm->jnt_type[j];
+        if (jt == RSRX_JNT_FREE) {
+          for (int i = 0; i < 3; i++) {
+            pos[i] = sm[ar::QPOS + qa + i];
+            sm[ar::XANCHOR + j * 3 + i] = pos[i];
+            sm[ar::XAXIS + j * 3 + i] = (i == 2) ? 1.f : 0.f;
+          }
+          for (int i = 0; i < 4; i++) quat[i] = sm[ar::QPOS + qa + 3 + i];
+          normalize4(quat);
+          for (int i = 0; i < 4; i++) sm[ar::QPOS + qa + 3 + i] = quat[i];
+        } else {
+          float jp[3] = {dm->jnt_pos[j][0], dm->jnt_pos[j][1], dm->jnt_pos[j][2]};
+          float jax[3] = {dm->jnt_axis[j][0], dm->jnt_axis[j][1], dm->jnt_axis[j][2]};
+          float anchor[3], axis[3];
+          rotate(anchor, jp, quat);
+          for (int i = 0; i < 3; i++) anchor[i] += pos[i];
+          rotate(axis, jax, quat);
+          for (int i = 0; i < 3; i++) { sm[ar::XANCHOR + j * 3 + i] = anchor[i]; sm[ar::XAXIS + j * 3 + i] = axis[i]; }
+          const float dq = sm[ar::QPOS + qa] - dm->qpos0[qa];
+          if (jt == RSRX_JNT_HINGE) {
+            float s, c;
+            sincosf(dq * 0.5f, &s, &c);
+            float ql[4] = {c, jax[0] * s, jax[1] * s, jax[2] * s}, q2[4];
+            quat_mul(q2, quat, ql);
+            for (int i = 0; i < 4; i++) quat[i] = q2[i];
+            rotate(t, jp, quat);
+            for (int i = 0; i < 3; i++) pos[i] = anchor[i] - t[i];
+          } else {
+            for (int i = 0; i < 3; i++) pos[i] += axis[i] * dq;
+          }
+        }
+      }
+      for (int i = 0; i < 3; i++) sm[ar::XPOS + b * 3 + i] = pos[i];
+      for (int i = 0; i < 4; i++) sm[ar::XQUAT + b * 4 + i] = quat[i];
+    }
+    RSRX_SYNC();
+  }
+  if (lane < nbody) {
+    const int b = lane;
+    float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
+    float m[9], t[3];
+    quat_to_mat(m, q);
+    for (int i = 0; i < 9; i++) sm[ar::XMAT + b * 9 + i] = m[i];
+    float ip[3] = {dm->body_ipos[b][0], dm->body_ipos[b][1], dm->body_ipos[b][2]};
+    rotate(t, ip, q);
+    for (int i = 0; i < 3; i++) sm[ar::XIPOS + b * 3 + i] = sm[ar::XPOS + b * 3 + i] + t[i];
+  }
+  if (lane < dm->ngeom) {
+    const int g = lane;
+    if (dm->geom_static[g]) {
+      for (int i = 0; i < 3; i++) sm[ar::GXPOS + g * 3 + i] = dm->geom_static_xpos[g][i];
+      for (int i = 0; i < 9; i++) sm[ar::GXMAT + g * 9 + i] = dm->geom_static_xmat[g][i];
+    } else {
+      const int b = dm->geom_bodyid[g];
+      float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
+      float gp[3] = {dm->geom_pos[g][0], dm->geom_pos[g][1], dm->geom_pos[g][2]};
+      float gq[4] = {dm->geom_quat[g][0], dm->geom_quat[g][1], dm->geom_quat[g][2], dm->geom_quat[g][3]};
+      float t[3], q2[4], m[9];
+      rotate(t, gp, q);
+      for (int i = 0; i < 3; i++) sm[ar::GXPOS + g * 3 + i] = sm[ar::XPOS + b * 3 + i] + t[i];
+      quat_mul(q2, q, gq);
+      quat_to_mat(m, q2);
+      for (int i = 0; i < 9; i++) sm[ar::GXMAT + g * 9 + i] = m[i];
+    }
+  }
+  if (lane < dm->nsite) {
+    const int s = lane, b = dm->site_bodyid[s];
+    float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
+    float sp[3] = {dm->site_pos[s][0], dm->site_pos[s][1], dm->site_pos[s][2]}, t[3];
+    rotate(t, sp, q);
+    for (int i = 0; i < 3; i++) sm[ar::SXPOS + s * 3 + i] = sm[ar::XPOS + b * 3 + i] + t[i];
+  }
+  RSRX_SYNC();
+}
+
+// smooth.py::com_pos — subtree_com of tree roots, cinert, cdof
+__device__ void com_pos(const DModel* __restrict__ dm, float* sm, int lane) {
+  const int nbody = dm->nbody;
+  // a root's subtree is the contiguous body range [b, subtree_end)
+  if (lane < nbody && lane > 0 && dm->body_rootid[lane] == lane) {
+    const int b = lane;
+    float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+    for (int c = dm->body_subtree_end[b] - 1; c >= b; --c) {  // leaves first, like the reverse tree scan
+      const float mc = sm[ar::BMASS + c];
+      px += sm[ar::XIPOS + c * 3] * mc; py += sm[ar::XIPOS + c * 3 + 1] * mc; pz += sm[ar::XIPOS + c * 3 + 2] * mc;
+      ms += mc;
+    }
+    if (ms < MJ_MINVAL) {
+      for (int i = 0; i < 3; i++) sm[ar::SCOM + b * 3 + i] = sm[ar::XIPOS + b * 3 + i];
+    } else {
+      const float d = fmaxf(ms, MJ_MINVAL);
+      sm[ar::SCOM + b * 3] = px / d; sm[ar::SCOM + b * 3 + 1] = py / d; sm[ar::SCOM + b * 3 + 2] = pz / d;
+    }
+  }
+  RSRX_SYNC();
+  if (lane < nbody && lane > 0 && !dm->body_static[lane]) {
+    const int b = lane, r = dm->body_rootid[b];
+    float off[3] = {sm[ar::XIPOS + b * 3] - sm[ar::SCOM + r * 3], sm[ar::XIPOS + b * 3 + 1] - sm[ar::SCOM + r * 3 + 1],
+                    sm[ar::XIPOS + b * 3 + 2] - sm[ar::SCOM + r * 3 + 2]};
+    const float ms = sm[ar::BMASS + b];
+    float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
+    float iq[4] = {dm->body_iquat[b][0], dm->body_iquat[b][1], dm->body_iquat[b][2], dm->body_iquat[b][3]};
+    float q2[4], R[9];
+    quat_mul(q2, q, iq);
+    quat_to_mat(R, q2);  // ximat
+    const float I0 = dm->body_inertia[b][0], I1 = dm->body_inertia[b][1], I2 = dm->body_inertia[b][2];
+    float in[6];  // 00 11 22 01 02 12
+    const int rr[6] = {0, 1, 2, 0, 0, 1}, cc[6] = {0, 1, 2, 1, 2, 2};
+    float h[3][3];
+    for (int r3 = 0; r3 < 3; r3++) {
+      float e[3] = {0.f, 0.f, 0.f};
+      e[r3] = -1.f;
+      cross3(h[r3], off, e);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int r3 = rr[k], c3 = cc[k];
+      float s = R[r3 * 3] * I0 * R[c3 * 3] + R[r3 * 3 + 1] * I1 * R[c3 * 3 + 1] + R[r3 * 3 + 2] * I2 * R[c3 * 3 + 2];
+      in[k] = s + dot3(h[r3], h[c3]) * ms;
+    }
+    float* ci = sm + ar::CINERT + b * 10;
+    for (int k = 0; k < 6; k++) ci[k] = in[k];
+    ci[6] = off[0] * ms; ci[7] = off[1] * ms; ci[8] = off[2] * ms; ci[9] = ms;
+  }
+  if (lane < dm->nv) {
+    const int d = lane, j = dm->dof_jntid[d], b = dm->jnt_bodyid[j], k = d - dm->jnt_dofadr[j];
+    const int r = dm->body_rootid[b], jt = dm->jnt_type[j];
+    float off[3] = {sm[ar::SCOM + r * 3] - sm[ar::XANCHOR + j * 3], sm[ar::SCOM + r * 3 + 1] - sm[ar::XANCHOR + j * 3 + 1],
+                    sm[ar::SCOM + r * 3 + 2] - sm[ar::XANCHOR + j * 3 + 2]};
+    float* cd = sm + ar::CDOF + d * 6;
+    if (jt == RSRX_JNT_FREE) {
+      if (k < 3) {
+        for (int i = 0; i < 6; i++) cd[i] = (i == 3 + k) ? 1.f : 0.f;
+      } else {
+        const int a = k - 3;
+        float ax[3] = {sm[ar::XMAT + b * 9 + a], sm[ar::XMAT + b * 9 + 3 + a], sm[ar::XMAT + b * 9 + 6 + a]}, c[3];
+        cross3(c, ax, off);
+        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = c[0]; cd[4] = c[1]; cd[5] = c[2];
+      }
+    } else if (jt == RSRX_JNT_SLIDE) {
+      cd[0] = cd[1] = cd[2] = 0.f;
+      for (int i = 0; i < 3; i++) cd[3 + i] = sm[ar::XAXIS + j * 3 + i];
+    } else {
+      float ax[3] = {sm[ar::XAXIS + j * 3], sm[ar::XAXIS + j * 3 + 1], sm[ar::XAXIS + j * 3 + 2]}, c[3];
+      cross3(c, ax, off);
+      cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = c[0]; cd[4] = c[1]; cd[5] = c[2];
+    }
+  }
+  RSRX_SYNC();
+}
+
+// In-place dense Cholesky (lower) of the nv x nv matrix at A (leading dim LD);
+// lane i owns row i.  Right-looking, one column per step.
+__device__ void warp_cholesky(float* A, int n, int lane) {
+  for (int k = 0; k < n; ++k) {
+    const float akk = A[k * LD + k];
+    const float d = sqrtf(akk > MJ_MINVAL ? akk : MJ_MINVAL);
+    float l = 0.f;
+    if (lane > k && lane < n) l = A[lane * LD + k] / d;
+    RSRX_SYNC();
+    if (lane == k) A[k * LD + k] = d;
+    if (lane > k && lane < n) A[lane * LD + k] = l;
+    RSRX_SYNC();
+    if (lane > k && lane < n) {
+      for (int j = k + 1; j <= lane; ++j) A[lane * LD + j] -= l * A[j * LD + k];
+    }
+    RSRX_SYNC();
+  }
+}
+// x <- (L L^T)^-1 x, x an nv-vector in shared memory
+__device__ void warp_chol_solve(const float* L, int n, float* x, int lane) {
+  for (int k = 0; k < n; ++k) {  // forward: L y = b
+    const float yk = x[k] / L[k * LD + k];
+    RSRX_SYNC();
+    if (lane == k) x[k] = yk;
+    if (lane > k && lane < n) x[lane] -= L[lane * LD + k] * yk;
+    RSRX_SYNC();
+  }
+  for (int k = n - 1; k >= 0; --k) {  // backward: L^T x = y
+    const float xk = x[k] / L[k * LD + k];
+    RSRX_SYNC();
+    if (lane == k) x[k] = xk;
+    if (lane < k) x[lane] -= L[k * LD + lane] * xk;
+    RSRX_SYNC();
+  }
+}
+
+// smooth.py::crb + support.make_m (dense) + factor_m
+__device__ void crb_and_factor(const DModel* __restrict__ dm, float* sm, int lane) {
+  const int nv = dm->nv, nbody = dm->nbody;
+  if (lane < nbody && lane > 0 && !dm->body_static[lane]) {
+    const int b = lane;
+    float acc[10];
+    for (int i = 0; i < 10; i++) acc[i] = 0.f;
+    for (int c = dm->body_subtree_end[b] - 1; c >= b; --c)
+      for (int i = 0; i < 10; i++) acc[i] += sm[ar::CINERT + c * 10 + i];
+    for (int i = 0; i < 10; i++) sm[ar::CRB + b * 10 + i] = acc[i];
+  }
+  for (int e = lane; e < nv * LD; e += 32) sm[ar::MM + e] = 0.f;
+  RSRX_SYNC();
+  if (lane < nv) {
+    float f[6];
+    inert_mul(f, sm + ar::CRB + dm->dof_bodyid[lane] * 10, sm + ar::CDOF + lane * 6);
+    for (int k = 0; k < 6; k++) sm[ar::CDOFDOT + lane * 6 + k] = f[k];
+  }
+  RSRX_SYNC();
+  for (int e = lane; e < dm->nment; e += 32) {
+    const int i = dm->ment_i[e], j = dm->ment_j[e];
+    float s = 0.f;
+    for (int k = 0; k < 6; k++) s += sm[ar::CDOF + j * 6 + k] * sm[ar::CDOFDOT + i * 6 + k];
+    if (i == j) s += dm->dof_armature[i];
+    sm[ar::MM + i * LD + j] = s;
+    sm[ar::MM + j * LD + i] = s;
+  }
+  RSRX_SYNC();
+  for (int e = lane; e < nv * LD; e += 32) sm[ar::LM + e] = sm[ar::MM + e];
+  RSRX_SYNC();
+  warp_cholesky(sm + ar::LM, nv, lane);
+}
+
+// ------------------------------------------------------------------- collision
+// collision_convex.py::_manifold_points with deterministic tie-breaking (see
+// oracle/rsr_oracle.c and DESIGN.md): a taken vertex scores like a masked one.
+__device__ void manifold_points(const float (*poly)[3], const bool* mask, int n, const float* nrm, int idx[4]) {
+  float dmk[8];
+  int a = 0, b = 0, c = 0, d = 0;
+  for (int i = 0; i < n; i++) dmk[i] = mask[i] ? 0.f : -1e6f;
+  float best = dmk[0];
+  for (int i = 1; i < n; i++) if (dmk[i] > best) { best = dmk[i]; a = i; }
+  dmk[a] = -1e6f;
+  best = -1e30f;
+  for (int i = 0; i < n; i++) {
+    float t[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]};
+    float v = dot3(t, t) + dmk[i];
+    if (v > best) { best = v; b = i; }
+  }
+  dmk[b] = -1e6f;
+  float ab[3], amb[3] = {poly[a][0] - poly[b][0], poly[a][1] - poly[b][1], poly[a][2] - poly[b][2]};
+  cross3(ab, nrm, amb);
+  best = -1e30f;
+  for (int i = 0; i < n; i++) {
+    float ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]};
+    float v = fabsf(dot3(ap, ab)) + dmk[i];
+    if (v > best) { best = v; c = i; }
+  }
+  dmk[c] = -1e6f;
+  float ac[3], bc[3];
+  float amc[3] = {poly[a][0] - poly[c][0], poly[a][1] - poly[c][1], poly[a][2] - poly[c][2]};
+  float bmc[3] = {poly[b][0] - poly[c][0], poly[b][1] - poly[c][1], poly[b][2] - poly[c][2]};
+  cross3(ac, nrm, amc);
+  cross3(bc, nrm, bmc);
+  best = -1e30f;
+  for (int i = 0; i < n; i++) {
+    float bp[3] = {poly[b][0] - poly[i][0], poly[b][1] - poly[i][1], poly[b][2] - poly[i][2]};
+    float v = fabsf(dot3(bp, bc)) + dmk[i];
+    if (v > best) { best = v; d = i; }
+  }
+  for (int i = 0; i < n; i++) {
+    float ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]};
+    float v = fabsf(dot3(ap, ac)) + dmk[i];
+    if (v > best) { best = v; d = i; }
+  }
+  idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = d;
+}
+
+// collision_convex.py::plane_convex on the 8 box vertices
+__device__ void plane_box(const float* ppos, const float* pmat, const float* bpos, const float* bmat, const float* size,
+                          float dist[4], float pos[4][3], float nrm[3]) {
+  float vert[8][3], support[8], n[3], pp[3], d[3];
+  float pn[3] = {pmat[2], pmat[5], pmat[8]};
+  for (int i = 0; i < 3; i++) d[i] = ppos[i] - bpos[i];
+  matT_vec(pp, bmat, d);
+  matT_vec(n, bmat, pn);
+  float smax = -1e30f;
+  for (int k = 0; k < 8; k++) {
+    vert[k][0] = (k & 1) ? size[0] : -size[0];
+    vert[k][1] = (k & 2) ? size[1] : -size[1];
+    vert[k][2] = (k & 4) ? size[2] : -size[2];
+    float t[3] = {pp[0] - vert[k][0], pp[1] - vert[k][1], pp[2] - vert[k][2]};
+    support[k] = dot3(t, n);
+    if (support[k] > smax) smax = support[k];
+  }
+  bool mask[8];
+  float thr = smax - 1e-3f;
+  if (thr < 0.f) thr = 0.f;
+  for (int k = 0; k < 8; k++) mask[k] = support[k] > thr;
+  int idx[4];
+  manifold_points(vert, mask, 8, n, idx);
+  for (int c = 0; c < 4; c++) {
+    bool unique = true;
+    for (int e = 0; e < c; e++) if (idx[e] == idx[c]) unique = false;
+    float wp[3];
+    mat_vec(wp, bmat, vert[idx[c]]);
+    dist[c] = unique ? -support[idx[c]] : 1.f;
+    for (int i = 0; i < 3; i++) pos[c][i] = bpos[i] + wp[i] - 0.5f * dist[c] * pn[i];
+  }
+  for (int i = 0; i < 3; i++) nrm[i] = pn[i];
+}
+
+__device__ int clip_halfspace(float (*poly)[3], int n, const float* pn, float h, float (*out)[3]) {
+  int no = 0;
+  for (int i = 0; i < n; i++) {
+    const float* a = poly[i];
+    const float* b = poly[(i + 1) % n];
+    float da = dot3(a, pn) - h, db = dot3(b, pn) - h;
+    if (da <= 0.f) { out[no][0] = a[0]; out[no][1] = a[1]; out[no][2] = a[2]; no++; }
+    if ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f)) {
+      float t = da / (da - db);
+      out[no][0] = a[0] + t * (b[0] - a[0]); out[no][1] = a[1] + t * (b[1] - a[1]); out[no][2] = a[2] + t * (b[2] - a[2]);
+      no++;
+    }
+  }
+  return no;
+}
+
+// SAT + face clipping / edge-edge; same rules as the oracle
+__device__ void box_box(const float* p1, const float* m1, const float* s1, const float* p2, const float* m2,
+                        const float* s2, float dist[4], float pos[4][3], float nrm[3]) {
+  float R[9], t[3], d[3];
+  for (int i = 0; i < 3; i++) d[i] = p1[i] - p2[i];
+  matT_vec(t, m2, d);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) R[r * 3 + c] = m2[r] * m1[c] + m2[3 + r] * m1[3 + c] + m2[6 + r] * m1[6 + c];
+  float axA[3][3], axB[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+  for (int a = 0; a < 3; a++) for (int i = 0; i < 3; i++) axA[a][i] = R[i * 3 + a];
+  float bestf = 1e30f, beste = 1e30f, sgnf = 1.f, sgne = 1.f;
+  int bf = 0, be = 6;
+  float axf[3] = {0.f, 0.f, 0.f}, axe[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < 15; k++) {
+    float ax[3];
+    bool degenerate = false;
+    if (k < 3) { ax[0] = axA[k][0]; ax[1] = axA[k][1]; ax[2] = axA[k][2]; }
+    else if (k < 6) { ax[0] = axB[k - 3][0]; ax[1] = axB[k - 3][1]; ax[2] = axB[k - 3][2]; }
+    else {
+      cross3(ax, axA[(k - 6) % 3], axB[(k - 6) / 3]);
+      degenerate = dot3(ax, ax) < 1e-6f;
+      normalize3(ax);
+    }
+    float ca = dot3(t, ax);
+    float ra = s1[0] * fabsf(dot3(axA[0], ax)) + s1[1] * fabsf(dot3(axA[1], ax)) + s1[2] * fabsf(dot3(axA[2], ax));
+    float rb = s2[0] * fabsf(ax[0]) + s2[1] * fabsf(ax[1]) + s2[2] * fabsf(ax[2]);
+    float dist1 = (ca + ra) - (-rb);
+    float dist2 = rb - (ca - ra);
+    float sg = dist1 > dist2 ? -1.f : 1.f;
+    float ov = dist1 < dist2 ? dist1 : dist2;
+    if (degenerate) ov = 1e6f;
+    if (k < 6) {
+      if (ov < bestf) { bestf = ov; bf = k; sgnf = sg; axf[0] = ax[0]; axf[1] = ax[1]; axf[2] = ax[2]; }
+    } else {
+      if (ov < beste) { beste = ov; be = k; sgne = sg; axe[0] = ax[0]; axe[1] = ax[1]; axe[2] = ax[2]; }
+    }
+  }
+  const bool is_edge = beste * 1.05f < bestf;
+  const int best = is_edge ? be : bf;
+  const float bov = is_edge ? beste : bestf;
+  float n[3];
+  if (is_edge) { n[0] = axe[0] * sgne; n[1] = axe[1] * sgne; n[2] = axe[2] * sgne; }
+  else { n[0] = axf[0] * sgnf; n[1] = axf[1] * sgnf; n[2] = axf[2] * sgnf; }
+  float lp[4][3];
+  for (int c = 0; c < 4; c++) { dist[c] = 1.f; lp[c][0] = lp[c][1] = lp[c][2] = 0.f; }
+  if (bov < 0.f) {
+    // separated
+  } else if (!is_edge) {
+    const bool refA = best < 3;
+    const int r = refA ? best : best - 3;
+    const float (*axP)[3] = refA ? axA : axB;
+    const float (*axQ)[3] = refA ? axB : axA;
+    const float* hP = refA ? s1 : s2;
+    const float* hQ = refA ? s2 : s1;
+    float cP[3], cQ[3], nref[3];
+    for (int i = 0; i < 3; i++) { cP[i] = refA ? t[i] : 0.f; cQ[i] = refA ? 0.f : t[i]; nref[i] = refA ? n[i] : -n[i]; }
+    int q = 0;
+    float bestd = -1.f;
+    for (int k = 0; k < 3; k++) { float v = fabsf(dot3(axQ[k], nref)); if (v > bestd) { bestd = v; q = k; } }
+    const float sq = dot3(axQ[q], nref) > 0.f ? -1.f : 1.f;
+    const int u = (q + 1) % 3, v = (q + 2) % 3;
+    float poly[8][3], tmp[8][3];
+    const float su[4] = {1.f, -1.f, -1.f, 1.f}, sv[4] = {1.f, 1.f, -1.f, -1.f};
+    for (int k = 0; k < 4; k++)
+      for (int i = 0; i < 3; i++)
+        poly[k][i] = cQ[i] + sq * hQ[q] * axQ[q][i] + su[k] * hQ[u] * axQ[u][i] + sv[k] * hQ[v] * axQ[v][i];
+    int np = 4;
+    const int pu = (r + 1) % 3, pv = (r + 2) % 3;
+    for (int s = 0; s < 4 && np > 0; s++) {
+      const int sa = s < 2 ? pu : pv;
+      const float sg = (s & 1) ? -1.f : 1.f;
+      float pn[3] = {sg * axP[sa][0], sg * axP[sa][1], sg * axP[sa][2]};
+      float h = hP[sa] + dot3(cP, pn);
+      np = clip_halfspace(poly, np, pn, h, tmp);
+      for (int k = 0; k < np; k++) { poly[k][0] = tmp[k][0]; poly[k][1] = tmp[k][1]; poly[k][2] = tmp[k][2]; }
+    }
+    if (np > 0) {
+      float depth[8], ref[8][3];
+      bool mask[8];
+      for (int k = 0; k < np; k++) {
+        float rel[3] = {poly[k][0] - cP[0], poly[k][1] - cP[1], poly[k][2] - cP[2]};
+        depth[k] = hP[r] - dot3(rel, nref);
+        mask[k] = depth[k] > 0.f;
+        for (int i = 0; i < 3; i++) ref[k][i] = poly[k][i] + depth[k] * nref[i];
+      }
+      int idx[4];
+      manifold_points(ref, mask, np, nref, idx);
+      for (int c = 0; c < 4; c++) {
+        bool unique = true;
+        for (int e = 0; e < c; e++) if (idx[e] == idx[c]) unique = false;
+        const int k = idx[c];
+        if (unique && mask[k]) {
+          dist[c] = -depth[k];
+          for (int i = 0; i < 3; i++) lp[c][i] = poly[k][i] + 0.5f * depth[k] * nref[i];
+        }
+      }
+    }
+  } else {
+    const int ia = (best - 6) % 3, jb = (best - 6) / 3;
+    float ea[3], eb[3];
+    for (int i = 0; i < 3; i++) { ea[i] = t[i]; eb[i] = 0.f; }
+    for (int k = 0; k < 3; k++) {
+      if (k != ia) {
+        float s = dot3(axA[k], n) >= 0.f ? 1.f : -1.f;
+        for (int i = 0; i < 3; i++) ea[i] += s * s1[k] * axA[k][i];
+      }
+      if (k != jb) {
+        float s = dot3(axB[k], n) >= 0.f ? 1.f : -1.f;
+        for (int i = 0; i < 3; i++) eb[i] -= s * s2[k] * axB[k][i];
+      }
+    }
+    const float* ua = axA[ia];
+    const float* ub = axB[jb];
+    float w0[3] = {ea[0] - eb[0], ea[1] - eb[1], ea[2] - eb[2]};
+    float bb = dot3(ua, ub), dd = dot3(ua, w0), ee = dot3(ub, w0);
+    float den = 1.f - bb * bb;
+    float sa = den > 1e-12f ? (bb * ee - dd) / den : 0.f;
+    float sb = den > 1e-12f ? (ee - bb * dd) / den : 0.f;
+    sa = clipf(sa, -s1[ia], s1[ia]);
+    sb = clipf(sb, -s2[jb], s2[jb]);
+    float pa[3], pb[3], df[3];
+    for (int i = 0; i < 3; i++) { pa[i] = ea[i] + sa * ua[i]; pb[i] = eb[i] + sb * ub[i]; df[i] = pb[i] - pa[i]; }
+    dist[0] = dot3(df, n);
+    for (int i = 0; i < 3; i++) lp[0][i] = 0.5f * (pa[i] + pb[i]);
+  }
+  for (int c = 0; c < 4; c++) {
+    float wp[3];
+    mat_vec(wp, m2, lp[c]);
+    for (int i = 0; i < 3; i++) pos[c][i] = p2[i] + wp[i];
+  }
+  mat_vec(nrm, m2, n);
+}
+
+// constraint.py::_kbi
+__device__ __forceinline__ void kbi(const DModel* __restrict__ dm, const float* solref, const float* solimp, float pos,
+                                    float* k, float* b, float* imp) {
+  float timeconst = solref[0];
+  const float dampratio = solref[1];
+  const float dt2 = 2.f * dm->timestep;
+  if (timeconst < dt2) timeconst = dt2;
+  const float dmin = clipf(solimp[0], MJ_MINIMP, MJ_MAXIMP), dmax = clipf(solimp[1], MJ_MINIMP, MJ_MAXIMP);
+  const float width = solimp[2] > MJ_MINVAL ? solimp[2] : MJ_MINVAL;
+  const float mid = clipf(solimp[3], MJ_MINIMP, MJ_MAXIMP);
+  const float power = solimp[4] > 1.f ? solimp[4] : 1.f;
+  *k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  *b = 2.f / (dmax * timeconst);
+  if (solref[0] <= 0.f) *k = -solref[0] / (dmax * dmax);
+  if (solref[1] <= 0.f) *b = -solref[1] / dmax;
+  const float x = fabsf(pos) / width;
+  if (x > 1.f) { *imp = dmax; return; }
+  float y;
+  if (x < mid) y = (1.f / pw(mid, power - 1.f)) * pw(x, power);
+  else y = 1.f - (1.f / pw(1.f - mid, power - 1.f)) * pw(1.f - x, power);
+  *imp = clipf(dmin + y * (dmax - dmin), dmin, dmax);
+}
+
+// collision_driver.py::collision: one lane per geom pair (narrow phase in
+// registers/local memory), warp prefix-sum compaction of the active contacts
+// into the shared-memory contact list in (pair, slot) order.  Contacts that MJX
+// would keep as zeroed rows (dist >= 0) are dropped.  Returns ncon.
+__device__ int collision(const DModel* __restrict__ dm, float* sm, int lane, int* status) {
+  int ncon = 0;
+  for (int base = 0; base < dm->npair; base += 32) {
+    const int p = base + lane;
+    float dist[4] = {1.f, 1.f, 1.f, 1.f}, pos[4][3], nrm[3] = {0.f, 0.f, 1.f};
+    int cnt = 0, g1 = 0, g2 = 0;
+    float margin = 0.f;
+    if (p < dm->npair) {
+      g1 = dm->pair_g1[p]; g2 = dm->pair_g2[p];
+      margin = dm->pair_margin[p];
+      float s2[3] = {dm->geom_size[g2][0], dm->geom_size[g2][1], dm->geom_size[g2][2]};
+      float p1[3], m1[9], p2[3], m2[9];
+      for (int i = 0; i < 3; i++) { p1[i] = sm[ar::GXPOS + g1 * 3 + i]; p2[i] = sm[ar::GXPOS + g2 * 3 + i]; }
+      for (int i = 0; i < 9; i++) { m1[i] = sm[ar::GXMAT + g1 * 9 + i]; m2[i] = sm[ar::GXMAT + g2 * 9 + i]; }
+      if (dm->geom_type[g1] == RSRX_GEOM_PLANE) {
+        plane_box(p1, m1, p2, m2, s2, dist, pos, nrm);
+      } else {
+        float s1[3] = {dm->geom_size[g1][0], dm->geom_size[g1][1], dm->geom_size[g1][2]};
+        box_box(p1, m1, s1, p2, m2, s2, dist, pos, nrm);
+      }
+      for (int c = 0; c < 4; c++) cnt += (dist[c] - margin < 0.f) ? 1 : 0;
+    }
+    // exclusive prefix sum of cnt over lanes
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int slot = ncon + incl - cnt;
+    if (cnt > 0) {
+      float frame[9];
+      make_frame(frame, nrm);
+      const int b1 = dm->geom_bodyid[g1], b2 = dm->geom_bodyid[g2];
+      float mu[3];
+      for (int i = 0; i < 3; i++) mu[i] = fmaxf(sm[ar::GFRIC + g1 * 3 + i], sm[ar::GFRIC + g2 * 3 + i]);
+      float solref[2] = {dm->pair_solref[p][0], dm->pair_solref[p][1]}, solimp[5];
+      for (int i = 0; i < 5; i++) solimp[i] = dm->pair_solimp[p][i];
+      const float tran = dm->pair_tran[p];
+      const float invw = (tran + mu[0] * mu[0] * tran) * 2.f * mu[0] * mu[0] / dm->impratio;
+      for (int c = 0; c < 4; c++) {
+        if (!(dist[c] - margin < 0.f)) continue;
+        if (slot >= MAXC) { *status |= RSRX_STATUS_CONTACT_OVERFLOW; break; }
+        float* cr = sm + ar::CON + slot * ar::CSTRIDE;
+        for (int i = 0; i < 3; i++) cr[cf::POS + i] = pos[c][i];
+        for (int i = 0; i < 9; i++) cr[cf::FRAME + i] = frame[i];
+        const float ps = dist[c] - margin;
+        float k, b, imp;
+        kbi(dm, solref, solimp, ps, &k, &b, &imp);
+        float rr = invw * (1.f - imp) / imp;
+        if (rr < MJ_MINVAL) rr = MJ_MINVAL;
+        cr[cf::DIST] = dist[c];
+        cr[cf::MU] = mu[0]; cr[cf::MU + 1] = mu[0]; cr[cf::MU + 2] = mu[1];
+        cr[cf::KIMPD] = k * imp * ps;
+        cr[cf::B] = b;
+        cr[cf::D] = 1.f / rr;
+        cr[cf::BODIES] = __int_as_float(b1 | (b2 << 8) | (g1 << 16) | (g2 << 24));
+        cr[cf::MASK] = __int_as_float((int)(dm->body_dofmask[b1] | dm->body_dofmask[b2]));
+        slot++;
+      }
+    }
+    ncon += total;
+    RSRX_SYNC();
+  }
+  if (ncon > MAXC) ncon = MAXC;
+  return ncon;
+}
+
+// ----------------------------------------------------------------- constraints
+// constraint.py::make_constraint.  Sparse rows (equality, dof friction, joint
+// limits) are kept as (dof, coef) pairs; contact rows as 4 base rows per contact
+// (normal, tangent1, tangent2, torsion) of the contact-frame Jacobian difference,
+// from which the 6 pyramid-edge rows J_n +- mu_k J_k are formed on the fly.
+// Row order: [sparse rows][6 rows per contact].  Returns nsr (number of sparse rows).
+__device__ int make_constraint(const DModel* __restrict__ dm, float* sm, int lane, int ncon) {
+  const int nv = dm->nv;
+  int* sr_dofa = reinterpret_cast<int*>(sm + ar::SR_DOFA);
+  int* sr_dofb = reinterpret_cast<int*>(sm + ar::SR_DOFB);
+  int* sr_type = reinterpret_cast<int*>(sm + ar::SR_TYPE);
+  // --- sparse rows: lane L handles candidate L: [eq | friction dofs | limited joints]
+  const int neq = dm->neq, nfr_c = nv, nlim_c = dm->njnt;
+  const int cand = lane;
+  bool have = false;
+  int type = 0, dofa = 0, dofb = -1;
+  float ca = 0.f, cb = 0.f, pos = 0.f, invw = 0.f, floss = 0.f, margin = 0.f;
+  float solref[2] = {0.02f, 1.f}, solimp[5] = {0.9f, 0.95f, 0.001f, 0.5f, 2.f};
+  if (cand < neq) {
+    const int e = cand, q1 = dm->eq_q1[e], q2 = dm->eq_q2[e];
+    have = true; type = 0; dofa = dm->eq_d1[e]; ca = 1.f;
+    const float pos1 = sm[ar::QPOS + q1] - dm->qpos0[q1];
+    if (q2 >= 0) {
+      const float dif = sm[ar::QPOS + q2] - dm->qpos0[q2];
+      const float dp[5] = {1.f, dif, dif * dif, dif * dif * dif, dif * dif * dif * dif};
+      float deriv = 0.f, poly = 0.f;
+      for (int i = 0; i < 5; i++) poly += dm->eq_data[e][i] * dp[i];
+      for (int i = 1; i < 5; i++) deriv += dm->eq_data[e][i] * dp[i - 1] * (float)i;
+      dofb = dm->eq_d2[e]; cb = -deriv;
+      pos = pos1 - poly;
+    } else {
+      pos = pos1 - dm->eq_data[e][0];
+    }
+    invw = dm->eq_invweight[e];
+    solref[0] = dm->eq_solref[e][0]; solref[1] = dm->eq_solref[e][1];
+    for (int i = 0; i < 5; i++) solimp[i] = dm->eq_solimp[e][i];
+  } else if (cand < neq + nfr_c) {
+    const int d = cand - neq;
+    if (dm->dof_hasfriction[d]) {
+      have = true; type = 1; dofa = d; ca = 1.f; pos = 0.f; invw = dm->dof_invweight0[d];
+      floss = sm[ar::FLOSS + d];
+      solref[0] = dm->dof_solref[d][0]; solref[1] = dm->dof_solref[d][1];
+      for (int i = 0; i < 5; i++) solimp[i] = dm->dof_solimp[d][i];
+    }
+  }
+  // limits may not fit the first 32 candidates: handled by a second candidate slot
+  bool have2 = false;
+  int dofa2 = 0;
+  float ca2 = 0.f, pos2 = 0.f, invw2 = 0.f, margin2 = 0.f;
+  float solref2[2] = {0.02f, 1.f}, solimp2[5] = {0.9f, 0.95f, 0.001f, 0.5f, 2.f};
+  if (lane < nlim_c) {
+    const int j = lane;
+    if (dm->jnt_limited[j] && dm->jnt_type[j] != RSRX_JNT_FREE) {
+      const float q = sm[ar::QPOS + dm->jnt_qposadr[j]];
+      const float dmin = q - dm->jnt_range[j][0], dmax = dm->jnt_range[j][1] - q;
+      margin2 = dm->jnt_margin[j];
+      const float ps = fminf(dmin, dmax) - margin2;
+      if (ps < 0.f) {
+        have2 = true; dofa2 = dm->jnt_dofadr[j]; ca2 = dmin < dmax ? 1.f : -1.f; pos2 = ps;
+        invw2 = dm->dof_invweight0[dofa2];
+        solref2[0] = dm->jnt_solref[j][0]; solref2[1] = dm->jnt_solref[j][1];
+        for (int i = 0; i < 5; i++) solimp2[i] = dm->jnt_solimp[j][i];
+      }
+    }
+  }
+  const unsigned m1 = __ballot_sync(0xffffffffu, have), m2 = __ballot_sync(0xffffffffu, have2);
+  const int n1 = __popc(m1), nsr = n1 + __popc(m2);
+  const unsigned lt = (1u << lane) - 1u;
+  if (have) {
+    const int r = __popc(m1 & lt);
+    float k, b, imp;
+    kbi(dm, solref, solimp, pos - margin, &k, &b, &imp);
+    float rr = invw * (1.f - imp) / imp;
+    if (rr < MJ_MINVAL) rr = MJ_MINVAL;
+    float vel = ca * sm[ar::QVEL + dofa];
+    if (dofb >= 0) vel += cb * sm[ar::QVEL + dofb];
+    // oracle sums J[d]*qvel[d] in dof order
+    if (dofb >= 0 && dofb < dofa) vel = cb * sm[ar::QVEL + dofb] + ca * sm[ar::QVEL + dofa];
+    sm[ar::E_D + r] = 1.f / rr;
+    sm[ar::E_AREF + r] = -b * vel - k * imp * (pos - margin);
+    sr_dofa[r] = dofa; sr_dofb[r] = dofb; sr_type[r] = type;
+    sm[ar::SR_CA + r] = ca; sm[ar::SR_CB + r] = cb; sm[ar::SR_FLOSS + r] = floss;
+  }
+  if (have2) {
+    const int r = n1 + __popc(m2 & lt);
+    float k, b, imp;
+    kbi(dm, solref2, solimp2, pos2, &k, &b, &imp);
+    float rr = invw2 * (1.f - imp) / imp;
+    if (rr < MJ_MINVAL) rr = MJ_MINVAL;
+    const float vel = ca2 * sm[ar::QVEL + dofa2];
+    sm[ar::E_D + r] = 1.f / rr;
+    sm[ar::E_AREF + r] = -b * vel - k * imp * pos2;
+    sr_dofa[r] = dofa2; sr_dofb[r] = -1; sr_type[r] = 2;
+    sm[ar::SR_CA + r] = ca2; sm[ar::SR_CB + r] = 0.f; sm[ar::SR_FLOSS + r] = 0.f;
+  }
+  // --- contact base rows B[c][p][dof] (support.jac + frame rotation)
+  for (int t = lane; t < ncon * nv; t += 32) {
+    const int c = t / nv, d = t - c * nv;
+    const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    const int bodies = __float_as_int(cr[cf::BODIES]);
+    const int b1 = bodies & 0xff, b2 = (bodies >> 8) & 0xff;
+    const bool in1 = (dm->body_dofmask[b1] >> d) & 1u, in2 = (dm->body_dofmask[b2] >> d) & 1u;
+    float dp[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f};
+    const float* cd = sm + ar::CDOF + d * 6;
+    if (in2) {
+      const int r2 = dm->body_rootid[b2];
+      float off[3] = {cr[0] - sm[ar::SCOM + r2 * 3], cr[1] - sm[ar::SCOM + r2 * 3 + 1], cr[2] - sm[ar::SCOM + r2 * 3 + 2]}, x[3];
+      cross3(x, cd, off);
+      for (int i = 0; i < 3; i++) { dp[i] = cd[3 + i] + x[i]; dr[i] = cd[i]; }
+    }
+    if (in1) {
+      const int r1 = dm->body_rootid[b1];
+      float off[3] = {cr[0] - sm[ar::SCOM + r1 * 3], cr[1] - sm[ar::SCOM + r1 * 3 + 1], cr[2] - sm[ar::SCOM + r1 * 3 + 2]}, x[3];
+      cross3(x, cd, off);
+      for (int i = 0; i < 3; i++) { dp[i] -= cd[3 + i] + x[i]; dr[i] -= cd[i]; }
+    }
+    float* B = sm + ar::BROW + c * 4 * nv;
+    B[0 * nv + d] = dot3(cr + cf::FRAME, dp);
+    B[1 * nv + d] = dot3(cr + cf::FRAME + 3, dp);
+    B[2 * nv + d] = dot3(cr + cf::FRAME + 6, dp);
+    B[3 * nv + d] = dot3(cr + cf::FRAME, dr);
+  }
+  RSRX_SYNC();
+  // --- contact rows: D, aref
+  for (int t = lane; t < ncon * 4; t += 32) {  // base velocities u_p = B_p . qvel
+    const float* Bp = sm + ar::BROW + t * nv;
+    float s = 0.f;
+    for (int d = 0; d < nv; d++) s += Bp[d] * sm[ar::QVEL + d];
+    sm[ar::UB + t] = s;
+  }
+  RSRX_SYNC();
+  for (int t = lane; t < ncon * 6; t += 32) {
+    const int c = t / 6, e = t - c * 6, k = e >> 1;
+    const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    const float f = (e & 1) ? -cr[cf::MU + k] : cr[cf::MU + k];
+    const float vel = sm[ar::UB + c * 4] + sm[ar::UB + c * 4 + 1 + k] * f;
+    sm[ar::E_D + nsr + t] = cr[cf::D];
+    sm[ar::E_AREF + nsr + t] = -cr[cf::B] * vel - cr[cf::KIMPD];
+  }
+  RSRX_SYNC();
+  return nsr;
+}
+
+// ------------------------------------------------------------ velocity / forces
+// smooth.py::com_vel, passive.py, smooth.py::rne, forward.py::fwd_actuation,
+// fwd_acceleration
+__device__ void velocity_and_forces(const DModel* __restrict__ dm, float* sm, int lane) {
+  const int nv = dm->nv, nbody = dm->nbody;
+  float* cacc = sm + ar::CRB;           // [NB][6] (crb no longer needed)
+  float* cfrc = sm + ar::CRB + NB * 6;  // needs NB*6 more: CRB has NB*10 = 160 >= 96 + 64? no -> use XIPOS.. see below
+  (void)cfrc;
+  // com_vel: level by level
+  if (lane < nbody && dm->body_static[lane]) {
+    for (int i = 0; i < 6; i++) { sm[ar::CVEL + lane * 6 + i] = 0.f; cacc[lane * 6 + i] = (i >= 3) ? -dm->gravity[i - 3] : 0.f; }
+  }
+  RSRX_SYNC();
+  for (int lev = 1; lev < dm->nlevel; ++lev) {
+    const int b = lane;
+    if (b < nbody && dm->body_depth[b] == lev && !dm->body_static[b]) {
+      const int p = dm->body_parentid[b];
+      float cvel[6];
+      for (int i = 0; i < 6; i++) cvel[i] = sm[ar::CVEL + p * 6 + i];
+      const int jn = dm->body_jntnum[b], ja0 = dm->body_jntadr[b];
+      for (int k = 0; k < jn; k++) {
+        const int j = ja0 + k, d = dm->jnt_dofadr[j];
+        if (dm->jnt_type[j] == RSRX_JNT_FREE) {
+          for (int a = 0; a < 3; a++)
+            for (int i = 0; i < 6; i++) cvel[i] += sm[ar::CDOF + (d + a) * 6 + i] * sm[ar::QVEL + d + a];
+          for (int a = 0; a < 3; a++) {
+            for (int i = 0; i < 6; i++) sm[ar::CDOFDOT + (d + a) * 6 + i] = 0.f;
+            float r[6];
+            motion_cross(r, cvel, sm + ar::CDOF + (d + 3 + a) * 6);
+            for (int i = 0; i < 6; i++) sm[ar::CDOFDOT + (d + 3 + a) * 6 + i] = r[i];
+          }
+          for (int a = 3; a < 6; a++)
+            for (int i = 0; i < 6; i++) cvel[i] += sm[ar::CDOF + (d + a) * 6 + i] * sm[ar::QVEL + d + a];
+        } else {
+          float r[6];
+          motion_cross(r, cvel, sm + ar::CDOF + d * 6);
+          for (int i = 0; i < 6; i++) sm[ar::CDOFDOT + d * 6 + i] = r[i];
+          for (int i = 0; i < 6; i++) cvel[i] += sm[ar::CDOF + d * 6 + i] * sm[ar::QVEL + d];
+        }
+      }
+      for (int i = 0; i < 6; i++) sm[ar::CVEL + b * 6 + i] = cvel[i];
+      // rne forward pass: cacc
+      float ca[6];
+      for (int i = 0; i < 6; i++) ca[i] = cacc[p * 6 + i];
+      const int dn = dm->body_dofnum[b], d0 = dm->body_dofadr[b];
+      for (int k = 0; k < dn; k++)
+        for (int i = 0; i < 6; i++) ca[i] += sm[ar::CDOFDOT + (d0 + k) * 6 + i] * sm[ar::QVEL + d0 + k];
+      for (int i = 0; i < 6; i++) cacc[b * 6 + i] = ca[i];
+    }
+    RSRX_SYNC();
+  }
+  // local body forces -> HH scratch [NB][6] (H is rebuilt later by the solver)
+  float* lfrc = sm + ar::HH;
+  if (lane < nbody && lane > 0 && !dm->body_static[lane]) {
+    const int b = lane;
+    float f1[6], f2[6], f3[6];
+    inert_mul(f1, sm + ar::CINERT + b * 10, cacc + b * 6);
+    inert_mul(f2, sm + ar::CINERT + b * 10, sm + ar::CVEL + b * 6);
+    motion_cross_force(f3, sm + ar::CVEL + b * 6, f2);
+    for (int i = 0; i < 6; i++) lfrc[b * 6 + i] = f1[i] + f3[i];
+  }
+  RSRX_SYNC();
+  // qfrc_bias[d] = cdof[d] . sum_{c in subtree(body(d))} lfrc[c]; passive; actuation
+  if (lane < nv) {
+    const int d = lane, b = dm->dof_bodyid[d];
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = dm->body_subtree_end[b] - 1; c >= b; --c)
+      for (int i = 0; i < 6; i++) acc[i] += lfrc[c * 6 + i];
+    float s = 0.f;
+    for (int i = 0; i < 6; i++) s += sm[ar::CDOF + d * 6 + i] * acc[i];
+    sm[ar::V_BIAS + d] = s;
+    sm[ar::V_PASSIVE + d] = -sm[ar::DAMP + d] * sm[ar::QVEL + d];
+    sm[ar::V_ACT + d] = 0.f;
+  }
+  RSRX_SYNC();
+  if (lane < dm->nu) {
+    const int u = lane, qa = dm->act_qadr[u], d = dm->act_dof[u];
+    float ctrl = sm[ar::CTRL + u];
+    if (dm->act_ctrllimited[u]) ctrl = clipf(ctrl, dm->act_ctrlrange[u][0], dm->act_ctrlrange[u][1]);
+    const float gear = dm->act_gear[u];
+    const float length = gear * sm[ar::QPOS + qa], velocity = gear * sm[ar::QVEL + d];
+    const float bias = dm->act_bias[u][0] + dm->act_bias[u][1] * length + dm->act_bias[u][2] * velocity;
+    float force = dm->act_gain[u] * ctrl + bias;
+    if (dm->act_forcelimited[u]) force = clipf(force, dm->act_forcerange[u][0], dm->act_forcerange[u][1]);
+    atomicAdd(sm + ar::V_ACT + d, gear * force);
+  }
+  RSRX_SYNC();
+  if (lane < nv) {
+    const int d = lane;
+    float fa = sm[ar::V_ACT + d];
+    if (dm->dof_actfrclimited[d]) fa = clipf(fa, dm->dof_actfrcrange[d][0], dm->dof_actfrcrange[d][1]);
+    sm[ar::V_ACT + d] = fa;
+    const float fs = sm[ar::V_PASSIVE + d] - sm[ar::V_BIAS + d] + fa;
+    sm[ar::V_SMOOTH + d] = fs;
+    sm[ar::V_QACCS + d] = fs;
+  }
+  RSRX_SYNC();
+  warp_chol_solve(sm + ar::LM, nv, sm + ar::V_QACCS, lane);
+}
+
+// ---------------------------------------------------------------------- solver
+struct SolverDims { int nsr, ncon, nrow; };
+
+// out[r] = J[r] . x for every row (x: nv-vector in shared memory)
+__device__ void mul_J(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, const float* x, float* out) {
+  const int nv = dm->nv;
+  const int* sr_dofa = reinterpret_cast<const int*>(sm + ar::SR_DOFA);
+  const int* sr_dofb = reinterpret_cast<const int*>(sm + ar::SR_DOFB);
+  if (lane < sd.nsr) {
+    const int a = sr_dofa[lane], b = sr_dofb[lane];
+    float s = sm[ar::SR_CA + lane] * x[a];
+    if (b >= 0) s = (b < a) ? sm[ar::SR_CB + lane] * x[b] + s : s + sm[ar::SR_CB + lane] * x[b];
+    out[lane] = s;
+  }
+  for (int t = lane; t < sd.ncon * 4; t += 32) {
+    const float* Bp = sm + ar::BROW + t * nv;
+    float s = 0.f;
+    for (int d = 0; d < nv; d++) s += Bp[d] * x[d];
+    sm[ar::UB + t] = s;
+  }
+  RSRX_SYNC();
+  for (int t = lane; t < sd.ncon * 6; t += 32) {
+    const int c = t / 6, e = t - c * 6, k = e >> 1;
+    const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    const float f = (e & 1) ? -cr[cf::MU + k] : cr[cf::MU + k];
+    out[sd.nsr + t] = sm[ar::UB + c * 4] + sm[ar::UB + c * 4 + 1 + k] * f;
+  }
+  RSRX_SYNC();
+}
+
+__device__ void mul_M(const DModel* __restrict__ dm, const float* sm, int lane, const float* x, float* out) {
+  const int nv = dm->nv;
+  if (lane < nv) {
+    float s = 0.f;
+    for (int j = 0; j < nv; j++) s += sm[ar::MM + lane * LD + j] * x[j];
+    out[lane] = s;
+  }
+}
+
+// solver.py::_update_constraint.  Returns the total cost; writes E_ACT, qfrc_constraint.
+__device__ float update_constraint(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, float* gauss_out) {
+  const int nv = dm->nv;
+  const int* sr_type = reinterpret_cast<const int*>(sm + ar::SR_TYPE);
+  float cost = 0.f;
+  for (int r = lane; r < sd.nrow; r += 32) {
+    const float ja = sm[ar::E_JAREF + r], D = sm[ar::E_D + r];
+    float f, act;
+    const int type = r < sd.nsr ? sr_type[r] : 3;
+    if (type == 0) {
+      act = 1.f; f = -D * ja; cost += 0.5f * D * ja * ja;
+    } else if (type == 1) {
+      const float fl = sm[ar::SR_FLOSS + r], rf = fl / D;
+      if (ja <= -rf) { act = 0.f; f = fl; cost += fl * (-0.5f * rf - ja); }
+      else if (ja >= rf) { act = 0.f; f = -fl; cost += fl * (-0.5f * rf + ja); }
+      else { act = 1.f; f = -D * ja; cost += 0.5f * D * ja * ja; }
+    } else {
+      act = ja < 0.f ? 1.f : 0.f;
+      f = act != 0.f ? -D * ja : 0.f;
+      if (act != 0.f) cost += 0.5f * D * ja * ja;
+    }
+    sm[ar::E_ACT + r] = act;
+    sm[ar::E_JV + r] = f;  // E_JV doubles as the force array between line searches
+  }
+  RSRX_SYNC();
+  // contact forces in base-row space: g0 = sum f, g_{1+k} = mu_k (f_{2k} - f_{2k+1})
+  for (int t = lane; t < sd.ncon * 4; t += 32) {
+    const int c = t >> 2, p = t & 3;
+    const float* fr = sm + ar::E_JV + sd.nsr + c * 6;
+    const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    float g;
+    if (p == 0) g = fr[0] + fr[1] + fr[2] + fr[3] + fr[4] + fr[5];
+    else g = cr[cf::MU + p - 1] * (fr[2 * (p - 1)] - fr[2 * (p - 1) + 1]);
+    sm[ar::UB + t] = g;
+  }
+  RSRX_SYNC();
+  float gpart = 0.f;
+  if (lane < nv) {
+    const int d = lane;
+    const int* sr_dofa = reinterpret_cast<const int*>(sm + ar::SR_DOFA);
+    const int* sr_dofb = reinterpret_cast<const int*>(sm + ar::SR_DOFB);
+    float s = 0.f;
+    for (int r = 0; r < sd.nsr; r++) {
+      if (sr_dofa[r] == d) s += sm[ar::SR_CA + r] * sm[ar::E_JV + r];
+      if (sr_dofb[r] == d) s += sm[ar::SR_CB + r] * sm[ar::E_JV + r];
+    }
+    const int nv4 = 4 * nv;
+    for (int c = 0; c < sd.ncon; c++) {
+      const float* B = sm + ar::BROW + c * nv4;
+      const float* g = sm + ar::UB + c * 4;
+      s += B[d] * g[0] + B[nv + d] * g[1] + B[2 * nv + d] * g[2] + B[3 * nv + d] * g[3];
+    }
+    sm[ar::V_QFRCC + d] = s;
+    gpart = (sm[ar::V_MA + d] - sm[ar::V_SMOOTH + d]) * (sm[ar::V_QACC + d] - sm[ar::V_QACCS + d]);
+  }
+  const float gauss = 0.5f * warp_sum(gpart);
+  cost = warp_sum(cost) + gauss;
+  *gauss_out = gauss;
+  RSRX_SYNC();
+  return cost;
+}
+
+// solver.py::_update_gradient (Newton): grad, H = M + J^T diag(D*active) J,
+// Cholesky in place, Mgrad = H^-1 grad
+__device__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd) {
+  const int nv = dm->nv;
+  const int* sr_dofa = reinterpret_cast<const int*>(sm + ar::SR_DOFA);
+  const int* sr_dofb = reinterpret_cast<const int*>(sm + ar::SR_DOFB);
+  if (lane < nv) {
+    const float g = sm[ar::V_MA + lane] - sm[ar::V_SMOOTH + lane] - sm[ar::V_QFRCC + lane];
+    sm[ar::V_GRAD + lane] = g;
+    sm[ar::V_MGRAD + lane] = g;
+  }
+  const int nv4 = 4 * nv;
+  for (int e = lane; e < dm->ntri; e += 32) {
+    const int i = dm->tri_i[e], j = dm->tri_j[e];  // i >= j
+    float h = sm[ar::MM + i * LD + j];
+    for (int r = 0; r < sd.nsr; r++) {
+      if (sm[ar::E_ACT + r] == 0.f) continue;
+      const int a = sr_dofa[r], b = sr_dofb[r];
+      const float ji = (a == i ? sm[ar::SR_CA + r] : 0.f) + (b == i ? sm[ar::SR_CB + r] : 0.f);
+      const float jj = (a == j ? sm[ar::SR_CA + r] : 0.f) + (b == j ? sm[ar::SR_CB + r] : 0.f);
+      if (ji != 0.f && jj != 0.f) h += ji * sm[ar::E_D + r] * jj;
+    }
+    for (int c = 0; c < sd.ncon; c++) {
+      const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+      const unsigned mask = (unsigned)__float_as_int(cr[cf::MASK]);
+      if (!(((mask >> i) & 1u) && ((mask >> j) & 1u))) continue;
+      const float* B = sm + ar::BROW + c * nv4;
+      const float* act = sm + ar::E_ACT + sd.nsr + c * 6;
+      const float D = cr[cf::D];
+      const float b0i = B[i], b0j = B[j];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float mu = cr[cf::MU + k];
+        const float bki = B[(1 + k) * nv + i] * mu, bkj = B[(1 + k) * nv + j] * mu;
+        if (act[2 * k] != 0.f) h += (b0i + bki) * D * (b0j + bkj);
+        if (act[2 * k + 1] != 0.f) h += (b0i - bki) * D * (b0j - bkj);
+      }
+    }
+    sm[ar::HH + i * LD + j] = h;
+  }
+  RSRX_SYNC();
+  warp_cholesky(sm + ar::HH, nv, lane);
+  warp_chol_solve(sm + ar::HH, nv, sm + ar::V_MGRAD, lane);
+}
+
+// _Context.create: qacc <- src, Jaref, Ma, constraint update.  Returns cost.
+__device__ float ctx_create(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, const float* src,
+                            float* gauss) {
+  const int nv = dm->nv;
+  if (lane < nv) sm[ar::V_QACC + lane] = src[lane];
+  RSRX_SYNC();
+  mul_J(dm, sm, lane, sd, sm + ar::V_QACC, sm + ar::E_JAREF);
+  for (int r = lane; r < sd.nrow; r += 32) sm[ar::E_JAREF + r] -= sm[ar::E_AREF + r];
+  mul_M(dm, sm, lane, sm + ar::V_QACC, sm + ar::V_MA);
+  RSRX_SYNC();
+  return update_constraint(dm, sm, lane, sd, gauss);
+}
+
+struct LSPoint { float alpha, cost, d0, d1; };
+
+// _LSPoint.create for up to three alphas in one pass over the rows
+template <int NA>
+__device__ void ls_points(const DModel* __restrict__ dm, const float* sm, int lane, const SolverDims& sd,
+                          const float* alpha, const float* qg, LSPoint* out) {
+  const int* sr_type = reinterpret_cast<const int*>(sm + ar::SR_TYPE);
+  float q0[NA], q1[NA], q2[NA];
+#pragma unroll
+  for (int a = 0; a < NA; a++) { q0[a] = 0.f; q1[a] = 0.f; q2[a] = 0.f; }
+  for (int r = lane; r < sd.nrow; r += 32) {
+    const float ja = sm[ar::E_JAREF + r], jv = sm[ar::E_JV + r], D = sm[ar::E_D + r];
+    const float c0 = 0.5f * ja * ja * D, c1 = jv * ja * D, c2 = 0.5f * jv * jv * D;
+    const int type = r < sd.nsr ? sr_type[r] : 3;
+    float fl = 0.f, rf = 0.f;
+    if (type == 1) { fl = sm[ar::SR_FLOSS + r]; rf = fl / D; }
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const float x = ja + alpha[a] * jv;
+      if (type == 0) { q0[a] += c0; q1[a] += c1; q2[a] += c2; }
+      else if (type == 1) {
+        if (x <= -rf) { q0[a] += fl * (-0.5f * rf - ja); q1[a] += -fl * jv; }
+        else if (x >= rf) { q0[a] += fl * (-0.5f * rf + ja); q1[a] += fl * jv; }
+        else { q0[a] += c0; q1[a] += c1; q2[a] += c2; }
+      } else if (x < 0.f) { q0[a] += c0; q1[a] += c1; q2[a] += c2; }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    const float t0 = warp_sum(q0[a]) + qg[0], t1 = warp_sum(q1[a]) + qg[1], t2 = warp_sum(q2[a]) + qg[2];
+    out[a].alpha = alpha[a];
+    out[a].cost = alpha[a] * alpha[a] * t2 + alpha[a] * t1 + t0;
+    out[a].d0 = 2.f * alpha[a] * t2 + t1;
+    out[a].d1 = 2.f * t2 + (t2 == 0.f ? MJ_MINVAL : 0.f);
+  }
+}
+
+// solver.py::_linesearch
+__device__ void linesearch(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, float gauss) {
+  const int nv = dm->nv;
+  float s2 = 0.f, g1 = 0.f, g2 = 0.f;
+  mul_M(dm, sm, lane, sm + ar::V_SEARCH, sm + ar::V_MV);
+  RSRX_SYNC();
+  if (lane < nv) {
+    const float s = sm[ar::V_SEARCH + lane];
+    s2 = s * s;
+    g1 = s * sm[ar::V_MA + lane] - s * sm[ar::V_SMOOTH + lane];
+    g2 = s * sm[ar::V_MV + lane];
+  }
+  const float smag = sqrtf(warp_sum(s2)) * dm->meaninertia * (float)(nv > 1 ? nv : 1);
+  const float gtol = dm->tolerance * dm->ls_tolerance * smag;
+  const float qg[3] = {gauss, warp_sum(g1), 0.5f * warp_sum(g2)};
+  mul_J(dm, sm, lane, sd, sm + ar::V_SEARCH, sm + ar::E_JV);
+  LSPoint p0, lo, hi;
+  {
+    float a0 = 0.f;
+    ls_points<1>(dm, sm, lane, sd, &a0, qg, &p0);
+    float a1 = p0.alpha - p0.d0 / p0.d1;
+    LSPoint lo0;
+    ls_points<1>(dm, sm, lane, sd, &a1, qg, &lo0);
+    const bool lesser = lo0.d0 < p0.d0;
+    hi = lesser ? p0 : lo0;
+    lo = lesser ? lo0 : p0;
+  }
+  bool swap = true;
+  int it = 0;
+  for (;;) {
+    bool done = it >= dm->ls_iterations;
+    done |= !swap;
+    done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+    done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+    if (done) break;
+    float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+    LSPoint pt[3];
+    ls_points<3>(dm, sm, lane, sd, al, qg, pt);
+    const LSPoint &lo_next = pt[0], &hi_next = pt[1], &mid = pt[2];
+    const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+    if (swap_lo_next) lo = lo_next;
+    const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+    if (swap_lo_mid) lo = mid;
+    const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+    if (swap_hi_next) hi = hi_next;
+    const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+    if (swap_hi_mid) hi = mid;
+    swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+    it++;
+  }
+  const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+  const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+  if (improved) {
+    if (lane < nv) {
+      sm[ar::V_QACC + lane] += sm[ar::V_SEARCH + lane] * alpha;
+      sm[ar::V_MA + lane] += sm[ar::V_MV + lane] * alpha;
+    }
+    for (int r = lane; r < sd.nrow; r += 32) sm[ar::E_JAREF + r] += sm[ar::E_JV + r] * alpha;
+  }
+  RSRX_SYNC();
+}
+
+// solver.py::solve.  Returns the number of Newton iterations.
+__device__ int solve(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, int* status) {
+  const int nv = dm->nv;
+  if (sd.nrow == 0) {
+    if (lane < nv) { sm[ar::V_QACC + lane] = sm[ar::V_QACCS + lane]; sm[ar::V_QFRCC + lane] = 0.f; }
+    RSRX_SYNC();
+    return 0;
+  }
+  float gauss;
+  const float cw = ctx_create(dm, sm, lane, sd, sm + ar::WARM, &gauss);
+  const float cs = ctx_create(dm, sm, lane, sd, sm + ar::V_QACCS, &gauss);
+  float cost = cs;
+  if (cw < cs) cost = ctx_create(dm, sm, lane, sd, sm + ar::WARM, &gauss);
+  float prev_cost = INFINITY;
+  update_gradient(dm, sm, lane, sd);
+  if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
+  RSRX_SYNC();
+  const float scale = 1.f / (dm->meaninertia * (float)(nv > 1 ? nv : 1));
+  int niter = 0;
+  for (;;) {
+    const float improvement = (prev_cost - cost) * scale;
+    float g = 0.f;
+    if (lane < nv) g = sm[ar::V_GRAD + lane] * sm[ar::V_GRAD + lane];
+    const float gradient = sqrtf(warp_sum(g)) * scale;
+    bool done = niter >= dm->iterations;
+    done |= improvement < dm->tolerance;
+    done |= gradient < dm->tolerance;
+    if (done) break;
+    linesearch(dm, sm, lane, sd, gauss);
+    prev_cost = cost;
+    cost = update_constraint(dm, sm, lane, sd, &gauss);
+    update_gradient(dm, sm, lane, sd);
+    if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
+    RSRX_SYNC();
+    niter++;
+  }
+  if (niter >= dm->iterations) *status |= RSRX_STATUS_SOLVER_CAP;
+  if (lane < nv) sm[ar::WARM + lane] = sm[ar::V_QACC + lane];
+  RSRX_SYNC();
+  return niter;
+}
+
+// forward.py::forward.  Returns niter; fills dims.
+__device__ int forward(const DModel* __restrict__ dm, float* sm, int lane, SolverDims* sd, int* status) {
+  kinematics(dm, sm, lane);
+  com_pos(dm, sm, lane);
+  crb_and_factor(dm, sm, lane);
+  const int ncon = collision(dm, sm, lane, status);
+  const int nsr = make_constraint(dm, sm, lane, ncon);
+  sd->nsr = nsr; sd->ncon = ncon; sd->nrow = nsr + 6 * ncon;
+  velocity_and_forces(dm, sm, lane);
+  return solve(dm, sm, lane, *sd, status);
+}
+
+// forward.py::implicit + _advance (implicitfast; only dof damping contributes to qDeriv)
+__device__ void implicit_advance(const DModel* __restrict__ dm, float* sm, int lane) {
+  const int nv = dm->nv;
+  const float dt = dm->timestep;
+  for (int e = lane; e < nv * LD; e += 32) sm[ar::HH + e] = sm[ar::MM + e];
+  RSRX_SYNC();
+  if (lane < nv) {
+    sm[ar::HH + lane * LD + lane] += dt * sm[ar::DAMP + lane];
+    sm[ar::V_TMP + lane] = sm[ar::V_SMOOTH + lane] + sm[ar::V_QFRCC + lane];
+  }
+  RSRX_SYNC();
+  warp_cholesky(sm + ar::HH, nv, lane);
+  warp_chol_solve(sm + ar::HH, nv, sm + ar::V_TMP, lane);
+  if (lane < nv) sm[ar::QVEL + lane] += sm[ar::V_TMP + lane] * dt;
+  RSRX_SYNC();
+  if (lane < dm->njnt) {
+    const int j = lane, qa = dm->jnt_qposadr[j], d = dm->jnt_dofadr[j];
+    if (dm->jnt_type[j] == RSRX_JNT_FREE) {
+      for (int i = 0; i < 3; i++) sm[ar::QPOS + qa + i] += dt * sm[ar::QVEL + d + i];
+      float v[3] = {sm[ar::QVEL + d + 3], sm[ar::QVEL + d + 4], sm[ar::QVEL + d + 5]};
+      const float nrm = sqrtf(dot3(v, v));
+      if (nrm > 0.f) { v[0] /= nrm; v[1] /= nrm; v[2] /= nrm; }
+      float s, c;
+      sincosf(dt * nrm * 0.5f, &s, &c);
+      float qr[4] = {c, v[0] * s, v[1] * s, v[2] * s}, q2[4];
+      float q0[4] = {sm[ar::QPOS + qa + 3], sm[ar::QPOS + qa + 4], sm[ar::QPOS + qa + 5], sm[ar::QPOS + qa + 6]};
+      quat_mul(q2, q0, qr);
+      normalize4(q2);
+      for (int i = 0; i < 4; i++) sm[ar::QPOS + qa + 3 + i] = q2[i];
+    } else {
+      sm[ar::QPOS + qa] += dt * sm[ar::QVEL + d];
+    }
+  }
+  RSRX_SYNC();
+}
+
+}  // namespace rsrx
