@@ -1305,8 +1305,10 @@ int oracle_env_reset(const rsrx_model_blob* m, const rsrx_env_cfg* cfg, const do
 static void env_step_w(work* w, const rsrx_env_cfg* cfg, orc_env_state* s, const double* action_in) {
   const rsrx_model_blob* m = w->m;
   int kind = cfg->env_kind, nu = m->nu;
+  /* episode_length <= 0: the bare (unwrapped) env, as rsr_pipeline.env_params_tuning steps it */
+  const int wrapped = cfg->episode_length > 0;
   /* AutoReset pre: steps <- 0 where done; done <- 0 */
-  if (s->done != 0) s->steps = 0;
+  if (wrapped && s->done != 0) s->steps = 0;
   s->done = 0;
   /* ---- pre-physics action shaping */
   orc_data* d0 = &s->d;
@@ -1429,11 +1431,11 @@ static void env_step_w(work* w, const rsrx_env_cfg* cfg, orc_env_state* s, const
   s->reward = reward;
   /* ---- EpisodeWrapper */
   s->steps += cfg->action_repeat;
-  if (s->steps >= cfg->episode_length) { s->truncation = 1 - done; done = 1; }
+  if (wrapped && s->steps >= cfg->episode_length) { s->truncation = 1 - done; done = 1; }
   else s->truncation = 0;
   s->done = done;
   /* ---- AutoReset post: pipeline_state and obs only */
-  if (done != 0) {
+  if (wrapped && done != 0) {
     s->d = s->first;
     memcpy(s->obs, s->first_obs, sizeof(s->obs));
   }

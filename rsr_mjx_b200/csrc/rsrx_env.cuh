@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(32) step_kernel(const DModel* __restrict__ dm,
   // ---- AutoReset pre + action shaping (lane 0; reads the *lagged* kinematics of the row)
   if (lane == 0) {
     float steps = info[RSRX_INFO_STEPS];
-    if (st.done[e] != 0.f) steps = 0.f;
+    if (dm->episode_length > 0 && st.done[e] != 0.f) steps = 0.f;
     info[RSRX_INFO_STEPS] = steps;
     float act[NU];
     const int nu = dm->nu;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(32) step_kernel(const DModel* __restrict__ dm,
     // EpisodeWrapper
     float steps = info[RSRX_INFO_STEPS] + (float)dm->action_repeat;
     float trunc = 0.f;
-    if (steps >= (float)dm->episode_length) { trunc = 1.f - done; done = 1.f; }
+    if (dm->episode_length > 0 && steps >= (float)dm->episode_length) { trunc = 1.f - done; done = 1.f; }
     info[RSRX_INFO_STEPS] = steps;
     info[RSRX_INFO_TRUNCATION] = trunc;
     st.reward[e] = reward;
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(32) step_kernel(const DModel* __restrict__ dm,
   status = __reduce_or_sync(0xffffffffu, status);
   if (lane == 0 && status) st.status[e] |= status;
   RSRX_SYNC();
-  // ---- AutoReset post: pipeline_state and obs only
-  if (done != 0.f) {
+  // ---- AutoReset post: pipeline_state and obs only (episode_length <= 0: bare env, no wrappers)
+  if (done != 0.f && dm->episode_length > 0) {
     const float* frow = st.first_data + (size_t)e * L.data_stride;
     for (int i = lane; i < L.data_stride; i += 32) row[i] = frow[i];
     for (int i = lane; i < OBS_STRIDE; i += 32) st.obs[(size_t)e * OBS_STRIDE + i] = st.first_obs[(size_t)e * OBS_STRIDE + i];

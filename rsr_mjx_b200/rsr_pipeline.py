@@ -1,0 +1,167 @@
+"""RSR pipeline entry points with the reference's signatures
+(RSR/rsr_pipeline.py): `env_params_tuning`, `build_policy_rsr_data`,
+`policy_params_training`.
+
+env_params_tuning — the reference tunes one scalar (the cube geom's friction,
+written to all three coefficients of the LAST geom, rsr_pipeline.py:125-136) by
+Adam on `grad(loss_fn)` through `env.step`, one tiny device dispatch per sample
+(15 samples x 1000 Adam steps).  Here the same loss
+    L(p) = sum_i | w . (obs_pred_i(p) - obs_true_i) |       (rsr_pipeline.py:119-123,146-162)
+is evaluated for a whole grid of candidate p in ONE batched launch (P x S envs,
+one bare-env step each, per-env geom_friction) and the interval is zoomed around
+the minimiser — a forward sweep instead of reverse-mode AD (which MJX's
+while_loop solver does not support anyway).
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, prng, rsr_loss
+from .envs import AirbotPlayBase
+
+# compute_error weights, rsr_pipeline.py:120
+ERROR_WEIGHTS = (1, 1, 1, 1, 1, 1, 10, 10, 10, 0, 0, 0, 10, 10, 10, 10, 10, 0, 0, 0, 0, 0, 0)
+
+
+def _scalar(x) -> float:
+    if isinstance(x, dict):
+        if len(x) != 1:
+            raise ValueError("env_params_tuning sweeps exactly one scalar parameter")
+        x = next(iter(x.values()))
+    return float(np.asarray(x if not torch.is_tensor(x) else x.cpu()).reshape(-1)[0])
+
+
+class FrictionSweep:
+    """Batched evaluation of the env_params_tuning loss for many friction values."""
+
+    def __init__(self, kind: str, obs, actions, next_obs_true, num_params: int = 64, device="cuda", **env_kwargs):
+        obs = np.asarray(obs, np.float32)
+        actions = np.asarray(actions, np.float32)
+        next_obs_true = np.asarray(next_obs_true, np.float32)
+        if obs.ndim != 2 or actions.ndim != 2 or next_obs_true.shape != obs.shape or actions.shape[0] != obs.shape[0]:
+            raise ValueError("obs[S,23], actions[S,5], next_obs_true[S,23] expected")
+        self.S, self.P = obs.shape[0], int(num_params)
+        N = self.S * self.P
+        # episode_length=0 -> the bare env, as the reference steps `init_env` without wrappers
+        self.env = AirbotPlayBase(kind, num_envs=N, episode_length=0, device=device, **env_kwargs)
+        env, m, L = self.env, self.env.model, self.env.layout
+        one = AirbotPlayBase(kind, num_envs=1, episode_length=0, device=device, **env_kwargs)
+        # obs2state (rsr_pipeline.py:75-98): reset(PRNGKey(0)), one step with zero action; per sample overwrite
+        # joint angles, cube position in qpos and the (stale) xpos[cube]; info/metrics come from state_1.
+        s0 = one.reset(prng.PRNGKey(0)[None])
+        row0 = s0._buf["data"].clone()
+        s1 = one.step(s0, torch.zeros(1, m.nu, device=device))
+        info1 = s1._buf["info"].clone()
+        data = row0.repeat(N, 1)
+        o = torch.from_numpy(obs).to(device).repeat(self.P, 1)  # env index = p * S + i
+        jid = torch.as_tensor(env.joint_id, device=device, dtype=torch.long)
+        data[:, L.qpos + jid] = o[:, 0:6]
+        cq = env._box_qposadr  # the reference writes qpos[cube_id+2 : cube_id+5] = 15:18 (same address)
+        data[:, L.qpos + cq:L.qpos + cq + 3] = o[:, 12:15]
+        data[:, L.xpos + 3 * env.cube_id:L.xpos + 3 * env.cube_id + 3] = o[:, 12:15]
+        self._data0 = data
+        self._info0 = info1.repeat(N, 1)
+        self._actions = torch.from_numpy(actions).to(device).repeat(self.P, 1).contiguous()
+        self._true = torch.from_numpy(next_obs_true).to(device).repeat(self.P, 1)
+        self._w = torch.tensor(ERROR_WEIGHTS, dtype=torch.float32, device=device)
+        self._buf = env._alloc()
+        self._gf = torch.from_numpy(m.geom_friction.astype(np.float32)).to(device).repeat(N, 1, 1).contiguous()
+
+    def loss(self, params: torch.Tensor) -> torch.Tensor:
+        """params[P] -> loss[P] (one launch)."""
+        env = self.env
+        p = torch.as_tensor(params, dtype=torch.float32, device=self._gf.device).reshape(self.P)
+        self._gf[:, -1, :] = p.repeat_interleave(self.S)[:, None]
+        env.set_per_env(geom_friction=self._gf)
+        b = self._buf
+        b["data"].copy_(self._data0)
+        b["info"].copy_(self._info0)
+        b["done"].zero_()
+        env.step_raw(b, self._actions.data_ptr())
+        err = (b["obs"][:, :23] - self._true) @ self._w
+        return err.abs().reshape(self.P, self.S).sum(1)
+
+
+def env_params_tuning(init_env: AirbotPlayBase, num_steps: int, init_env_params, env_params_min, env_params_max,
+                      obs: Any, actions: Any, next_obs_true: Any, log_path: Optional[str] = None,
+                      num_params: int = 64, zoom: float = 0.25):
+    """Tune the cube friction to reproduce `next_obs_true` (reference signature,
+    rsr_pipeline.py:49-56).  `num_steps` sweeps of `num_params` candidates each; every
+    sweep keeps the best candidate and shrinks the interval to `zoom` of its width.
+
+    Returns (tuned_env_params, train_log) like the reference."""
+    lo, hi = _scalar(env_params_min), _scalar(env_params_max)
+    if not lo < hi:
+        raise ValueError("env_params_min must be below env_params_max")
+    p0 = min(max(_scalar(init_env_params), lo), hi)
+    sweep = FrictionSweep(init_env.kind, obs, actions, next_obs_true, num_params=num_params, device=init_env.device,
+                          **init_env._params)
+    log: Dict[str, list] = {"time_cost": [], "loss": [], "params": []}
+    best_p, best_l = p0, float("inf")
+    a, b = lo, hi
+    for i in range(max(int(num_steps), 1)):
+        t0 = time.time()
+        cand = torch.linspace(a, b, sweep.P, device=init_env.device)
+        cand[0] = best_p if i else p0  # always re-evaluate the incumbent
+        losses = sweep.loss(cand)
+        k = int(torch.argmin(losses))
+        if float(losses[k]) <= best_l:
+            best_p, best_l = float(cand[k]), float(losses[k])
+        width = (b - a) * zoom
+        a, b = max(lo, best_p - width / 2), min(hi, best_p + width / 2)
+        dt = time.time() - t0
+        line = f"step {i}: {dt:.2f}s. params = {best_p}. loss = {best_l}."
+        log["time_cost"].append(dt)
+        log["loss"].append(best_l)
+        log["params"].append(best_p)
+        if log_path:
+            with open(log_path, "a") as f:
+                f.write(line + "\n")
+    tuned = {k: best_p for k in init_env_params} if isinstance(init_env_params, dict) else best_p
+    return tuned, log
+
+
+def build_policy_rsr_data(past_states: Any, past_actions: Any, past_next_states_real: Any, past_next_states_sim: Any,
+                          current_next_states_sim: Any, num_samples: int = 10, min_val: float = -3.0,
+                          max_val: float = 3.0, bandwidth: float = 0.1, seed: int = 0, device="cuda") -> rsr_loss.RSRData:
+    """Builds the fixed RSR statistics shared by PPO and SAC (rsr_pipeline.py:209-271)."""
+    arrays = tuple(torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v, dtype=torch.float32)
+                   for v in (past_states, past_actions, past_next_states_real, past_next_states_sim,
+                             current_next_states_sim))
+    past_states, past_actions, past_next_states_real, past_next_states_sim, current_next_states_sim = arrays
+    if any(v.ndim != 2 for v in arrays):
+        raise ValueError(f'all RSR datasets must be rank 2, got {tuple(tuple(v.shape) for v in arrays)}')
+    counts = {v.shape[0] for v in arrays}
+    if len(counts) != 1:
+        raise ValueError(f'RSR datasets must have equal lengths, got {tuple(tuple(v.shape) for v in arrays)}')
+    if not counts or next(iter(counts)) == 0:
+        raise ValueError('RSR datasets must not be empty')
+    if past_next_states_real.shape[1] != past_states.shape[1]:
+        raise ValueError('real next-state width must match state width')
+    if past_next_states_sim.shape[1] != past_states.shape[1]:
+        raise ValueError('previous sim next-state width must match state width')
+    if current_next_states_sim.shape[1] != past_states.shape[1]:
+        raise ValueError('current sim next-state width must match state width')
+    real = torch.hstack([past_states, past_actions, past_next_states_real])
+    prev = torch.hstack([past_states, past_actions, past_next_states_sim])
+    cur = torch.hstack([past_states, past_actions, current_next_states_sim])
+    return rsr_loss.build_rsr_data(real, prev, cur, num_samples=num_samples, min_value=min_val, max_value=max_val,
+                                   bandwidth=bandwidth, seed=seed, device=device)
+
+
+def policy_params_training(env, *args, algorithm: str = "ppo", **kwargs):
+    """PPO/SAC policy training with the RSR term (rsr_pipeline.py:274-436).
+
+    The trainer is a *caller* of the hot path; the
+    torch PPO loop lives in rsr_mjx_b200.ppo when present."""
+    try:
+        from . import ppo
+    except ImportError as e:  # pragma: no cover
+        raise NotImplementedError("policy_params_training: the torch PPO/SAC trainers are SURVEY.md §8f 'next' rows") from e
+    if algorithm.lower() != "ppo":
+        raise NotImplementedError("only algorithm='ppo' is available (SAC: SURVEY.md §8f N3)")
+    return ppo.train(env, *args, **kwargs)

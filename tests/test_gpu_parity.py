@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via rsr_mjx_b200.envs)
+against the CPU oracle on the same seeded inputs, against the committed golden
+fixtures, and size-independent properties at BASELINE sizes.
+
+Tolerances (north star: 1e-4 relative in fp32, identical done/reset masks):
+  qpos / obs / reward / info : |gpu - oracle_f32| <= 1e-4 * max(1, |ref|_inf)   every step, every env
+  qvel                       : same norm, <= 1e-4 at the 99th percentile and <= 2e-3 worst case
+                               (the float32 Newton solver stops at a noise-level iterate; the oracle's own
+                               f32-vs-f64 spread is of the same size — tests/test_oracle_physics.py)
+PARITY UNPINNED w.r.t. real MJX: the oracle is our restatement.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity_utils as P
+from oracle import oracle as O
+from rsr_mjx_b200 import _lib, airbot_spec as A, domain_randomize as DR, prng
+from rsr_mjx_b200.envs import AirbotPlayBase
+from rsr_mjx_b200.model import pack_model
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KINDS = ["sf", "cube", "T"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(oracle_built):
+    _lib.build()
+    return True
+
+
+def _mk(kind, N, seed=0, episode_length=1200, **kw):
+    env = AirbotPlayBase(kind, num_envs=N, episode_length=episode_length, **kw)
+    keys = prng.split(prng.PRNGKey(seed), N)
+    q, v, c = A.sample_reset(env.model, kind, keys)
+    return env, keys, (q, v, c)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reset_parity(kind):
+    N = 16
+    env, keys, (q, v, c) = _mk(kind, N)
+    st = env.reset(keys)
+    torch.cuda.synchronize()
+    b = P.buffers_to_numpy(st)
+    assert (b["status"] == 0).all() and (b["done"] == 0).all() and (b["reward"] == 0).all()
+    blob, L, m = pack_model(env.model), env.layout, env.model
+    for e in range(N):
+        so = O.env_reset(blob, env.cfg, q[e], v[e], c[e], precision="f32")
+        row = P.oracle_row(env, so.d)
+        for off, n, tol in ((L.qpos, m.nq, 1e-6), (L.qvel, m.nv, 1e-6), (L.ctrl, m.nu, 1e-6), (L.xpos, 3 * m.nbody, 1e-6),
+                            (L.xquat, 4 * m.nbody, 1e-6), (L.site_xpos, 3 * m.nsite, 1e-6), (L.geom_xpos, 3 * m.ngeom, 1e-6),
+                            (L.qacc_warmstart, m.nv, 1e-3)):
+            assert P.rel_err(b["data"][e, off:off + n], row[off:off + n]) <= tol
+        assert P.rel_err(b["obs"][e], np.array(so.obs)) <= 1e-6
+        assert P.rel_err(b["info"][e], P.oracle_info(so)) <= 1e-6
+        np.testing.assert_array_equal(b["first_data"][e], b["data"][e])
+        np.testing.assert_array_equal(b["first_obs"][e], b["obs"][e])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_forward_internals(kind):
+    """mass matrix, bias forces, unconstrained and constrained accelerations, contact set"""
+    N = 12
+    env, keys, ic = _mk(kind, N, seed=3)
+    st = env.reset_from(*ic)
+    act = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (N, 5)).astype(np.float32)).cuda()
+    for _ in range(6):
+        env.step(st, act)
+    torch.cuda.synchronize()
+    b = P.buffers_to_numpy(st)
+    dump = env.physics_step_debug(st._buf["data"].clone()).cpu().numpy()
+    blob, nv = pack_model(env.model), env.model.nv
+    for e in range(N):
+        so = P.gpu_to_oracle_states(env, {k: v[e:e + 1] for k, v in b.items()})[0]
+        ins = O.inspect(blob, so.d, precision="f32")
+        assert P.rel_err(dump[e, :nv * nv].reshape(nv, nv), ins["M"]) <= 1e-5
+        assert P.rel_err(dump[e, 400:400 + nv], np.array(so.d.qfrc_bias)[:nv]) <= 1e-4
+        assert P.rel_err(dump[e, 420:420 + nv], np.array(so.d.qacc_smooth)[:nv]) <= 1e-3
+        assert P.rel_err(dump[e, 440:440 + nv], np.array(so.d.qacc)[:nv]) <= 2e-3
+        assert int(dump[e, 480]) == so.d.ncon and int(dump[e, 481]) == so.d.nefc
+        # same contacts, same order
+        nc = so.d.ncon
+        geoms = np.array([c["geom1"] * 64 + c["geom2"] for c in ins["contacts"]])
+        np.testing.assert_array_equal(dump[e, 483 + 32 + 96:483 + 32 + 96 + nc].astype(int), geoms)
+        dist = np.array([c["dist"] for c in ins["contacts"]])
+        np.testing.assert_allclose(dump[e, 483:483 + nc], dist, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_step_parity_teacher_forced(kind):
+    N, T, ncheck = 16, 40, 16
+    env, keys, ic = _mk(kind, N, seed=1)
+    st = env.reset_from(*ic)
+    blob, L, m = pack_model(env.model), env.layout, env.model
+    rng = np.random.default_rng(2)
+    e_q, e_v, e_o, e_r = [], [], [], []
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, m.nu)).astype(np.float32)
+        b0 = P.buffers_to_numpy(st)
+        env.step(st, torch.from_numpy(a).cuda())
+        torch.cuda.synchronize()
+        b1 = P.buffers_to_numpy(st)
+        for e in range(ncheck):
+            so = P.gpu_to_oracle_states(env, {k: v[e:e + 1] for k, v in b0.items()})[0]
+            O.env_step(blob, env.cfg, so, a[e], precision="f32")
+            row = P.oracle_row(env, so.d)
+            e_q.append(P.rel_err(b1["data"][e, L.qpos:L.qpos + m.nq], row[L.qpos:L.qpos + m.nq]))
+            e_v.append(P.rel_err(b1["data"][e, L.qvel:L.qvel + m.nv], row[L.qvel:L.qvel + m.nv]))
+            e_o.append(P.rel_err(b1["obs"][e], np.array(so.obs)))
+            e_r.append(abs(b1["reward"][e] - so.reward) / max(1.0, abs(so.reward)))
+            assert b1["done"][e] == so.done
+            assert P.rel_err(b1["info"][e], P.oracle_info(so)) <= 1e-4
+            assert P.rel_err(b1["data"][e, L.ctrl:L.ctrl + m.nu], row[L.ctrl:L.ctrl + m.nu]) <= 1e-5
+            assert P.rel_err(b1["metrics"][e, :5], np.array(so.metrics)) <= 1e-4
+    assert (P.buffers_to_numpy(st)["status"] == 0).all()
+    assert max(e_q) <= 1e-4 and max(e_o) <= 1e-4 and max(e_r) <= 1e-4
+    assert np.percentile(e_v, 99) <= 1e-4 and max(e_v) <= 2e-3
+
+
+@pytest.mark.parametrize("name", ["sf", "cube", "T", "sf_short"])
+def test_golden_free_running(name):
+    """CUDA (float32) free-running against the float64 golden trajectories."""
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    kind = name.split("_")[0]
+    N, T = g["qpos0"].shape[0], g["actions"].shape[0]
+    env = AirbotPlayBase(kind, num_envs=N, episode_length=int(g["episode_length"]))
+    st = env.reset(g["keys"])
+    torch.cuda.synchronize()
+    assert P.rel_err(st.obs.cpu().numpy(), g["reset_obs"][:, :env.observation_size]) <= 1e-5
+    L, m = env.layout, env.model
+    for t in range(T):
+        env.step(st, torch.from_numpy(g["actions"][t]).cuda())
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(st.done.cpu().numpy(), g["done"][t])
+        np.testing.assert_array_equal(st.info["steps"].cpu().numpy(), g["steps"][t])
+        np.testing.assert_array_equal(st.info["truncation"].cpu().numpy(), g["truncation"][t])
+        if t < 5 or name == "sf_short":  # float32 roundoff grows along a free-running contact-rich rollout
+            assert P.rel_err(st.pipeline_state.qpos.cpu().numpy(), g["qpos"][t]) <= 1e-4
+            assert P.rel_err(st.obs.cpu().numpy(), g["obs"][t][:, :env.observation_size]) <= 1e-4
+            assert P.rel_err(st.reward.cpu().numpy(), g["reward"][t]) <= 1e-4
+    # it stays close over the whole fixture
+    assert P.rel_err(st.pipeline_state.qpos.cpu().numpy(), g["qpos"][T - 1]) <= 5e-2
+
+
+def test_domain_randomization_parity():
+    g = np.load(os.path.join(GOLD, "cube_dr.npz"))
+    N = g["qpos0"].shape[0]
+    env = AirbotPlayBase("cube", num_envs=N, episode_length=1200, randomization_fn=DR.domain_randomize,
+                         randomization_rng=prng.split(prng.PRNGKey(45 + 7), N))
+    per = {k: env._per_env_tensors[k].cpu().numpy() for k in env._per_env_tensors}
+    for k in per:
+        np.testing.assert_array_equal(per[k], g["dr_" + k])
+    st = env.reset(g["keys"])
+    m, L = env.model, env.layout
+    blobs = [pack_model(m.replace_arrays(**{k: v[i] for k, v in per.items()})) for i in range(N)]
+    for t in range(12):
+        b0 = P.buffers_to_numpy(st)
+        env.step(st, torch.from_numpy(g["actions"][t]).cuda())
+        torch.cuda.synchronize()
+        b1 = P.buffers_to_numpy(st)
+        for e in range(N):
+            so = P.gpu_to_oracle_states(env, {k: v[e:e + 1] for k, v in b0.items()})[0]
+            O.env_step(blobs[e], env.cfg, so, g["actions"][t, e], precision="f32")
+            row = P.oracle_row(env, so.d)
+            assert P.rel_err(b1["data"][e, L.qpos:L.qpos + m.nq], row[L.qpos:L.qpos + m.nq]) <= 1e-4
+            assert P.rel_err(b1["obs"][e], np.array(so.obs)) <= 1e-4
+    # and the randomisation matters: env 0 with nominal parameters ends elsewhere
+    env_nom = AirbotPlayBase("cube", num_envs=N, episode_length=1200)
+    st2 = env_nom.reset(g["keys"])
+    for t in range(12):
+        env_nom.step(st2, torch.from_numpy(g["actions"][t]).cuda())
+    assert (st2.pipeline_state.qvel - st.pipeline_state.qvel).abs().max().item() > 1e-4
+
+
+def test_autoreset_and_episode_semantics():
+    """wrapper.py:117-138 + brax EpisodeWrapper: restore pipeline_state/obs only, info persists"""
+    N = 8
+    env, keys, ic = _mk("sf", N, seed=5, episode_length=3)
+    st = env.reset(keys)
+    first = P.buffers_to_numpy(st)
+    a = torch.full((N, 5), 0.5, device="cuda")
+    for t in range(1, 8):
+        env.step(st, a)
+        torch.cuda.synchronize()
+        b = P.buffers_to_numpy(st)
+        steps = b["info"][:, _lib.INFO["STEPS"]]
+        if t % 3 == 0:
+            assert (b["done"] == 1).all() and (b["info"][:, _lib.INFO["TRUNCATION"]] == 1).all() and (steps == 3).all()
+            np.testing.assert_array_equal(b["data"], first["data"])
+            np.testing.assert_array_equal(b["obs"], first["obs"])
+            # info is NOT restored: new_cube_pos moved away from its reset constant
+            assert np.abs(b["info"][:, _lib.INFO["NEWPOS"]] - np.float32(0.37342)).min() > 1e-4
+        else:
+            assert (b["done"] == 0).all() and (steps == (t % 3)).all()
+    np.testing.assert_array_equal(b["first_data"], first["first_data"])
+
+
+@pytest.mark.parametrize("kind,N", [("sf", 8192), ("T", 8192)])
+def test_full_size_properties(kind, N):
+    """BASELINE sizes: finite, no status flags, deterministic, env i independent of the batch it runs in"""
+    env, keys, ic = _mk(kind, N, seed=11)
+    acts = torch.rand(12, N, 5, device="cuda", generator=torch.Generator("cuda").manual_seed(0)) * 2 - 1
+
+    def run(e, ic_, n):
+        s = e.reset_from(*[x[:n] for x in ic_])
+        for t in range(acts.shape[0]):
+            e.step(s, acts[t, :n].contiguous())
+        torch.cuda.synchronize()
+        return s
+
+    s1 = run(env, ic, N)
+    assert int(s1._buf["status"].max()) == 0
+    for k in ("data", "obs", "reward", "info"):
+        assert torch.isfinite(s1._buf[k]).all()
+    d1 = {k: v.clone() for k, v in s1._buf.items()}
+    s2 = run(env, ic, N)
+    for k in d1:
+        assert torch.equal(d1[k], s2._buf[k]), k  # bitwise deterministic
+    small = AirbotPlayBase(kind, num_envs=64, episode_length=1200)
+    s3 = run(small, ic, 64)
+    assert torch.equal(s3._buf["data"], d1["data"][:64]) and torch.equal(s3._buf["obs"], d1["obs"][:64])
+    # sanity of the physics at scale: the pushed object stays on the table top
+    z = s1.pipeline_state.xpos[:, env.cfg.cube_body, 2]
+    assert (z > 0.78).all() and (z < 0.86).all()
+
+
+def test_api_shape_errors():
+    env, keys, ic = _mk("sf", 4)
+    st = env.reset(keys)
+    with pytest.raises(ValueError):
+        env.step(st, torch.zeros(3, 5, device="cuda"))
+    with pytest.raises(ValueError):
+        env.reset(keys[:2])
+    with pytest.raises(ValueError):
+        env.set_per_env(body_mass=torch.zeros(4, 3))
+    assert env.observation_size == 23 and env.action_size == 5 and env.dt == pytest.approx(0.01)
+    assert st.pipeline_state.qpos.shape == (4, 22) and st.pipeline_state.xpos.shape == (4, 14, 3)
+    assert set(st.metrics) == {"push_reward", "ctrl_cost", "siet_to_box_reward"}
+    assert {"target_pos", "new_cube_pos", "site_pos", "cube_pos", "last_action", "steps", "truncation",
+            "first_pipeline_state", "first_obs"} <= set(st.info)
+
+
+def test_friction_sweep_matches_oracle_per_param():
+    """env_params_tuning as a batched sweep (rsr_pipeline.py:49-206): every (param, sample) env of the one
+    launch equals an independent bare-env oracle step with geom_friction[-1,:] = param."""
+    from rsr_mjx_b200 import rsr_pipeline as RP
+    kind, S, Pn = "sf", 5, 8
+    rng = np.random.default_rng(0)
+    m = A.load_model(kind)
+    cfg = A.make_env_cfg(m, kind, episode_length=0)
+    # synthetic "real" transitions: states near the reset pose with the fingers at the cube
+    q, v, c = A.sample_reset(m, kind, prng.PRNGKey(0)[None])
+    s0 = O.env_reset(pack_model(m), cfg, q[0], v[0], c[0], precision="f32")
+    obs = np.tile(np.array(s0.obs)[:23], (S, 1)).astype(np.float32)
+    obs[:, 0:6] += rng.uniform(-0.02, 0.02, (S, 6)).astype(np.float32)
+    obs[:, 12:14] += rng.uniform(-0.01, 0.01, (S, 2)).astype(np.float32)
+    actions = rng.uniform(-1, 1, (S, 5)).astype(np.float32)
+    true = obs + rng.normal(0, 1e-3, obs.shape).astype(np.float32)
+    sweep = RP.FrictionSweep(kind, obs, actions, true, num_params=Pn)
+    params = torch.linspace(0.1, 3.0, Pn)
+    loss = sweep.loss(params).cpu().numpy()
+    torch.cuda.synchronize()
+    assert int(sweep._buf["status"].max()) == 0
+    # oracle: same construction (obs2state), one bare step per (param, sample)
+    one = AirbotPlayBase(kind, num_envs=1, episode_length=0)
+    st0 = one.reset(prng.PRNGKey(0)[None])
+    b0 = P.buffers_to_numpy(st0)
+    st1 = one.step(st0, torch.zeros(1, 5, device="cuda"))
+    torch.cuda.synchronize()
+    b1 = P.buffers_to_numpy(st1)
+    w = np.array(RP.ERROR_WEIGHTS, np.float64)
+    for pi in (0, 3, 7):
+        gf = m.geom_friction.copy()
+        gf[-1, :] = np.float32(params[pi].item())
+        blob = pack_model(m.replace_arrays(geom_friction=gf))
+        tot = 0.0
+        for i in range(S):
+            so = P.gpu_to_oracle_states(one, {k: (b0[k] if k in ("data", "first_data") else b1[k]) for k in b0})[0]
+            so.d.qpos[0:6] = list(obs[i, 0:6].astype(np.float64))
+            so.d.qpos[15:18] = list(obs[i, 12:15].astype(np.float64))
+            so.d.xpos[13][:] = list(obs[i, 12:15].astype(np.float64))
+            O.env_step(blob, cfg, so, actions[i], precision="f32")
+            tot += abs(float(w @ (np.array(so.obs)[:23] - true[i])))
+        assert loss[pi] == pytest.approx(tot, rel=2e-3, abs=1e-4)
+    tuned, log = RP.env_params_tuning(one, 3, {"geom_friction": 0.4}, {"geom_friction": 0.08}, {"geom_friction": 4.0},
+                                      obs, actions, true, num_params=16)
+    assert 0.08 <= tuned["geom_friction"] <= 4.0 and log["loss"][-1] <= log["loss"][0] + 1e-9 and len(log["params"]) == 3
