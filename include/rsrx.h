@@ -132,6 +132,7 @@ int rsrx_physics_step(const rsrx_model* m, int N, float* data, int nsteps, const
  * qfrc_constraint[nv], ncon, nefc, niter, contact dist[cap], contact pos[cap*3].
  * `dump` is [N][rsrx_debug_stride()] floats. */
 int rsrx_debug_stride(void);
+int rsrx_max_contacts(void); /* active-contact cap per env (RSRX_STATUS_CONTACT_OVERFLOW beyond it) */
 int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, const rsrx_per_env* per_env, float* dump,
                             void* stream);
 

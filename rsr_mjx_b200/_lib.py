@@ -77,6 +77,7 @@ def lib():
     L.rsrx_physics_step.argtypes = [vp, i32, vp, i32, C.POINTER(PerEnvC), vp, vp]
     L.rsrx_physics_step_debug.argtypes = [vp, i32, vp, C.POINTER(PerEnvC), vp, vp]
     L.rsrx_debug_stride.restype = i32
+    L.rsrx_max_contacts.restype = i32
     L.rsrx_kde.argtypes = [vp, i32, i32, vp, i32, f32, vp, vp]
     L.rsrx_rsr_loss.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, f32, f32, f32, vp, vp, vp, vp]
     if L.rsrx_model_blob_size() != C.sizeof(ModelBlob) or L.rsrx_env_cfg_size() != C.sizeof(EnvCfg):
@@ -91,5 +92,5 @@ def check(rc: int, what: str = "rsrx"):
 
 
 EXPORTS = ("rsrx_model_create", "rsrx_model_destroy", "rsrx_model_layout", "rsrx_model_blob_size", "rsrx_env_cfg_size",
-           "rsrx_env_reset", "rsrx_env_step", "rsrx_physics_step", "rsrx_debug_stride", "rsrx_physics_step_debug",
+           "rsrx_env_reset", "rsrx_env_step", "rsrx_physics_step", "rsrx_debug_stride", "rsrx_max_contacts", "rsrx_physics_step_debug",
            "rsrx_rsr_loss", "rsrx_kde", "rsrx_last_error", "rsrx_version")

@@ -2,6 +2,7 @@
 // launches.  No torch types; the caller owns every state buffer.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -29,6 +30,7 @@ extern "C" const char* rsrx_version(void) { return "rsrx 0.1 (sm_100a)"; }
 extern "C" size_t rsrx_model_blob_size(void) { return sizeof(rsrx_model_blob); }
 extern "C" size_t rsrx_env_cfg_size(void) { return sizeof(rsrx_env_cfg); }
 extern "C" int rsrx_debug_stride(void) { return dbg::STRIDE; }
+extern "C" int rsrx_max_contacts(void) { return MAXC; }
 
 // ---- host-side double math for the static precomputation -----------------------
 namespace {
@@ -170,6 +172,42 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
     d.pair_margin[p] = (float)(b.geom_margin[g1] > b.geom_margin[g2] ? b.geom_margin[g1] : b.geom_margin[g2]);
     d.pair_tran[p] = (float)b.body_invweight0[b.geom_bodyid[g1]][0] + (float)b.body_invweight0[b.geom_bodyid[g2]][0];
   }
+  // ---- dof blocks: dofs of one kinematic tree, plus trees joined by a collision pair, form one block of H
+  {
+    int comp[NV];
+    for (int i = 0; i < b.nv; i++) comp[i] = b.body_rootid[b.dof_bodyid[i]];
+    auto relabel = [&](int from, int to) { for (int i = 0; i < b.nv; i++) if (comp[i] == from) comp[i] = to; };
+    bool nz[NV][NV] = {{false}};
+    for (int e = 0; e < d.nment; e++) nz[d.ment_i[e]][d.ment_j[e]] = true;
+    for (int p = 0; p < b.npair; p++) {
+      int b1 = b.geom_bodyid[b.pair_geom1[p]], b2 = b.geom_bodyid[b.pair_geom2[p]];
+      uint32_t mask = d.body_dofmask[b1] | d.body_dofmask[b2];
+      for (int i = 0; i < b.nv; i++)
+        for (int j = 0; j <= i; j++)
+          if (((mask >> i) & 1u) && ((mask >> j) & 1u)) nz[i][j] = true;
+      if (d.body_dofmask[b1] && d.body_dofmask[b2]) {
+        int c1 = -1, c2 = -1;
+        for (int i = 0; i < b.nv; i++) { if ((d.body_dofmask[b1] >> i) & 1u) c1 = comp[i]; if ((d.body_dofmask[b2] >> i) & 1u) c2 = comp[i]; }
+        if (c1 != c2) relabel(c2, c1);
+      }
+    }
+    int pos = 0;
+    bool placed[NV] = {false};
+    for (int i = 0; i < b.nv; i++) {
+      if (placed[i]) continue;
+      int start = pos;
+      for (int j = i; j < b.nv; j++)
+        if (!placed[j] && comp[j] == comp[i]) { placed[j] = true; d.pos_of_dof[j] = pos; d.dof_of_pos[pos] = j; pos++; }
+      for (int q = start; q < pos; q++) { d.blk_start[q] = start; d.blk_end[q] = pos - 1; }
+    }
+    d.nhent = 0;
+    for (int i = 0; i < b.nv; i++)
+      for (int j = 0; j <= i; j++)
+        if (nz[i][j]) {
+          if (d.blk_start[d.pos_of_dof[i]] != d.blk_start[d.pos_of_dof[j]]) return fail("internal: H entry outside its block");
+          d.hent_i[d.nhent] = (unsigned char)i; d.hent_j[d.nhent] = (unsigned char)j; d.nhent++;
+        }
+  }
   for (int u = 0; u < b.nu; u++) {
     int j = b.act_trnid[u];
     d.act_qadr[u] = b.jnt_qposadr[j]; d.act_dof[u] = b.jnt_dofadr[j];
@@ -226,6 +264,7 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
   rsrx_model* m = new rsrx_model();
   if (build_dmodel(*reinterpret_cast<const rsrx_model_blob*>(blob_host), *cfg_host, m->host)) { delete m; return 1; }
   m->smem_bytes = ar::TOTAL * (int)sizeof(float);
+  if (const char* pad = getenv("RSRX_SMEM_PAD")) m->smem_bytes += atoi(pad);  // occupancy experiments only
   cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);

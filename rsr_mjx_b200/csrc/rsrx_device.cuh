@@ -16,7 +16,7 @@ constexpr int NU = RSRX_MAXU;     // 8
 constexpr int NG = RSRX_MAXGEOM;  // 32
 constexpr int NS = RSRX_MAXSITE;  // 4
 constexpr int NP = RSRX_MAXPAIR;  // 64
-constexpr int MAXC = 32;          // active-contact cap per env (overflow -> status bit)
+constexpr int MAXC = 24;          // active-contact cap per env (overflow -> status bit)
 constexpr int MAXSR = 24;         // sparse rows: equality + dof friction + joint limits
 constexpr int MAXROW = MAXSR + 6 * MAXC;
 constexpr int LD = NV + 1;        // padded leading dimension of the dense nv x nv matrices
@@ -54,6 +54,9 @@ struct DModel {
       dof_solimp[NV][5], dof_actfrcrange[NV][2];
   unsigned char ment_i[MAXMENT], ment_j[MAXMENT];
   unsigned char tri_i[NTRI], tri_j[NTRI];
+  // block permutation for the Cholesky factorisations + structurally non-zero entries of H
+  int pos_of_dof[NV], dof_of_pos[NV], blk_start[NV], blk_end[NV], nhent;
+  unsigned char hent_i[NTRI], hent_j[NTRI];
   // geoms
   int geom_type[NG], geom_bodyid[NG], geom_static[NG];
   float geom_pos[NG][3], geom_quat[NG][4], geom_size[NG][3], geom_friction[NG][3];
@@ -104,8 +107,7 @@ constexpr int CDOF = CRB + NB * 10;
 constexpr int CDOFDOT = CDOF + NV * 6;  // crb_cdof while building M, then cdof_dot
 constexpr int CVEL = CDOFDOT + NV * 6;
 constexpr int MM = CVEL + NB * 6;
-constexpr int LM = MM + NV * LD;
-constexpr int HH = LM + NV * LD;
+constexpr int HH = MM + NV * LD;
 // nv-vectors
 constexpr int V_BIAS = HH + NV * LD;
 constexpr int V_PASSIVE = V_BIAS + NV;
@@ -125,8 +127,9 @@ constexpr int CSTRIDE = 24;
 constexpr int CON = V_TMP + NV;
 constexpr int BROW = CON + MAXC * CSTRIDE;  // [c][4][nv]
 constexpr int UB = BROW + MAXC * 4 * NV;    // [c][4] base-row scratch
+constexpr int CW = UB + MAXC * 4;           // [c][8] per-contact Hessian weights
 // efc rows
-constexpr int E_D = UB + MAXC * 4;
+constexpr int E_D = CW + MAXC * 8;
 constexpr int E_AREF = E_D + MAXROW;
 constexpr int E_JAREF = E_AREF + MAXROW;
 constexpr int E_JV = E_JAREF + MAXROW;
@@ -138,7 +141,8 @@ constexpr int SR_CA = SR_DOFB + MAXSR;
 constexpr int SR_CB = SR_CA + MAXSR;
 constexpr int SR_FLOSS = SR_CB + MAXSR;
 constexpr int SR_TYPE = SR_FLOSS + MAXSR;  // int: 0 equality, 1 friction, 2 limit
-constexpr int OBSBUF = SR_TYPE + MAXSR;
+constexpr int SR_RF = SR_TYPE + MAXSR;     // R * frictionloss
+constexpr int OBSBUF = SR_RF + MAXSR;
 constexpr int TOTAL = OBSBUF + OBS_STRIDE;
 }  // namespace ar
 
@@ -161,7 +165,8 @@ constexpr int CDIST = NITER + 1;        // MAXC
 constexpr int CPOS = CDIST + MAXC;      // MAXC*3
 constexpr int CGEOM = CPOS + MAXC * 3;  // MAXC (g1*64+g2)
 constexpr int QFRC_ACT = CGEOM + MAXC;
-constexpr int STRIDE = QFRC_ACT + NV;
+constexpr int LS_TOTAL = QFRC_ACT + NV;
+constexpr int STRIDE = LS_TOTAL + 1;
 }  // namespace dbg
 
 // ---- small math (mirrors mjx/_src/math.py) ---------------------------------------

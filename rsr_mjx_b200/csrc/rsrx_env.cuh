@@ -15,7 +15,7 @@ struct PerEnv {
 };
 
 // load per-env model arrays + the dynamic state of env `e` into the arena
-__device__ void load_env(const DModel* __restrict__ dm, float* sm, int lane, int e, const float* __restrict__ row,
+__device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, int lane, int e, const float* __restrict__ row,
                          const PerEnv& pe) {
   const rsrx_layout& L = dm->lay;
   for (int i = lane; i < dm->nq; i += 32) sm[ar::QPOS + i] = row[L.qpos + i];
@@ -33,7 +33,7 @@ __device__ void load_env(const DModel* __restrict__ dm, float* sm, int lane, int
 }
 
 // write the pipeline_state row (qpos/qvel/ctrl/warmstart/time + lagged kinematics)
-__device__ void store_env(const DModel* __restrict__ dm, const float* sm, int lane, float* __restrict__ row, float time) {
+__device__ __noinline__ void store_env(const DModel* __restrict__ dm, const float* sm, int lane, float* __restrict__ row, float time) {
   const rsrx_layout& L = dm->lay;
   for (int i = lane; i < dm->nq; i += 32) row[L.qpos + i] = sm[ar::QPOS + i];
   for (int i = lane; i < dm->nv; i += 32) { row[L.qvel + i] = sm[ar::QVEL + i]; row[L.qacc_warmstart + i] = sm[ar::WARM + i]; }
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(32) physics_kernel(const DModel* __restrict__ 
         dp[dbg::QFRC_C + i] = sm[ar::V_QFRCC + i];
         dp[dbg::QFRC_ACT + i] = sm[ar::V_ACT + i];
       }
-      if (lane == 0) { dp[dbg::NCON] = (float)sd.ncon; dp[dbg::NEFC] = (float)sd.nrow; dp[dbg::NITER] = (float)niter; }
+      if (lane == 0) { dp[dbg::NCON] = (float)sd.ncon; dp[dbg::NEFC] = (float)sd.nrow; dp[dbg::NITER] = (float)(niter & 0xff); dp[dbg::LS_TOTAL] = (float)(niter >> 8); }
       for (int c = lane; c < MAXC; c += 32) {
         const float* cr = sm + ar::CON + c * ar::CSTRIDE;
         const bool v = c < sd.ncon;

@@ -12,7 +12,7 @@ namespace rsrx {
 
 // ------------------------------------------------------------------ kinematics
 // smooth.py::kinematics — static bodies/geoms come precomputed from the host.
-__device__ void kinematics(const DModel* __restrict__ dm, float* sm, int lane) {
+__device__ __noinline__ void kinematics(const DModel* __restrict__ dm, float* sm, int lane) {
   const int nbody = dm->nbody;
   if (lane < nbody && dm->body_static[lane]) {
     for (int i = 0; i < 3; i++) sm[ar::XPOS + lane * 3 + i] = dm->static_xpos[lane][i];
@@ -109,7 +109,7 @@ __device__ void kinematics(const DModel* __restrict__ dm, float* sm, int lane) {
 }
 
 // smooth.py::com_pos — subtree_com of tree roots, cinert, cdof
-__device__ void com_pos(const DModel* __restrict__ dm, float* sm, int lane) {
+__device__ __noinline__ void com_pos(const DModel* __restrict__ dm, float* sm, int lane) {
   const int nbody = dm->nbody;
   // a root's subtree is the contiguous body range [b, subtree_end)
   if (lane < nbody && lane > 0 && dm->body_rootid[lane] == lane) {
@@ -184,44 +184,70 @@ __device__ void com_pos(const DModel* __restrict__ dm, float* sm, int lane) {
   RSRX_SYNC();
 }
 
-// In-place dense Cholesky (lower) of the nv x nv matrix at A (leading dim LD);
-// lane i owns row i.  Right-looking, one column per step.
-__device__ void warp_cholesky(float* A, int n, int lane) {
+// x <- A^-1 x for an SPD nv x nv matrix A held in the BLOCK-PERMUTED dof order
+// (DModel::pos_of_dof: dofs that can ever be coupled — same kinematic tree or a
+// collision pair between their trees — are contiguous; everything outside the
+// diagonal blocks is structurally zero and never touched).  A's lower triangle
+// (leading dim LD) is overwritten by its Cholesky factor; x is an nv-vector in
+// dof order.  COMPACT code on purpose (the kernel is instruction-fetch bound, see
+// profiles/): rolled loops, lane p owns row p, which lives in shared memory
+// (stride LD = 21 words: conflict-free) and is touched by that lane only;
+// whatever crosses lanes (pivot, column k) travels by shuffle, so the
+// factorisation needs no barriers.
+__device__ __noinline__ void warp_chol_factor_solve(const DModel* __restrict__ dm, float* A, float* x, int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int n = dm->nv;
+  const bool own = lane < n;
+  const int p = own ? lane : n - 1;  // surplus lanes shadow the last row (reads only)
+  float* row = A + p * LD;
+  const int pend = dm->blk_end[p], pstart = dm->blk_start[p];
+  float xi = x[dm->dof_of_pos[p]];
+#pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    const float akk = A[k * LD + k];
+    const int kend = dm->blk_end[k];
+    const float aik = row[k];
+    const float akk = __shfl_sync(FULL, aik, k);
     const float d = sqrtf(akk > MJ_MINVAL ? akk : MJ_MINVAL);
-    float l = 0.f;
-    if (lane > k && lane < n) l = A[lane * LD + k] / d;
-    RSRX_SYNC();
-    if (lane == k) A[k * LD + k] = d;
-    if (lane > k && lane < n) A[lane * LD + k] = l;
-    RSRX_SYNC();
-    if (lane > k && lane < n) {
-      for (int j = k + 1; j <= lane; ++j) A[lane * LD + j] -= l * A[j * LD + k];
+    const bool in = own && lane > k && lane <= kend;
+    const float l = in ? aik / d : 0.f;
+    if (own && lane == k) row[k] = d;
+    if (in) row[k] = l;
+    const float yk = __shfl_sync(FULL, xi, k) / d;  // forward substitution, fused
+    xi = (own && lane == k) ? yk : xi - l * yk;
+#pragma unroll 2
+    for (int j = k + 1; j <= kend; ++j) {
+      const float lj = __shfl_sync(FULL, l, j);
+      if (in && j <= lane) row[j] -= l * lj;
     }
-    RSRX_SYNC();
   }
+  RSRX_SYNC();
+  // backward: L^T x = y, column-oriented; lane p reads L[k][p] (row k is contiguous)
+#pragma unroll 1
+  for (int k = n - 1; k >= 0; --k) {
+    const float xk = __shfl_sync(FULL, xi, k) / A[k * LD + k];
+    if (own && lane == k) xi = xk;
+    else if (own && lane < k && lane >= dm->blk_start[k]) xi -= A[k * LD + p] * xk;
+  }
+  (void)pend; (void)pstart;
+  if (own) x[dm->dof_of_pos[p]] = xi;
+  RSRX_SYNC();
 }
-// x <- (L L^T)^-1 x, x an nv-vector in shared memory
-__device__ void warp_chol_solve(const float* L, int n, float* x, int lane) {
-  for (int k = 0; k < n; ++k) {  // forward: L y = b
-    const float yk = x[k] / L[k * LD + k];
-    RSRX_SYNC();
-    if (lane == k) x[k] = yk;
-    if (lane > k && lane < n) x[lane] -= L[lane * LD + k] * yk;
-    RSRX_SYNC();
+
+// HH <- M (+ dt * diag(damp) when damp != nullptr), written in the block-permuted order
+__device__ __noinline__ void copy_M_permuted(const DModel* __restrict__ dm, float* sm, int lane, const float* damp, float dt) {
+#pragma unroll 1
+  for (int e = lane; e < dm->ntri; e += 32) {
+    const int i = dm->tri_i[e], j = dm->tri_j[e];
+    const int pi = dm->pos_of_dof[i], pj = dm->pos_of_dof[j];
+    float v = sm[ar::MM + i * LD + j];
+    if (damp && i == j) v += dt * damp[i];
+    sm[ar::HH + max(pi, pj) * LD + min(pi, pj)] = v;
   }
-  for (int k = n - 1; k >= 0; --k) {  // backward: L^T x = y
-    const float xk = x[k] / L[k * LD + k];
-    RSRX_SYNC();
-    if (lane == k) x[k] = xk;
-    if (lane < k) x[lane] -= L[k * LD + lane] * xk;
-    RSRX_SYNC();
-  }
+  RSRX_SYNC();
 }
 
 // smooth.py::crb + support.make_m (dense) + factor_m
-__device__ void crb_and_factor(const DModel* __restrict__ dm, float* sm, int lane) {
+__device__ __noinline__ void crb_and_factor(const DModel* __restrict__ dm, float* sm, int lane) {
   const int nv = dm->nv, nbody = dm->nbody;
   if (lane < nbody && lane > 0 && !dm->body_static[lane]) {
     const int b = lane;
@@ -248,9 +274,6 @@ __device__ void crb_and_factor(const DModel* __restrict__ dm, float* sm, int lan
     sm[ar::MM + j * LD + i] = s;
   }
   RSRX_SYNC();
-  for (int e = lane; e < nv * LD; e += 32) sm[ar::LM + e] = sm[ar::MM + e];
-  RSRX_SYNC();
-  warp_cholesky(sm + ar::LM, nv, lane);
 }
 
 // ------------------------------------------------------------------- collision
@@ -482,7 +505,7 @@ __device__ void box_box(const float* p1, const float* m1, const float* s1, const
 }
 
 // constraint.py::_kbi
-__device__ __forceinline__ void kbi(const DModel* __restrict__ dm, const float* solref, const float* solimp, float pos,
+__device__ __noinline__ void kbi(const DModel* __restrict__ dm, const float* solref, const float* solimp, float pos,
                                     float* k, float* b, float* imp) {
   float timeconst = solref[0];
   const float dampratio = solref[1];
@@ -508,7 +531,7 @@ __device__ __forceinline__ void kbi(const DModel* __restrict__ dm, const float* 
 // registers/local memory), warp prefix-sum compaction of the active contacts
 // into the shared-memory contact list in (pair, slot) order.  Contacts that MJX
 // would keep as zeroed rows (dist >= 0) are dropped.  Returns ncon.
-__device__ int collision(const DModel* __restrict__ dm, float* sm, int lane, int* status) {
+__device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, int lane, int* status) {
   int ncon = 0;
   for (int base = 0; base < dm->npair; base += 32) {
     const int p = base + lane;
@@ -583,7 +606,7 @@ __device__ int collision(const DModel* __restrict__ dm, float* sm, int lane, int
 // (normal, tangent1, tangent2, torsion) of the contact-frame Jacobian difference,
 // from which the 6 pyramid-edge rows J_n +- mu_k J_k are formed on the fly.
 // Row order: [sparse rows][6 rows per contact].  Returns nsr (number of sparse rows).
-__device__ int make_constraint(const DModel* __restrict__ dm, float* sm, int lane, int ncon) {
+__device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float* sm, int lane, int ncon) {
   const int nv = dm->nv;
   int* sr_dofa = reinterpret_cast<int*>(sm + ar::SR_DOFA);
   int* sr_dofb = reinterpret_cast<int*>(sm + ar::SR_DOFB);
@@ -658,7 +681,7 @@ __device__ int make_constraint(const DModel* __restrict__ dm, float* sm, int lan
     sm[ar::E_D + r] = 1.f / rr;
     sm[ar::E_AREF + r] = -b * vel - k * imp * (pos - margin);
     sr_dofa[r] = dofa; sr_dofb[r] = dofb; sr_type[r] = type;
-    sm[ar::SR_CA + r] = ca; sm[ar::SR_CB + r] = cb; sm[ar::SR_FLOSS + r] = floss;
+    sm[ar::SR_CA + r] = ca; sm[ar::SR_CB + r] = cb; sm[ar::SR_FLOSS + r] = floss; sm[ar::SR_RF + r] = floss * rr;
   }
   if (have2) {
     const int r = n1 + __popc(m2 & lt);
@@ -670,7 +693,7 @@ __device__ int make_constraint(const DModel* __restrict__ dm, float* sm, int lan
     sm[ar::E_D + r] = 1.f / rr;
     sm[ar::E_AREF + r] = -b * vel - k * imp * pos2;
     sr_dofa[r] = dofa2; sr_dofb[r] = -1; sr_type[r] = 2;
-    sm[ar::SR_CA + r] = ca2; sm[ar::SR_CB + r] = 0.f; sm[ar::SR_FLOSS + r] = 0.f;
+    sm[ar::SR_CA + r] = ca2; sm[ar::SR_CB + r] = 0.f; sm[ar::SR_FLOSS + r] = 0.f; sm[ar::SR_RF + r] = 0.f;
   }
   // --- contact base rows B[c][p][dof] (support.jac + frame rotation)
   for (int t = lane; t < ncon * nv; t += 32) {
@@ -723,11 +746,9 @@ __device__ int make_constraint(const DModel* __restrict__ dm, float* sm, int lan
 // ------------------------------------------------------------ velocity / forces
 // smooth.py::com_vel, passive.py, smooth.py::rne, forward.py::fwd_actuation,
 // fwd_acceleration
-__device__ void velocity_and_forces(const DModel* __restrict__ dm, float* sm, int lane) {
+__device__ __noinline__ void velocity_and_forces(const DModel* __restrict__ dm, float* sm, int lane) {
   const int nv = dm->nv, nbody = dm->nbody;
   float* cacc = sm + ar::CRB;           // [NB][6] (crb no longer needed)
-  float* cfrc = sm + ar::CRB + NB * 6;  // needs NB*6 more: CRB has NB*10 = 160 >= 96 + 64? no -> use XIPOS.. see below
-  (void)cfrc;
   // com_vel: level by level
   if (lane < nbody && dm->body_static[lane]) {
     for (int i = 0; i < 6; i++) { sm[ar::CVEL + lane * 6 + i] = 0.f; cacc[lane * 6 + i] = (i >= 3) ? -dm->gravity[i - 3] : 0.f; }
@@ -816,97 +837,116 @@ __device__ void velocity_and_forces(const DModel* __restrict__ dm, float* sm, in
     sm[ar::V_SMOOTH + d] = fs;
     sm[ar::V_QACCS + d] = fs;
   }
-  RSRX_SYNC();
-  warp_chol_solve(sm + ar::LM, nv, sm + ar::V_QACCS, lane);
+  // factor_m + solve_m: qacc_smooth = M^-1 qfrc_smooth (factor a scratch copy of M; H is rebuilt later)
+  copy_M_permuted(dm, sm, lane, nullptr, 0.f);
+  warp_chol_factor_solve(dm, sm + ar::HH, sm + ar::V_QACCS, lane);
 }
 
 // ---------------------------------------------------------------------- solver
 struct SolverDims { int nsr, ncon, nrow; };
 
 // out[r] = J[r] . x for every row (x: nv-vector in shared memory)
-__device__ void mul_J(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, const float* x, float* out) {
+__device__ __noinline__ void mul_J(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon, const float* x,
+                                   float* out) {
   const int nv = dm->nv;
   const int* sr_dofa = reinterpret_cast<const int*>(sm + ar::SR_DOFA);
   const int* sr_dofb = reinterpret_cast<const int*>(sm + ar::SR_DOFB);
-  if (lane < sd.nsr) {
+  if (lane < nsr) {
     const int a = sr_dofa[lane], b = sr_dofb[lane];
     float s = sm[ar::SR_CA + lane] * x[a];
     if (b >= 0) s = (b < a) ? sm[ar::SR_CB + lane] * x[b] + s : s + sm[ar::SR_CB + lane] * x[b];
     out[lane] = s;
   }
-  for (int t = lane; t < sd.ncon * 4; t += 32) {
+#pragma unroll 1
+  for (int t = lane; t < ncon * 4; t += 32) {
     const float* Bp = sm + ar::BROW + t * nv;
     float s = 0.f;
+#pragma unroll 4
     for (int d = 0; d < nv; d++) s += Bp[d] * x[d];
     sm[ar::UB + t] = s;
   }
   RSRX_SYNC();
-  for (int t = lane; t < sd.ncon * 6; t += 32) {
+#pragma unroll 1
+  for (int t = lane; t < ncon * 6; t += 32) {
     const int c = t / 6, e = t - c * 6, k = e >> 1;
     const float* cr = sm + ar::CON + c * ar::CSTRIDE;
     const float f = (e & 1) ? -cr[cf::MU + k] : cr[cf::MU + k];
-    out[sd.nsr + t] = sm[ar::UB + c * 4] + sm[ar::UB + c * 4 + 1 + k] * f;
+    out[nsr + t] = sm[ar::UB + c * 4] + sm[ar::UB + c * 4 + 1 + k] * f;
   }
   RSRX_SYNC();
 }
 
-__device__ void mul_M(const DModel* __restrict__ dm, const float* sm, int lane, const float* x, float* out) {
+__device__ __noinline__ void mul_M(const DModel* __restrict__ dm, const float* sm, int lane, const float* x, float* out) {
   const int nv = dm->nv;
   if (lane < nv) {
     float s = 0.f;
+#pragma unroll 4
     for (int j = 0; j < nv; j++) s += sm[ar::MM + lane * LD + j] * x[j];
     out[lane] = s;
   }
 }
 
+// Per-row piecewise-quadratic description shared by _update_constraint and the
+// line search: a row is in its quadratic zone iff lo < x < hi (x = Jaref along the
+// search direction); outside, a dof-friction row is linear with force -+floss,
+// every other row contributes nothing.  equality: (-inf, inf); friction:
+// (-R*floss, R*floss); limit / contact: (-inf, 0).
+struct RowShape { float lo, hi, fl, rf; };
+__device__ __forceinline__ RowShape row_shape(const float* sm, int r, int nsr) {
+  RowShape s;
+  s.lo = -INFINITY; s.hi = 0.f; s.fl = 0.f; s.rf = 0.f;
+  if (r < nsr) {
+    const int type = reinterpret_cast<const int*>(sm + ar::SR_TYPE)[r];
+    if (type == 0) s.hi = INFINITY;
+    else if (type == 1) { s.fl = sm[ar::SR_FLOSS + r]; s.rf = sm[ar::SR_RF + r]; s.lo = -s.rf; s.hi = s.rf; }
+  }
+  return s;
+}
+
 // solver.py::_update_constraint.  Returns the total cost; writes E_ACT, qfrc_constraint.
-__device__ float update_constraint(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, float* gauss_out) {
-  const int nv = dm->nv;
-  const int* sr_type = reinterpret_cast<const int*>(sm + ar::SR_TYPE);
+__device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon,
+                                                float* gauss_out) {
+  const int nv = dm->nv, nrow = nsr + 6 * ncon;
   float cost = 0.f;
-  for (int r = lane; r < sd.nrow; r += 32) {
+#pragma unroll 1
+  for (int r = lane; r < nrow; r += 32) {
     const float ja = sm[ar::E_JAREF + r], D = sm[ar::E_D + r];
-    float f, act;
-    const int type = r < sd.nsr ? sr_type[r] : 3;
-    if (type == 0) {
-      act = 1.f; f = -D * ja; cost += 0.5f * D * ja * ja;
-    } else if (type == 1) {
-      const float fl = sm[ar::SR_FLOSS + r], rf = fl / D;
-      if (ja <= -rf) { act = 0.f; f = fl; cost += fl * (-0.5f * rf - ja); }
-      else if (ja >= rf) { act = 0.f; f = -fl; cost += fl * (-0.5f * rf + ja); }
-      else { act = 1.f; f = -D * ja; cost += 0.5f * D * ja * ja; }
-    } else {
-      act = ja < 0.f ? 1.f : 0.f;
-      f = act != 0.f ? -D * ja : 0.f;
-      if (act != 0.f) cost += 0.5f * D * ja * ja;
-    }
-    sm[ar::E_ACT + r] = act;
+    const RowShape s = row_shape(sm, r, nsr);
+    const bool quad = ja > s.lo && ja < s.hi;
+    const bool below = ja <= s.lo;
+    const float f = quad ? -D * ja : (below ? s.fl : -s.fl);
+    cost += quad ? 0.5f * D * ja * ja : s.fl * (-0.5f * s.rf + (below ? -ja : ja));
+    sm[ar::E_ACT + r] = quad ? 1.f : 0.f;
     sm[ar::E_JV + r] = f;  // E_JV doubles as the force array between line searches
   }
   RSRX_SYNC();
   // contact forces in base-row space: g0 = sum f, g_{1+k} = mu_k (f_{2k} - f_{2k+1})
-  for (int t = lane; t < sd.ncon * 4; t += 32) {
+#pragma unroll 1
+  for (int t = lane; t < ncon * 4; t += 32) {
     const int c = t >> 2, p = t & 3;
-    const float* fr = sm + ar::E_JV + sd.nsr + c * 6;
+    const float* fr = sm + ar::E_JV + nsr + c * 6;
     const float* cr = sm + ar::CON + c * ar::CSTRIDE;
     float g;
     if (p == 0) g = fr[0] + fr[1] + fr[2] + fr[3] + fr[4] + fr[5];
     else g = cr[cf::MU + p - 1] * (fr[2 * (p - 1)] - fr[2 * (p - 1) + 1]);
     sm[ar::UB + t] = g;
   }
+  if (lane < nv) sm[ar::V_QFRCC + lane] = 0.f;
+  RSRX_SYNC();
+  if (lane < nsr) {  // sparse rows: at most two dofs each
+    const int a = reinterpret_cast<const int*>(sm + ar::SR_DOFA)[lane], b = reinterpret_cast<const int*>(sm + ar::SR_DOFB)[lane];
+    const float f = sm[ar::E_JV + lane];
+    atomicAdd(sm + ar::V_QFRCC + a, sm[ar::SR_CA + lane] * f);
+    if (b >= 0) atomicAdd(sm + ar::V_QFRCC + b, sm[ar::SR_CB + lane] * f);
+  }
   RSRX_SYNC();
   float gpart = 0.f;
   if (lane < nv) {
     const int d = lane;
-    const int* sr_dofa = reinterpret_cast<const int*>(sm + ar::SR_DOFA);
-    const int* sr_dofb = reinterpret_cast<const int*>(sm + ar::SR_DOFB);
-    float s = 0.f;
-    for (int r = 0; r < sd.nsr; r++) {
-      if (sr_dofa[r] == d) s += sm[ar::SR_CA + r] * sm[ar::E_JV + r];
-      if (sr_dofb[r] == d) s += sm[ar::SR_CB + r] * sm[ar::E_JV + r];
-    }
+    float s = sm[ar::V_QFRCC + d];
     const int nv4 = 4 * nv;
-    for (int c = 0; c < sd.ncon; c++) {
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {
       const float* B = sm + ar::BROW + c * nv4;
       const float* g = sm + ar::UB + c * 4;
       s += B[d] * g[0] + B[nv + d] * g[1] + B[2 * nv + d] * g[2] + B[3 * nv + d] * g[3];
@@ -921,104 +961,95 @@ __device__ float update_constraint(const DModel* __restrict__ dm, float* sm, int
   return cost;
 }
 
-// solver.py::_update_gradient (Newton): grad, H = M + J^T diag(D*active) J,
-// Cholesky in place, Mgrad = H^-1 grad
-__device__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd) {
+// solver.py::_update_gradient (Newton): grad, H = M + J^T diag(D*active) J (in
+// the block-permuted dof order), Cholesky, Mgrad = H^-1 grad
+__device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon) {
   const int nv = dm->nv;
-  const int* sr_dofa = reinterpret_cast<const int*>(sm + ar::SR_DOFA);
-  const int* sr_dofb = reinterpret_cast<const int*>(sm + ar::SR_DOFB);
   if (lane < nv) {
     const float g = sm[ar::V_MA + lane] - sm[ar::V_SMOOTH + lane] - sm[ar::V_QFRCC + lane];
     sm[ar::V_GRAD + lane] = g;
     sm[ar::V_MGRAD + lane] = g;
   }
-  const int nv4 = 4 * nv;
-  for (int e = lane; e < dm->ntri; e += 32) {
-    const int i = dm->tri_i[e], j = dm->tri_j[e];  // i >= j
-    float h = sm[ar::MM + i * LD + j];
-    for (int r = 0; r < sd.nsr; r++) {
-      if (sm[ar::E_ACT + r] == 0.f) continue;
-      const int a = sr_dofa[r], b = sr_dofb[r];
-      const float ji = (a == i ? sm[ar::SR_CA + r] : 0.f) + (b == i ? sm[ar::SR_CB + r] : 0.f);
-      const float jj = (a == j ? sm[ar::SR_CA + r] : 0.f) + (b == j ? sm[ar::SR_CB + r] : 0.f);
-      if (ji != 0.f && jj != 0.f) h += ji * sm[ar::E_D + r] * jj;
+  copy_M_permuted(dm, sm, lane, nullptr, 0.f);
+  // per-contact weights of the 4x4 base-row Gram form: W00 = sum_r w_r,
+  // U_k = (w_2k - w_2k+1) mu_k, V_k = (w_2k + w_2k+1) mu_k^2, w_r = D * active_r
+#pragma unroll 1
+  for (int c = lane; c < ncon; c += 32) {
+    const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    const float* act = sm + ar::E_ACT + nsr + c * 6;
+    const float D = cr[cf::D];
+    float w00 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float wp = act[2 * k] * D, wm = act[2 * k + 1] * D, mu = cr[cf::MU + k];
+      w00 += wp + wm;
+      sm[ar::CW + c * 8 + 1 + k] = (wp - wm) * mu;
+      sm[ar::CW + c * 8 + 4 + k] = (wp + wm) * mu * mu;
     }
-    for (int c = 0; c < sd.ncon; c++) {
+    sm[ar::CW + c * 8] = w00;
+  }
+  RSRX_SYNC();
+  if (lane < nsr && sm[ar::E_ACT + lane] != 0.f) {  // sparse rows touch one diagonal entry (equality: a 2x2 block)
+    const int a = reinterpret_cast<const int*>(sm + ar::SR_DOFA)[lane], b = reinterpret_cast<const int*>(sm + ar::SR_DOFB)[lane];
+    const float ca = sm[ar::SR_CA + lane], cb = sm[ar::SR_CB + lane], D = sm[ar::E_D + lane];
+    const int pa = dm->pos_of_dof[a];
+    atomicAdd(sm + ar::HH + pa * LD + pa, ca * D * ca);
+    if (b >= 0) {
+      const int pb = dm->pos_of_dof[b];
+      atomicAdd(sm + ar::HH + pb * LD + pb, cb * D * cb);
+      atomicAdd(sm + ar::HH + max(pa, pb) * LD + min(pa, pb), ca * D * cb);
+    }
+  }
+  RSRX_SYNC();
+  const int nv4 = 4 * nv;
+#pragma unroll 1
+  for (int e = lane; e < dm->nhent; e += 32) {  // structurally non-zero entries only
+    const int i = dm->hent_i[e], j = dm->hent_j[e];  // dofs, i >= j
+    float h = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {
       const float* cr = sm + ar::CON + c * ar::CSTRIDE;
       const unsigned mask = (unsigned)__float_as_int(cr[cf::MASK]);
       if (!(((mask >> i) & 1u) && ((mask >> j) & 1u))) continue;
       const float* B = sm + ar::BROW + c * nv4;
-      const float* act = sm + ar::E_ACT + sd.nsr + c * 6;
-      const float D = cr[cf::D];
+      const float* W = sm + ar::CW + c * 8;
       const float b0i = B[i], b0j = B[j];
+      float acc = W[0] * b0i * b0j;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const float mu = cr[cf::MU + k];
-        const float bki = B[(1 + k) * nv + i] * mu, bkj = B[(1 + k) * nv + j] * mu;
-        if (act[2 * k] != 0.f) h += (b0i + bki) * D * (b0j + bkj);
-        if (act[2 * k + 1] != 0.f) h += (b0i - bki) * D * (b0j - bkj);
+        const float bki = B[(1 + k) * nv + i], bkj = B[(1 + k) * nv + j];
+        acc += W[1 + k] * (b0i * bkj + bki * b0j) + W[4 + k] * bki * bkj;
       }
+      h += acc;
     }
-    sm[ar::HH + i * LD + j] = h;
+    const int pi = dm->pos_of_dof[i], pj = dm->pos_of_dof[j];
+    sm[ar::HH + max(pi, pj) * LD + min(pi, pj)] += h;
   }
   RSRX_SYNC();
-  warp_cholesky(sm + ar::HH, nv, lane);
-  warp_chol_solve(sm + ar::HH, nv, sm + ar::V_MGRAD, lane);
+  warp_chol_factor_solve(dm, sm + ar::HH, sm + ar::V_MGRAD, lane);
 }
 
 // _Context.create: qacc <- src, Jaref, Ma, constraint update.  Returns cost.
-__device__ float ctx_create(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, const float* src,
-                            float* gauss) {
-  const int nv = dm->nv;
+__device__ __noinline__ float ctx_create(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon,
+                                         const float* src, float* gauss) {
+  const int nv = dm->nv, nrow = nsr + 6 * ncon;
   if (lane < nv) sm[ar::V_QACC + lane] = src[lane];
   RSRX_SYNC();
-  mul_J(dm, sm, lane, sd, sm + ar::V_QACC, sm + ar::E_JAREF);
-  for (int r = lane; r < sd.nrow; r += 32) sm[ar::E_JAREF + r] -= sm[ar::E_AREF + r];
+  mul_J(dm, sm, lane, nsr, ncon, sm + ar::V_QACC, sm + ar::E_JAREF);
+#pragma unroll 1
+  for (int r = lane; r < nrow; r += 32) sm[ar::E_JAREF + r] -= sm[ar::E_AREF + r];
   mul_M(dm, sm, lane, sm + ar::V_QACC, sm + ar::V_MA);
   RSRX_SYNC();
-  return update_constraint(dm, sm, lane, sd, gauss);
+  return update_constraint(dm, sm, lane, nsr, ncon, gauss);
 }
 
 struct LSPoint { float alpha, cost, d0, d1; };
 
-// _LSPoint.create for up to three alphas in one pass over the rows
-template <int NA>
-__device__ void ls_points(const DModel* __restrict__ dm, const float* sm, int lane, const SolverDims& sd,
-                          const float* alpha, const float* qg, LSPoint* out) {
-  const int* sr_type = reinterpret_cast<const int*>(sm + ar::SR_TYPE);
-  float q0[NA], q1[NA], q2[NA];
-#pragma unroll
-  for (int a = 0; a < NA; a++) { q0[a] = 0.f; q1[a] = 0.f; q2[a] = 0.f; }
-  for (int r = lane; r < sd.nrow; r += 32) {
-    const float ja = sm[ar::E_JAREF + r], jv = sm[ar::E_JV + r], D = sm[ar::E_D + r];
-    const float c0 = 0.5f * ja * ja * D, c1 = jv * ja * D, c2 = 0.5f * jv * jv * D;
-    const int type = r < sd.nsr ? sr_type[r] : 3;
-    float fl = 0.f, rf = 0.f;
-    if (type == 1) { fl = sm[ar::SR_FLOSS + r]; rf = fl / D; }
-#pragma unroll
-    for (int a = 0; a < NA; a++) {
-      const float x = ja + alpha[a] * jv;
-      if (type == 0) { q0[a] += c0; q1[a] += c1; q2[a] += c2; }
-      else if (type == 1) {
-        if (x <= -rf) { q0[a] += fl * (-0.5f * rf - ja); q1[a] += -fl * jv; }
-        else if (x >= rf) { q0[a] += fl * (-0.5f * rf + ja); q1[a] += fl * jv; }
-        else { q0[a] += c0; q1[a] += c1; q2[a] += c2; }
-      } else if (x < 0.f) { q0[a] += c0; q1[a] += c1; q2[a] += c2; }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < NA; a++) {
-    const float t0 = warp_sum(q0[a]) + qg[0], t1 = warp_sum(q1[a]) + qg[1], t2 = warp_sum(q2[a]) + qg[2];
-    out[a].alpha = alpha[a];
-    out[a].cost = alpha[a] * alpha[a] * t2 + alpha[a] * t1 + t0;
-    out[a].d0 = 2.f * alpha[a] * t2 + t1;
-    out[a].d1 = 2.f * t2 + (t2 == 0.f ? MJ_MINVAL : 0.f);
-  }
-}
-
-// solver.py::_linesearch
-__device__ void linesearch(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, float gauss) {
-  const int nv = dm->nv;
+// solver.py::_linesearch with _LSPoint.create evaluated for three alphas per pass
+// over the rows (one inlined evaluation site: the two start-up points go through
+// the same code).  Returns the number of bracketing iterations.
+__device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon, float gauss) {
+  const int nv = dm->nv, nrow = nsr + 6 * ncon;
   float s2 = 0.f, g1 = 0.f, g2 = 0.f;
   mul_M(dm, sm, lane, sm + ar::V_SEARCH, sm + ar::V_MV);
   RSRX_SYNC();
@@ -1030,41 +1061,91 @@ __device__ void linesearch(const DModel* __restrict__ dm, float* sm, int lane, c
   }
   const float smag = sqrtf(warp_sum(s2)) * dm->meaninertia * (float)(nv > 1 ? nv : 1);
   const float gtol = dm->tolerance * dm->ls_tolerance * smag;
-  const float qg[3] = {gauss, warp_sum(g1), 0.5f * warp_sum(g2)};
-  mul_J(dm, sm, lane, sd, sm + ar::V_SEARCH, sm + ar::E_JV);
+  const float qg0 = gauss, qg1 = warp_sum(g1), qg2 = 0.5f * warp_sum(g2);
+  mul_J(dm, sm, lane, nsr, ncon, sm + ar::V_SEARCH, sm + ar::E_JV);
   LSPoint p0, lo, hi;
-  {
-    float a0 = 0.f;
-    ls_points<1>(dm, sm, lane, sd, &a0, qg, &p0);
-    float a1 = p0.alpha - p0.d0 / p0.d1;
-    LSPoint lo0;
-    ls_points<1>(dm, sm, lane, sd, &a1, qg, &lo0);
-    const bool lesser = lo0.d0 < p0.d0;
-    hi = lesser ? p0 : lo0;
-    lo = lesser ? lo0 : p0;
-  }
-  bool swap = true;
-  int it = 0;
+  p0.alpha = p0.cost = p0.d0 = p0.d1 = 0.f;
+  lo = hi = p0;
+  float al0 = 0.f, al1 = 0.f, al2 = 0.f;
+  int phase = 0, it = 0;
+#pragma unroll 1
   for (;;) {
+    // ---- _LSPoint.create x 3
+    float q00 = 0.f, q01 = 0.f, q02 = 0.f, q10 = 0.f, q11 = 0.f, q12 = 0.f, q20 = 0.f, q21 = 0.f, q22 = 0.f;
+#pragma unroll 1
+    for (int r = lane; r < nrow; r += 32) {
+      const float ja = sm[ar::E_JAREF + r], jv = sm[ar::E_JV + r], D = sm[ar::E_D + r];
+      const RowShape s = row_shape(sm, r, nsr);
+      const float c0 = 0.5f * ja * ja * D, c1 = jv * ja * D, c2 = 0.5f * jv * jv * D;
+      const float lm = s.fl * (-0.5f * s.rf - ja), lp = s.fl * (-0.5f * s.rf + ja), l1 = s.fl * jv;
+      {
+        const float x = __fadd_rn(ja, __fmul_rn(al0, jv));
+        const bool quad = x > s.lo && x < s.hi, below = x <= s.lo;
+        q00 += quad ? c0 : (below ? lm : lp); q01 += quad ? c1 : (below ? -l1 : l1); q02 += quad ? c2 : 0.f;
+      }
+      {
+        const float x = __fadd_rn(ja, __fmul_rn(al1, jv));
+        const bool quad = x > s.lo && x < s.hi, below = x <= s.lo;
+        q10 += quad ? c0 : (below ? lm : lp); q11 += quad ? c1 : (below ? -l1 : l1); q12 += quad ? c2 : 0.f;
+      }
+      {
+        const float x = __fadd_rn(ja, __fmul_rn(al2, jv));
+        const bool quad = x > s.lo && x < s.hi, below = x <= s.lo;
+        q20 += quad ? c0 : (below ? lm : lp); q21 += quad ? c1 : (below ? -l1 : l1); q22 += quad ? c2 : 0.f;
+      }
+    }
+    LSPoint pt[3];
+    {
+      const float al[3] = {al0, al1, al2};
+      const float t0[3] = {warp_sum(q00) + qg0, warp_sum(q10) + qg0, warp_sum(q20) + qg0};
+      const float t1[3] = {warp_sum(q01) + qg1, warp_sum(q11) + qg1, warp_sum(q21) + qg1};
+      const float t2[3] = {warp_sum(q02) + qg2, warp_sum(q12) + qg2, warp_sum(q22) + qg2};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        // No FMA contraction: with fused multiply-adds the derivative at a Newton iterate no longer rounds to
+        // the value that ends MJX's bracketing and the loop runs to ls_iterations (measured 100 vs 28
+        // line-search iterations per substep).  Mirrors the oracle's unfused arithmetic.
+        pt[a].alpha = al[a];
+        pt[a].cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(al[a], al[a]), t2[a]), __fmul_rn(al[a], t1[a])), t0[a]);
+        pt[a].d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, al[a]), t2[a]), t1[a]);
+        pt[a].d1 = __fadd_rn(__fmul_rn(2.f, t2[a]), (t2[a] == 0.f ? MJ_MINVAL : 0.f));
+      }
+    }
+    // ---- bracketing logic
+    if (phase == 0) {
+      p0 = pt[0];
+      al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1;
+      phase = 1;
+      continue;
+    }
+    bool swap = true;
+    if (phase == 1) {
+      const LSPoint lo0 = pt[0];
+      const bool lesser = lo0.d0 < p0.d0;
+      hi = lesser ? p0 : lo0;
+      lo = lesser ? lo0 : p0;
+      phase = 2;
+    } else {
+      const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
+      const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+      if (swap_lo_next) lo = lo_next;
+      const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+      if (swap_lo_mid) lo = mid;
+      const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+      if (swap_hi_next) hi = hi_next;
+      const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+      if (swap_hi_mid) hi = mid;
+      swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+      it++;
+    }
     bool done = it >= dm->ls_iterations;
     done |= !swap;
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (done) break;
-    float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
-    LSPoint pt[3];
-    ls_points<3>(dm, sm, lane, sd, al, qg, pt);
-    const LSPoint &lo_next = pt[0], &hi_next = pt[1], &mid = pt[2];
-    const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
-    if (swap_lo_next) lo = lo_next;
-    const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
-    if (swap_lo_mid) lo = mid;
-    const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
-    if (swap_hi_next) hi = hi_next;
-    const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
-    if (swap_hi_mid) hi = mid;
-    swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
-    it++;
+    al0 = lo.alpha - lo.d0 / lo.d1;
+    al1 = hi.alpha - hi.d0 / hi.d1;
+    al2 = 0.5f * (lo.alpha + hi.alpha);
   }
   const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
   const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
@@ -1073,31 +1154,34 @@ __device__ void linesearch(const DModel* __restrict__ dm, float* sm, int lane, c
       sm[ar::V_QACC + lane] += sm[ar::V_SEARCH + lane] * alpha;
       sm[ar::V_MA + lane] += sm[ar::V_MV + lane] * alpha;
     }
-    for (int r = lane; r < sd.nrow; r += 32) sm[ar::E_JAREF + r] += sm[ar::E_JV + r] * alpha;
+#pragma unroll 1
+    for (int r = lane; r < nrow; r += 32) sm[ar::E_JAREF + r] += sm[ar::E_JV + r] * alpha;
   }
   RSRX_SYNC();
+  return it;
 }
 
-// solver.py::solve.  Returns the number of Newton iterations.
-__device__ int solve(const DModel* __restrict__ dm, float* sm, int lane, const SolverDims& sd, int* status) {
-  const int nv = dm->nv;
-  if (sd.nrow == 0) {
+// solver.py::solve.  Returns niter | (total line-search iterations << 8).
+__device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon, int* status) {
+  const int nv = dm->nv, nrow = nsr + 6 * ncon;
+  if (nrow == 0) {
     if (lane < nv) { sm[ar::V_QACC + lane] = sm[ar::V_QACCS + lane]; sm[ar::V_QFRCC + lane] = 0.f; }
     RSRX_SYNC();
     return 0;
   }
   float gauss;
-  const float cw = ctx_create(dm, sm, lane, sd, sm + ar::WARM, &gauss);
-  const float cs = ctx_create(dm, sm, lane, sd, sm + ar::V_QACCS, &gauss);
+  const float cw = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::WARM, &gauss);
+  const float cs = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::V_QACCS, &gauss);
   float cost = cs;
-  if (cw < cs) cost = ctx_create(dm, sm, lane, sd, sm + ar::WARM, &gauss);
+  if (cw < cs) cost = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::WARM, &gauss);
   float prev_cost = INFINITY;
-  update_gradient(dm, sm, lane, sd);
-  if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
-  RSRX_SYNC();
   const float scale = 1.f / (dm->meaninertia * (float)(nv > 1 ? nv : 1));
-  int niter = 0;
+  int niter = 0, ls_total = 0;
+#pragma unroll 1
   for (;;) {
+    update_gradient(dm, sm, lane, nsr, ncon);
+    if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
+    RSRX_SYNC();
     const float improvement = (prev_cost - cost) * scale;
     float g = 0.f;
     if (lane < nv) g = sm[ar::V_GRAD + lane] * sm[ar::V_GRAD + lane];
@@ -1106,18 +1190,15 @@ __device__ int solve(const DModel* __restrict__ dm, float* sm, int lane, const S
     done |= improvement < dm->tolerance;
     done |= gradient < dm->tolerance;
     if (done) break;
-    linesearch(dm, sm, lane, sd, gauss);
+    ls_total += linesearch(dm, sm, lane, nsr, ncon, gauss);
     prev_cost = cost;
-    cost = update_constraint(dm, sm, lane, sd, &gauss);
-    update_gradient(dm, sm, lane, sd);
-    if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
-    RSRX_SYNC();
+    cost = update_constraint(dm, sm, lane, nsr, ncon, &gauss);
     niter++;
   }
   if (niter >= dm->iterations) *status |= RSRX_STATUS_SOLVER_CAP;
   if (lane < nv) sm[ar::WARM + lane] = sm[ar::V_QACC + lane];
   RSRX_SYNC();
-  return niter;
+  return niter | (ls_total << 8);
 }
 
 // forward.py::forward.  Returns niter; fills dims.
@@ -1129,22 +1210,16 @@ __device__ int forward(const DModel* __restrict__ dm, float* sm, int lane, Solve
   const int nsr = make_constraint(dm, sm, lane, ncon);
   sd->nsr = nsr; sd->ncon = ncon; sd->nrow = nsr + 6 * ncon;
   velocity_and_forces(dm, sm, lane);
-  return solve(dm, sm, lane, *sd, status);
+  return solve(dm, sm, lane, nsr, ncon, status);
 }
 
 // forward.py::implicit + _advance (implicitfast; only dof damping contributes to qDeriv)
-__device__ void implicit_advance(const DModel* __restrict__ dm, float* sm, int lane) {
+__device__ __noinline__ void implicit_advance(const DModel* __restrict__ dm, float* sm, int lane) {
   const int nv = dm->nv;
   const float dt = dm->timestep;
-  for (int e = lane; e < nv * LD; e += 32) sm[ar::HH + e] = sm[ar::MM + e];
-  RSRX_SYNC();
-  if (lane < nv) {
-    sm[ar::HH + lane * LD + lane] += dt * sm[ar::DAMP + lane];
-    sm[ar::V_TMP + lane] = sm[ar::V_SMOOTH + lane] + sm[ar::V_QFRCC + lane];
-  }
-  RSRX_SYNC();
-  warp_cholesky(sm + ar::HH, nv, lane);
-  warp_chol_solve(sm + ar::HH, nv, sm + ar::V_TMP, lane);
+  if (lane < nv) sm[ar::V_TMP + lane] = sm[ar::V_SMOOTH + lane] + sm[ar::V_QFRCC + lane];
+  copy_M_permuted(dm, sm, lane, sm + ar::DAMP, dt);
+  warp_chol_factor_solve(dm, sm + ar::HH, sm + ar::V_TMP, lane);
   if (lane < nv) sm[ar::QVEL + lane] += sm[ar::V_TMP + lane] * dt;
   RSRX_SYNC();
   if (lane < dm->njnt) {
