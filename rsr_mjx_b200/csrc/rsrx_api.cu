@@ -200,6 +200,7 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
         if (!placed[j] && comp[j] == comp[i]) { placed[j] = true; d.pos_of_dof[j] = pos; d.dof_of_pos[pos] = j; pos++; }
       for (int q = start; q < pos; q++) { d.blk_start[q] = start; d.blk_end[q] = pos - 1; }
     }
+    { int t = 0; for (int ri = 0; ri < NV && t < NTRI; ri++) for (int rj = 0; rj <= ri && t < NTRI; rj++) { d.tri_ri[t] = (unsigned char)ri; d.tri_rj[t] = (unsigned char)rj; t++; } }
     d.nhent = 0;
     for (int i = 0; i < b.nv; i++)
       for (int j = 0; j <= i; j++)
@@ -263,7 +264,7 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
   if (blob_bytes != sizeof(rsrx_model_blob)) return fail("rsrx_model_create: blob size mismatch (host/lib out of sync)");
   rsrx_model* m = new rsrx_model();
   if (build_dmodel(*reinterpret_cast<const rsrx_model_blob*>(blob_host), *cfg_host, m->host)) { delete m; return 1; }
-  m->smem_bytes = ar::TOTAL * (int)sizeof(float);
+  m->smem_bytes = WPB * ar::TOTAL * (int)sizeof(float);
   if (const char* pad = getenv("RSRX_SMEM_PAD")) m->smem_bytes += atoi(pad);  // occupancy experiments only
   cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
@@ -314,7 +315,7 @@ extern "C" int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, con
   if (!m || !qpos || !qvel || !ctrl) return fail("rsrx_env_reset: null argument");
   if (N <= 0) return fail("rsrx_env_reset: N must be positive");
   if (check_state(st)) return 1;
-  reset_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(per_env), to_sp(st));
+  reset_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -324,7 +325,7 @@ extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const fl
   if (!m || !action) return fail("rsrx_env_step: null argument");
   if (N <= 0) return fail("rsrx_env_step: N must be positive");
   if (check_state(st)) return 1;
-  step_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(per_env), to_sp(st));
+  step_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -333,7 +334,7 @@ extern "C" int rsrx_physics_step(const rsrx_model* m, int N, float* data, int ns
                                  int32_t* status, void* stream) {
   if (!m || !data) return fail("rsrx_physics_step: null argument");
   if (N <= 0 || nsteps < 0) return fail("rsrx_physics_step: bad N / nsteps");
-  physics_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(per_env), status, nullptr);
+  physics_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(per_env), status, nullptr);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -342,7 +343,7 @@ extern "C" int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, 
                                        void* stream) {
   if (!m || !data || !dump) return fail("rsrx_physics_step_debug: null argument");
   if (N <= 0) return fail("rsrx_physics_step_debug: bad N");
-  physics_kernel<<<N, 32, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, 1, to_pe(per_env), nullptr, dump);
+  physics_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, 1, to_pe(per_env), nullptr, dump);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

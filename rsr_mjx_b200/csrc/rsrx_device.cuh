@@ -57,6 +57,7 @@ struct DModel {
   // block permutation for the Cholesky factorisations + structurally non-zero entries of H
   int pos_of_dof[NV], dof_of_pos[NV], blk_start[NV], blk_end[NV], nhent;
   unsigned char hent_i[NTRI], hent_j[NTRI];
+  unsigned char tri_ri[NTRI], tri_rj[NTRI];  // row-major lower-triangle enumeration t -> (ri, rj), ri >= rj
   // geoms
   int geom_type[NG], geom_bodyid[NG], geom_static[NG];
   float geom_pos[NG][3], geom_quat[NG][4], geom_size[NG][3], geom_friction[NG][3];

@@ -190,45 +190,46 @@ __device__ __noinline__ void com_pos(const DModel* __restrict__ dm, float* sm, i
 // diagonal blocks is structurally zero and never touched).  A's lower triangle
 // (leading dim LD) is overwritten by its Cholesky factor; x is an nv-vector in
 // dof order.  COMPACT code on purpose (the kernel is instruction-fetch bound, see
-// profiles/): rolled loops, lane p owns row p, which lives in shared memory
-// (stride LD = 21 words: conflict-free) and is touched by that lane only;
-// whatever crosses lanes (pivot, column k) travels by shuffle, so the
-// factorisation needs no barriers.
+// profiles/): rolled right-looking factorisation, one pivot per step; the
+// trailing update of step k is spread over the lanes entry by entry (lane t
+// owns entry (i, j) of the trailing triangle — DModel::tri_ri/tri_rj give the
+// row-major enumeration), the pivot column is scaled with one rsqrt (no IEEE
+// sqrt / division subroutines), forward substitution is fused into the pivot
+// step and travels by shuffle.
 __device__ __noinline__ void warp_chol_factor_solve(const DModel* __restrict__ dm, float* A, float* x, int lane) {
   constexpr unsigned FULL = 0xffffffffu;
   const int n = dm->nv;
   const bool own = lane < n;
   const int p = own ? lane : n - 1;  // surplus lanes shadow the last row (reads only)
-  float* row = A + p * LD;
-  const int pend = dm->blk_end[p], pstart = dm->blk_start[p];
   float xi = x[dm->dof_of_pos[p]];
+  float rdiag = 1.f;
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
     const int kend = dm->blk_end[k];
-    const float aik = row[k];
-    const float akk = __shfl_sync(FULL, aik, k);
-    const float d = sqrtf(akk > MJ_MINVAL ? akk : MJ_MINVAL);
+    const float akk = A[k * LD + k];
+    const float rd = rsqrtf(akk > MJ_MINVAL ? akk : MJ_MINVAL);
     const bool in = own && lane > k && lane <= kend;
-    const float l = in ? aik / d : 0.f;
-    if (own && lane == k) row[k] = d;
-    if (in) row[k] = l;
-    const float yk = __shfl_sync(FULL, xi, k) / d;  // forward substitution, fused
+    const float l = in ? A[p * LD + k] * rd : 0.f;
+    if (in) A[p * LD + k] = l;
+    if (own && lane == k) { A[k * LD + k] = akk * rd; rdiag = rd; }
+    const float yk = __shfl_sync(FULL, xi, k) * rd;  // forward substitution, fused
     xi = (own && lane == k) ? yk : xi - l * yk;
-#pragma unroll 2
-    for (int j = k + 1; j <= kend; ++j) {
-      const float lj = __shfl_sync(FULL, l, j);
-      if (in && j <= lane) row[j] -= l * lj;
+    RSRX_SYNC();
+    const int m = kend - k, nt = (m * (m + 1)) >> 1;
+#pragma unroll 1
+    for (int t = lane; t < nt; t += 32) {
+      const int i = k + 1 + dm->tri_ri[t], j = k + 1 + dm->tri_rj[t];
+      A[i * LD + j] -= A[i * LD + k] * A[j * LD + k];
     }
+    RSRX_SYNC();
   }
-  RSRX_SYNC();
   // backward: L^T x = y, column-oriented; lane p reads L[k][p] (row k is contiguous)
 #pragma unroll 1
   for (int k = n - 1; k >= 0; --k) {
-    const float xk = __shfl_sync(FULL, xi, k) / A[k * LD + k];
+    const float xk = __shfl_sync(FULL, xi, k) * __shfl_sync(FULL, rdiag, k);
     if (own && lane == k) xi = xk;
     else if (own && lane < k && lane >= dm->blk_start[k]) xi -= A[k * LD + p] * xk;
   }
-  (void)pend; (void)pstart;
   if (own) x[dm->dof_of_pos[p]] = xi;
   RSRX_SYNC();
 }
@@ -1046,8 +1047,12 @@ __device__ __noinline__ float ctx_create(const DModel* __restrict__ dm, float* s
 struct LSPoint { float alpha, cost, d0, d1; };
 
 // solver.py::_linesearch with _LSPoint.create evaluated for three alphas per pass
-// over the rows (one inlined evaluation site: the two start-up points go through
-// the same code).  Returns the number of bracketing iterations.
+// over the rows.  The loop body is kept small enough for the L0 instruction cache
+// (the kernel is instruction-fetch bound): sparse rows (one per lane) live in
+// registers in the general piecewise form, contact rows (one-sided quadratics) are
+// streamed from shared memory, the nine partial sums are reduced by one rolled
+// butterfly, and the two start-up points go through the same evaluation code.
+// Returns the number of bracketing iterations.
 __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon, float gauss) {
   const int nv = dm->nv, nrow = nsr + 6 * ncon;
   float s2 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -1063,58 +1068,64 @@ __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm,
   const float gtol = dm->tolerance * dm->ls_tolerance * smag;
   const float qg0 = gauss, qg1 = warp_sum(g1), qg2 = 0.5f * warp_sum(g2);
   mul_J(dm, sm, lane, nsr, ncon, sm + ar::V_SEARCH, sm + ar::E_JV);
+  // sparse row of this lane, general piecewise form (zero contribution when lane >= nsr)
+  float s_ja = 0.f, s_jv = 0.f, s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_lm = 0.f, s_lp = 0.f, s_l1 = 0.f;
+  float s_lo = 0.f, s_hi = 0.f;  // empty quadratic zone
+  if (lane < nsr) {
+    const float ja = sm[ar::E_JAREF + lane], jv = sm[ar::E_JV + lane], D = sm[ar::E_D + lane];
+    const RowShape s = row_shape(sm, lane, nsr);
+    s_ja = ja; s_jv = jv; s_lo = s.lo; s_hi = s.hi;
+    s_c0 = 0.5f * ja * ja * D; s_c1 = jv * ja * D; s_c2 = 0.5f * jv * jv * D;
+    s_lm = s.fl * (-0.5f * s.rf - ja); s_lp = s.fl * (-0.5f * s.rf + ja); s_l1 = s.fl * jv;
+  }
   LSPoint p0, lo, hi;
   p0.alpha = p0.cost = p0.d0 = p0.d1 = 0.f;
   lo = hi = p0;
-  float al0 = 0.f, al1 = 0.f, al2 = 0.f;
+  float al[3] = {0.f, 0.f, 0.f};
   int phase = 0, it = 0;
 #pragma unroll 1
   for (;;) {
     // ---- _LSPoint.create x 3
-    float q00 = 0.f, q01 = 0.f, q02 = 0.f, q10 = 0.f, q11 = 0.f, q12 = 0.f, q20 = 0.f, q21 = 0.f, q22 = 0.f;
-#pragma unroll 1
-    for (int r = lane; r < nrow; r += 32) {
-      const float ja = sm[ar::E_JAREF + r], jv = sm[ar::E_JV + r], D = sm[ar::E_D + r];
-      const RowShape s = row_shape(sm, r, nsr);
-      const float c0 = 0.5f * ja * ja * D, c1 = jv * ja * D, c2 = 0.5f * jv * jv * D;
-      const float lm = s.fl * (-0.5f * s.rf - ja), lp = s.fl * (-0.5f * s.rf + ja), l1 = s.fl * jv;
-      {
-        const float x = __fadd_rn(ja, __fmul_rn(al0, jv));
-        const bool quad = x > s.lo && x < s.hi, below = x <= s.lo;
-        q00 += quad ? c0 : (below ? lm : lp); q01 += quad ? c1 : (below ? -l1 : l1); q02 += quad ? c2 : 0.f;
-      }
-      {
-        const float x = __fadd_rn(ja, __fmul_rn(al1, jv));
-        const bool quad = x > s.lo && x < s.hi, below = x <= s.lo;
-        q10 += quad ? c0 : (below ? lm : lp); q11 += quad ? c1 : (below ? -l1 : l1); q12 += quad ? c2 : 0.f;
-      }
-      {
-        const float x = __fadd_rn(ja, __fmul_rn(al2, jv));
-        const bool quad = x > s.lo && x < s.hi, below = x <= s.lo;
-        q20 += quad ? c0 : (below ? lm : lp); q21 += quad ? c1 : (below ? -l1 : l1); q22 += quad ? c2 : 0.f;
-      }
+    float q[9];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float x = __fadd_rn(s_ja, __fmul_rn(al[a], s_jv));
+      const bool quad = x > s_lo && x < s_hi, below = x <= s_lo;
+      q[3 * a] = quad ? s_c0 : (below ? s_lm : s_lp);
+      q[3 * a + 1] = quad ? s_c1 : (below ? -s_l1 : s_l1);
+      q[3 * a + 2] = quad ? s_c2 : 0.f;
     }
-    LSPoint pt[3];
-    {
-      const float al[3] = {al0, al1, al2};
-      const float t0[3] = {warp_sum(q00) + qg0, warp_sum(q10) + qg0, warp_sum(q20) + qg0};
-      const float t1[3] = {warp_sum(q01) + qg1, warp_sum(q11) + qg1, warp_sum(q21) + qg1};
-      const float t2[3] = {warp_sum(q02) + qg2, warp_sum(q12) + qg2, warp_sum(q22) + qg2};
+#pragma unroll 1
+    for (int r = nsr + lane; r < nrow; r += 32) {
+      const float ja = sm[ar::E_JAREF + r], jv = sm[ar::E_JV + r], D = sm[ar::E_D + r];
+      const float c0 = 0.5f * ja * ja * D, c1 = jv * ja * D, c2 = 0.5f * jv * jv * D;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        // No FMA contraction: with fused multiply-adds the derivative at a Newton iterate no longer rounds to
-        // the value that ends MJX's bracketing and the loop runs to ls_iterations (measured 100 vs 28
-        // line-search iterations per substep).  Mirrors the oracle's unfused arithmetic.
-        pt[a].alpha = al[a];
-        pt[a].cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(al[a], al[a]), t2[a]), __fmul_rn(al[a], t1[a])), t0[a]);
-        pt[a].d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, al[a]), t2[a]), t1[a]);
-        pt[a].d1 = __fadd_rn(__fmul_rn(2.f, t2[a]), (t2[a] == 0.f ? MJ_MINVAL : 0.f));
+        const float x = __fadd_rn(ja, __fmul_rn(al[a], jv));
+        if (x < 0.f) { q[3 * a] += c0; q[3 * a + 1] += c1; q[3 * a + 2] += c2; }
       }
+    }
+#pragma unroll 1
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+    }
+    LSPoint pt[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      // No FMA contraction: with fused multiply-adds the derivative at a Newton iterate no longer rounds to the
+      // value that ends MJX's bracketing and the loop runs to ls_iterations (measured 100 vs 28 line-search
+      // iterations per substep).  Mirrors the oracle's unfused arithmetic.
+      const float t0 = q[3 * a] + qg0, t1 = q[3 * a + 1] + qg1, t2 = q[3 * a + 2] + qg2;
+      pt[a].alpha = al[a];
+      pt[a].cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(al[a], al[a]), t2), __fmul_rn(al[a], t1)), t0);
+      pt[a].d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, al[a]), t2), t1);
+      pt[a].d1 = __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f));
     }
     // ---- bracketing logic
     if (phase == 0) {
       p0 = pt[0];
-      al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1;
+      al[0] = al[1] = al[2] = p0.alpha - p0.d0 / p0.d1;
       phase = 1;
       continue;
     }
@@ -1143,9 +1154,9 @@ __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm,
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (done) break;
-    al0 = lo.alpha - lo.d0 / lo.d1;
-    al1 = hi.alpha - hi.d0 / hi.d1;
-    al2 = 0.5f * (lo.alpha + hi.alpha);
+    al[0] = lo.alpha - lo.d0 / lo.d1;
+    al[1] = hi.alpha - hi.d0 / hi.d1;
+    al[2] = 0.5f * (lo.alpha + hi.alpha);
   }
   const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
   const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
