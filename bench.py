@@ -147,7 +147,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from rsr_mjx_b200 import prng
+    from rsr_mjx_b200 import sharding
     from rsr_mjx_b200.envs import AirbotPlayBase
 
     rank = int(os.environ.get("RANK", "0"))
@@ -163,7 +163,7 @@ def main():
 
     env = AirbotPlayBase(args.kind, num_envs=N, episode_length=1200, device=dev)
     # env i of the global job = rank * N + i: disjoint reset keys per rank, no communication
-    keys = prng.split(prng.PRNGKey(0), N * world)[rank * N:(rank + 1) * N]
+    keys = sharding.shard_keys(0, N, rank, world)
     state = env.reset(keys)
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     actions = torch.rand(W + K, N, env.action_size, device=dev, generator=gen) * 2 - 1
@@ -217,10 +217,7 @@ def main():
     sampler.join(timeout=2)
     status_bad = int((state._buf["status"] != 0).sum().item())
 
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms = sharding.reduce_max([total_ms, e2e_ms], device=dev)
     if rank == 0:
         peak, peak_src = read_peaks()
         value = N * world * K / (total_ms * 1e-3)
