@@ -200,7 +200,11 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
         if (!placed[j] && comp[j] == comp[i]) { placed[j] = true; d.pos_of_dof[j] = pos; d.dof_of_pos[pos] = j; pos++; }
       for (int q = start; q < pos; q++) { d.blk_start[q] = start; d.blk_end[q] = pos - 1; }
     }
-    { int t = 0; for (int ri = 0; ri < NV && t < NTRI; ri++) for (int rj = 0; rj <= ri && t < NTRI; rj++) { d.tri_ri[t] = (unsigned char)ri; d.tri_rj[t] = (unsigned char)rj; t++; } }
+    for (int e = 0; e < d.ntri; e++) {
+      int i = d.tri_i[e], j = d.tri_j[e], pi = d.pos_of_dof[i], pj = d.pos_of_dof[j];
+      d.tri_src[e] = (unsigned short)(i * LD + j);
+      d.tri_dst[e] = (unsigned short)((pi > pj ? pi : pj) * LD + (pi > pj ? pj : pi));
+    }
     d.nhent = 0;
     for (int i = 0; i < b.nv; i++)
       for (int j = 0; j <= i; j++)

@@ -57,7 +57,7 @@ struct DModel {
   // block permutation for the Cholesky factorisations + structurally non-zero entries of H
   int pos_of_dof[NV], dof_of_pos[NV], blk_start[NV], blk_end[NV], nhent;
   unsigned char hent_i[NTRI], hent_j[NTRI];
-  unsigned char tri_ri[NTRI], tri_rj[NTRI];  // row-major lower-triangle enumeration t -> (ri, rj), ri >= rj
+  unsigned short tri_src[NTRI], tri_dst[NTRI];  // M[i][j] offset -> permuted H offset, per lower-triangle entry
   // geoms
   int geom_type[NG], geom_bodyid[NG], geom_static[NG];
   float geom_pos[NG][3], geom_quat[NG][4], geom_size[NG][3], geom_friction[NG][3];
@@ -123,9 +123,10 @@ constexpr int V_MGRAD = V_GRAD + NV;
 constexpr int V_SEARCH = V_MGRAD + NV;
 constexpr int V_MV = V_SEARCH + NV;
 constexpr int V_TMP = V_MV + NV;
+constexpr int V_RDIAG = V_TMP + NV;  // 1 / L_kk of the factor in HH
 // contacts
 constexpr int CSTRIDE = 24;
-constexpr int CON = V_TMP + NV;
+constexpr int CON = V_RDIAG + NV;
 constexpr int BROW = CON + MAXC * CSTRIDE;  // [c][4][nv]
 constexpr int UB = BROW + MAXC * 4 * NV;    // [c][4] base-row scratch
 constexpr int CW = UB + MAXC * 4;           // [c][8] per-contact Hessian weights

@@ -71,8 +71,12 @@ __device__ void get_obs(const DModel* __restrict__ dm, float* sm, const float* i
 
 // Warps per CTA: one env per warp, warps are independent (only __syncwarp).  Single-warp CTAs all land on
 // the same SM sub-partition (warp id within the CTA selects the scheduler), leaving 3 of the 4 schedulers
-// idle — measured 0.6 IPC/SM whatever the occupancy — so a CTA carries WPB = 4 envs.
-constexpr int WPB = 4;
+// idle — so a CTA carries WPB envs; with the per-substep phase barrier (rsrx_physics.cuh) WPB = 8 = one CTA
+// per SM keeps all resident warps in the same code region (measured 9.5 -> 6.3 ms at 8192 envs).
+#ifndef RSRX_WPB
+#define RSRX_WPB 8
+#endif
+constexpr int WPB = RSRX_WPB;
 
 struct StatePtrs {
   float *data, *first_data, *obs, *first_obs, *reward, *done, *info, *metrics;
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
   load_env(dm, sm, lane, e, row, pe);
   SolverDims sd;
   int status = 0;
-  forward(dm, sm, lane, &sd, &status);
+  forward<false>(dm, sm, lane, &sd, &status);
   for (int i = lane; i < dm->nu; i += 32) sm[ar::CTRL + i] = ctrl[(size_t)e * dm->nu + i];
   RSRX_SYNC();
   store_env(dm, sm, lane, row, 0.f);
@@ -145,7 +149,10 @@ __global__ void __launch_bounds__(32 * WPB) step_kernel(const DModel* __restrict
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * WPB + wib;
   float* sm = smem + wib * ar::TOTAL;
-  if (e >= N) return;
+  if (e >= N) {
+    for (int f = 0; f < dm->n_frames * kPhaseBarriers; ++f) __syncthreads();  // shadow the phase barriers
+    return;
+  }
   const rsrx_layout& L = dm->lay;
   const int kind = dm->env_kind;
   float* row = st.data + (size_t)e * L.data_stride;
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(32 * WPB) step_kernel(const DModel* __restrict
   int status = 0;
   SolverDims sd;
   for (int f = 0; f < dm->n_frames; ++f) {
-    forward(dm, sm, lane, &sd, &status);
+    forward<true>(dm, sm, lane, &sd, &status);
     implicit_advance(dm, sm, lane);
     time += dm->timestep;
   }
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
   sd.nsr = sd.ncon = sd.nrow = 0;
   int niter = 0;
   for (int f = 0; f < nsteps; ++f) {
-    niter = forward(dm, sm, lane, &sd, &status);
+    niter = forward<false>(dm, sm, lane, &sd, &status);
     if (dump) {
       float* dp = dump + (size_t)e * dbg::STRIDE;
       const int nv = dm->nv;

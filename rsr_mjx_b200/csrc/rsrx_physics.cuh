@@ -184,53 +184,71 @@ __device__ __noinline__ void com_pos(const DModel* __restrict__ dm, float* sm, i
   RSRX_SYNC();
 }
 
-// x <- A^-1 x for an SPD nv x nv matrix A held in the BLOCK-PERMUTED dof order
-// (DModel::pos_of_dof: dofs that can ever be coupled — same kinematic tree or a
-// collision pair between their trees — are contiguous; everything outside the
-// diagonal blocks is structurally zero and never touched).  A's lower triangle
-// (leading dim LD) is overwritten by its Cholesky factor; x is an nv-vector in
-// dof order.  COMPACT code on purpose (the kernel is instruction-fetch bound, see
-// profiles/): rolled right-looking factorisation, one pivot per step; the
-// trailing update of step k is spread over the lanes entry by entry (lane t
-// owns entry (i, j) of the trailing triangle — DModel::tri_ri/tri_rj give the
-// row-major enumeration), the pivot column is scaled with one rsqrt (no IEEE
-// sqrt / division subroutines), forward substitution is fused into the pivot
-// step and travels by shuffle.
-__device__ __noinline__ void warp_chol_factor_solve(const DModel* __restrict__ dm, float* A, float* x, int lane) {
+// Cholesky factorisation / solves of an SPD nv x nv matrix A held in the
+// BLOCK-PERMUTED dof order (DModel::pos_of_dof: dofs that can ever be coupled —
+// same kinematic tree or a collision pair between their trees — are contiguous;
+// everything outside the diagonal blocks is structurally zero and never touched).
+// A's lower triangle (leading dim LD) is overwritten by its factor; 1/L_kk goes to
+// ar::V_RDIAG.  COMPACT code on purpose (the kernel is instruction-fetch bound, see
+// profiles/): rolled right-looking factorisation; lane p owns row p, which lives in
+// shared memory (stride LD = 21 words: conflict-free) and is touched by that lane
+// only; whatever crosses lanes (pivot, column k) travels by shuffle, so there are
+// no barriers in the dependency chain; the pivot column is scaled by one rsqrt
+// (no IEEE sqrt / division subroutines).
+__device__ __noinline__ void warp_chol_factor(const DModel* __restrict__ dm, float* sm, int lane) {
   constexpr unsigned FULL = 0xffffffffu;
+  float* A = sm + ar::HH;
   const int n = dm->nv;
   const bool own = lane < n;
   const int p = own ? lane : n - 1;  // surplus lanes shadow the last row (reads only)
-  float xi = x[dm->dof_of_pos[p]];
+  float* row = A + p * LD;
+  const int pend = dm->blk_end[p];
   float rdiag = 1.f;
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    const int kend = dm->blk_end[k];
-    const float akk = A[k * LD + k];
+    const int kend = __shfl_sync(FULL, pend, k);
+    const float aik = row[k];
+    const float akk = __shfl_sync(FULL, aik, k);
     const float rd = rsqrtf(akk > MJ_MINVAL ? akk : MJ_MINVAL);
     const bool in = own && lane > k && lane <= kend;
-    const float l = in ? A[p * LD + k] * rd : 0.f;
-    if (in) A[p * LD + k] = l;
-    if (own && lane == k) { A[k * LD + k] = akk * rd; rdiag = rd; }
-    const float yk = __shfl_sync(FULL, xi, k) * rd;  // forward substitution, fused
-    xi = (own && lane == k) ? yk : xi - l * yk;
-    RSRX_SYNC();
-    const int m = kend - k, nt = (m * (m + 1)) >> 1;
-#pragma unroll 1
-    for (int t = lane; t < nt; t += 32) {
-      const int i = k + 1 + dm->tri_ri[t], j = k + 1 + dm->tri_rj[t];
-      A[i * LD + j] -= A[i * LD + k] * A[j * LD + k];
+    const float l = in ? aik * rd : 0.f;
+    if (in) row[k] = l;
+    if (own && lane == k) { row[k] = akk * rd; rdiag = rd; }
+#pragma unroll 2
+    for (int j = k + 1; j <= kend; ++j) {
+      const float lj = __shfl_sync(FULL, l, j);
+      if (in && j <= lane) row[j] -= l * lj;
     }
-    RSRX_SYNC();
   }
-  // backward: L^T x = y, column-oriented; lane p reads L[k][p] (row k is contiguous)
+  if (own) sm[ar::V_RDIAG + lane] = rdiag;
+  RSRX_SYNC();
+}
+
+// x <- (L L^T)^-1 x with the factor left in ar::HH by warp_chol_factor; x is an
+// nv-vector in dof order.
+__device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, float* sm, float* x, int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const float* A = sm + ar::HH;
+  const int n = dm->nv;
+  const bool own = lane < n;
+  const int p = own ? lane : n - 1;
+  const int pstart = dm->blk_start[p], pend = dm->blk_end[p], dof = dm->dof_of_pos[p];
+  const float rdiag = sm[ar::V_RDIAG + p];
+  const float* row = A + p * LD;
+  float xi = x[dof];
 #pragma unroll 1
-  for (int k = n - 1; k >= 0; --k) {
-    const float xk = __shfl_sync(FULL, xi, k) * __shfl_sync(FULL, rdiag, k);
-    if (own && lane == k) xi = xk;
-    else if (own && lane < k && lane >= dm->blk_start[k]) xi -= A[k * LD + p] * xk;
+  for (int k = 0; k < n; ++k) {  // forward: L y = b (row-oriented, own row)
+    const float yk = __shfl_sync(FULL, xi * rdiag, k);
+    if (own && lane == k) xi = yk;
+    else if (own && lane > k && k >= pstart) xi -= row[k] * yk;
   }
-  if (own) x[dm->dof_of_pos[p]] = xi;
+#pragma unroll 1
+  for (int k = n - 1; k >= 0; --k) {  // backward: L^T x = y (column-oriented: row k is contiguous over lanes)
+    const float xk = __shfl_sync(FULL, xi * rdiag, k);
+    if (own && lane == k) xi = xk;
+    else if (own && lane < k && k <= pend) xi -= A[k * LD + p] * xk;
+  }
+  if (own) x[dof] = xi;
   RSRX_SYNC();
 }
 
@@ -238,11 +256,10 @@ __device__ __noinline__ void warp_chol_factor_solve(const DModel* __restrict__ d
 __device__ __noinline__ void copy_M_permuted(const DModel* __restrict__ dm, float* sm, int lane, const float* damp, float dt) {
 #pragma unroll 1
   for (int e = lane; e < dm->ntri; e += 32) {
-    const int i = dm->tri_i[e], j = dm->tri_j[e];
-    const int pi = dm->pos_of_dof[i], pj = dm->pos_of_dof[j];
-    float v = sm[ar::MM + i * LD + j];
-    if (damp && i == j) v += dt * damp[i];
-    sm[ar::HH + max(pi, pj) * LD + min(pi, pj)] = v;
+    const int src = dm->tri_src[e], dst = dm->tri_dst[e];
+    float v = sm[ar::MM + src];
+    if (damp && dm->tri_i[e] == dm->tri_j[e]) v += dt * damp[dm->tri_i[e]];
+    sm[ar::HH + dst] = v;
   }
   RSRX_SYNC();
 }
@@ -840,7 +857,8 @@ __device__ __noinline__ void velocity_and_forces(const DModel* __restrict__ dm, 
   }
   // factor_m + solve_m: qacc_smooth = M^-1 qfrc_smooth (factor a scratch copy of M; H is rebuilt later)
   copy_M_permuted(dm, sm, lane, nullptr, 0.f);
-  warp_chol_factor_solve(dm, sm + ar::HH, sm + ar::V_QACCS, lane);
+  warp_chol_factor(dm, sm, lane);
+  warp_chol_solve(dm, sm, sm + ar::V_QACCS, lane);
 }
 
 // ---------------------------------------------------------------------- solver
@@ -906,9 +924,10 @@ __device__ __forceinline__ RowShape row_shape(const float* sm, int r, int nsr) {
 
 // solver.py::_update_constraint.  Returns the total cost; writes E_ACT, qfrc_constraint.
 __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon,
-                                                float* gauss_out) {
+                                                float* gauss_out, bool* changed_out) {
   const int nv = dm->nv, nrow = nsr + 6 * ncon;
   float cost = 0.f;
+  bool changed = false;
 #pragma unroll 1
   for (int r = lane; r < nrow; r += 32) {
     const float ja = sm[ar::E_JAREF + r], D = sm[ar::E_D + r];
@@ -917,9 +936,12 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
     const bool below = ja <= s.lo;
     const float f = quad ? -D * ja : (below ? s.fl : -s.fl);
     cost += quad ? 0.5f * D * ja * ja : s.fl * (-0.5f * s.rf + (below ? -ja : ja));
-    sm[ar::E_ACT + r] = quad ? 1.f : 0.f;
+    const float actf = quad ? 1.f : 0.f;
+    changed |= sm[ar::E_ACT + r] != actf;
+    sm[ar::E_ACT + r] = actf;
     sm[ar::E_JV + r] = f;  // E_JV doubles as the force array between line searches
   }
+  *changed_out = __any_sync(0xffffffffu, changed);
   RSRX_SYNC();
   // contact forces in base-row space: g0 = sum f, g_{1+k} = mu_k (f_{2k} - f_{2k+1})
 #pragma unroll 1
@@ -964,12 +986,18 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
 
 // solver.py::_update_gradient (Newton): grad, H = M + J^T diag(D*active) J (in
 // the block-permuted dof order), Cholesky, Mgrad = H^-1 grad
-__device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon) {
+__device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon,
+                                             bool reuse_factor) {
   const int nv = dm->nv;
   if (lane < nv) {
     const float g = sm[ar::V_MA + lane] - sm[ar::V_SMOOTH + lane] - sm[ar::V_QFRCC + lane];
     sm[ar::V_GRAD + lane] = g;
     sm[ar::V_MGRAD + lane] = g;
+  }
+  if (reuse_factor) {  // same active set as the previous iteration: H, hence its factor in ar::HH, is unchanged
+    RSRX_SYNC();
+    warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane);
+    return;
   }
   copy_M_permuted(dm, sm, lane, nullptr, 0.f);
   // per-contact weights of the 4x4 base-row Gram form: W00 = sum_r w_r,
@@ -1027,7 +1055,8 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
     sm[ar::HH + max(pi, pj) * LD + min(pi, pj)] += h;
   }
   RSRX_SYNC();
-  warp_chol_factor_solve(dm, sm + ar::HH, sm + ar::V_MGRAD, lane);
+  warp_chol_factor(dm, sm, lane);
+  warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane);
 }
 
 // _Context.create: qacc <- src, Jaref, Ma, constraint update.  Returns cost.
@@ -1041,7 +1070,8 @@ __device__ __noinline__ float ctx_create(const DModel* __restrict__ dm, float* s
   for (int r = lane; r < nrow; r += 32) sm[ar::E_JAREF + r] -= sm[ar::E_AREF + r];
   mul_M(dm, sm, lane, sm + ar::V_QACC, sm + ar::V_MA);
   RSRX_SYNC();
-  return update_constraint(dm, sm, lane, nsr, ncon, gauss);
+  bool changed;
+  return update_constraint(dm, sm, lane, nsr, ncon, gauss, &changed);
 }
 
 struct LSPoint { float alpha, cost, d0, d1; };
@@ -1188,9 +1218,10 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
   float prev_cost = INFINITY;
   const float scale = 1.f / (dm->meaninertia * (float)(nv > 1 ? nv : 1));
   int niter = 0, ls_total = 0;
+  bool changed = true;
 #pragma unroll 1
   for (;;) {
-    update_gradient(dm, sm, lane, nsr, ncon);
+    update_gradient(dm, sm, lane, nsr, ncon, !changed);
     if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
     RSRX_SYNC();
     const float improvement = (prev_cost - cost) * scale;
@@ -1203,7 +1234,7 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
     if (done) break;
     ls_total += linesearch(dm, sm, lane, nsr, ncon, gauss);
     prev_cost = cost;
-    cost = update_constraint(dm, sm, lane, nsr, ncon, &gauss);
+    cost = update_constraint(dm, sm, lane, nsr, ncon, &gauss, &changed);
     niter++;
   }
   if (niter >= dm->iterations) *status |= RSRX_STATUS_SOLVER_CAP;
@@ -1212,16 +1243,38 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
   return niter | (ls_total << 8);
 }
 
+// Phase barriers (step_kernel only).  The kernel is bound by instruction delivery: the L1 instruction
+// cache hit rate is 60 % when the CTA's warps sit in different phases, because the one-shot phases stream
+// ~130 KB of code per substep through it and evict the solver's loops.  Re-aligning the warps of a CTA at
+// phase boundaries lets one fetch serve all of them.  RSRX_SYNC_MASK selects the boundaries (bit 0: substep
+// start, 1: collision, 2: make_constraint, 3: velocity/forces, 4: solve, 5: integrate).
+#ifndef RSRX_SYNC_MASK
+#define RSRX_SYNC_MASK 1  // measured: the substep-start barrier alone is best (6.30 ms vs 6.46-6.49 with more)
+#endif
+constexpr int kPhaseBarriers = __builtin_popcount(RSRX_SYNC_MASK & 0x3f);
+template <bool SYNC>
+__device__ __forceinline__ void phase_barrier(int bit) {
+  if (SYNC && ((RSRX_SYNC_MASK >> bit) & 1)) __syncthreads();
+}
+
 // forward.py::forward.  Returns niter; fills dims.
-__device__ int forward(const DModel* __restrict__ dm, float* sm, int lane, SolverDims* sd, int* status) {
+template <bool SYNC>
+__device__ __forceinline__ int forward(const DModel* __restrict__ dm, float* sm, int lane, SolverDims* sd, int* status) {
+  phase_barrier<SYNC>(0);
   kinematics(dm, sm, lane);
   com_pos(dm, sm, lane);
   crb_and_factor(dm, sm, lane);
+  phase_barrier<SYNC>(1);
   const int ncon = collision(dm, sm, lane, status);
+  phase_barrier<SYNC>(2);
   const int nsr = make_constraint(dm, sm, lane, ncon);
   sd->nsr = nsr; sd->ncon = ncon; sd->nrow = nsr + 6 * ncon;
+  phase_barrier<SYNC>(3);
   velocity_and_forces(dm, sm, lane);
-  return solve(dm, sm, lane, nsr, ncon, status);
+  phase_barrier<SYNC>(4);
+  const int r = solve(dm, sm, lane, nsr, ncon, status);
+  phase_barrier<SYNC>(5);
+  return r;
 }
 
 // forward.py::implicit + _advance (implicitfast; only dof damping contributes to qDeriv)
@@ -1230,7 +1283,8 @@ __device__ __noinline__ void implicit_advance(const DModel* __restrict__ dm, flo
   const float dt = dm->timestep;
   if (lane < nv) sm[ar::V_TMP + lane] = sm[ar::V_SMOOTH + lane] + sm[ar::V_QFRCC + lane];
   copy_M_permuted(dm, sm, lane, sm + ar::DAMP, dt);
-  warp_chol_factor_solve(dm, sm + ar::HH, sm + ar::V_TMP, lane);
+  warp_chol_factor(dm, sm, lane);
+  warp_chol_solve(dm, sm, sm + ar::V_TMP, lane);
   if (lane < nv) sm[ar::QVEL + lane] += sm[ar::V_TMP + lane] * dt;
   RSRX_SYNC();
   if (lane < dm->njnt) {

@@ -1,0 +1,3 @@
+cp rsr_mjx_b200/librsrx.so /tmp/librsrx_orig.so
+for f in rsr_mjx_b200/librsrx_w*.so; do cp $f rsr_mjx_b200/librsrx.so; echo "variant $f"; python tools/dev_gpu_check.py sf 8 1 2>&1 | grep "N=8192"; done
+cp /tmp/librsrx_orig.so rsr_mjx_b200/librsrx.so
