@@ -61,6 +61,12 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
       b.neq > RSRX_MAXEQ)
     return fail("model blob exceeds compiled capacities");
   if (b.neq + b.nv > 32 || b.njnt > 32) return fail("too many constraint candidates for one warp");
+  {
+    int nsr = b.neq;
+    for (int i = 0; i < b.nv; i++) nsr += b.dof_frictionloss[i] > 0;
+    for (int j = 0; j < b.njnt; j++) nsr += (b.jnt_limited[j] && b.jnt_type[j] != RSRX_JNT_FREE);
+    if (nsr > MAXSR) return fail("too many equality / friction / limit rows");
+  }
   d.nbody = b.nbody; d.njnt = b.njnt; d.nq = b.nq; d.nv = b.nv; d.nu = b.nu; d.ngeom = b.ngeom; d.nsite = b.nsite;
   d.npair = b.npair; d.neq = b.neq;
   d.iterations = b.iterations; d.ls_iterations = b.ls_iterations;
@@ -103,6 +109,26 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
     for (int k = 0; k < 4; k++) d.static_xquat[i][k] = (float)sq[i][k];
   }
   d.nlevel = maxdepth + 1;
+  d.ntree = 0;
+  for (int i = 0; i < b.nbody; i++) d.body_treeid[i] = 0;
+  for (int i = 1; i < b.nbody; i++) {
+    if (b.body_parentid[i] == 0) {
+      if (d.ntree >= MAXTREE) return fail("too many kinematic trees");
+      d.tree_dofadr[d.ntree] = 0; d.tree_dofnum[d.ntree] = 0;
+      d.body_treeid[i] = d.ntree++;
+    } else {
+      d.body_treeid[i] = d.body_treeid[b.body_rootid[i]];
+    }
+  }
+  for (int t = 0; t < d.ntree; t++) {
+    int lo = 1 << 30, hi = -1;
+    for (int v = 0; v < b.nv; v++)
+      if (d.body_treeid[b.dof_bodyid[v]] == t) { if (v < lo) lo = v; if (v > hi) hi = v; }
+    if (hi >= 0) {
+      d.tree_dofadr[t] = lo; d.tree_dofnum[t] = hi - lo + 1;
+      for (int v = lo; v <= hi; v++) if (d.body_treeid[b.dof_bodyid[v]] != t) return fail("dofs of a kinematic tree must be contiguous");
+    }
+  }
   for (int j = 0; j < b.njnt; j++) {
     d.jnt_type[j] = b.jnt_type[j]; d.jnt_qposadr[j] = b.jnt_qposadr[j]; d.jnt_dofadr[j] = b.jnt_dofadr[j];
     d.jnt_bodyid[j] = b.jnt_bodyid[j]; d.jnt_limited[j] = b.jnt_limited[j];
@@ -171,6 +197,12 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
     for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = mix * (float)b.geom_solimp[g1][k] + (1.f - mix) * (float)b.geom_solimp[g2][k];
     d.pair_margin[p] = (float)(b.geom_margin[g1] > b.geom_margin[g2] ? b.geom_margin[g1] : b.geom_margin[g2]);
     d.pair_tran[p] = (float)b.body_invweight0[b.geom_bodyid[g1]][0] + (float)b.body_invweight0[b.geom_bodyid[g2]][0];
+    {
+      int b1 = b.geom_bodyid[g1], b2 = b.geom_bodyid[g2];
+      int na = d.body_dofmask[b1] ? d.tree_dofnum[d.body_treeid[b1]] : 0, nb = d.body_dofmask[b2] ? d.tree_dofnum[d.body_treeid[b2]] : 0;
+      if (na && nb && d.body_treeid[b1] == d.body_treeid[b2]) return fail("collision pairs inside one kinematic tree are not supported");
+      if (na + nb > NCOL) return fail("a collision pair couples more dofs than the kernel's Jacobian width");
+    }
   }
   // ---- dof blocks: dofs of one kinematic tree, plus trees joined by a collision pair, form one block of H
   {

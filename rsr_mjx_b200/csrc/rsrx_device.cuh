@@ -17,11 +17,12 @@ constexpr int NG = RSRX_MAXGEOM;  // 32
 constexpr int NS = RSRX_MAXSITE;  // 4
 constexpr int NP = RSRX_MAXPAIR;  // 64
 constexpr int MAXC = 24;          // active-contact cap per env (overflow -> status bit)
-constexpr int MAXSR = 24;         // sparse rows: equality + dof friction + joint limits
+constexpr int MAXSR = 20;         // sparse rows: equality + dof friction + joint limits
 constexpr int MAXROW = MAXSR + 6 * MAXC;
 constexpr int LD = NV + 1;        // padded leading dimension of the dense nv x nv matrices
 constexpr int NTRI = NV * (NV + 1) / 2;
 constexpr int MAXMENT = 96;       // (i, ancestor j) entries of the mass matrix
+constexpr int MAXTREE_ = 4;
 constexpr int OBS_STRIDE = 24;
 constexpr int METRICS_STRIDE = 8;
 
@@ -41,6 +42,7 @@ struct DModel {
   int body_parentid[NB], body_rootid[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB],
       body_depth[NB], body_static[NB], body_subtree_end[NB];
   uint32_t body_dofmask[NB];  // dofs on the path from the body to the world
+  int body_treeid[NB], ntree, tree_dofadr[MAXTREE_], tree_dofnum[MAXTREE_];
   float body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_iquat[NB][4], body_mass[NB], body_inertia[NB][3],
       body_invweight0[NB];
   float static_xpos[NB][3], static_xquat[NB][4];
@@ -83,37 +85,28 @@ struct DModel {
 };
 
 // ---- per-warp shared-memory arena (float words) --------------------------------
+// 16.4 KB per env so that 14 envs (2 CTAs x 7 warps) are resident per SM.  Arrays
+// that only live before the solver (region P) share storage with arrays that only
+// live inside it (region S); mjx's fwd_velocity stages therefore run before
+// collision / make_constraint (same results).
+constexpr int MAXTREE = MAXTREE_;   // kinematic trees (top-level bodies)
+constexpr int NCOL = 14;     // widest contact Jacobian: dofs of the two trees a collision pair joins
 namespace ar {
-constexpr int QPOS = 0;
+constexpr int PTRS = 0;  // 4 device pointers (per-env geom_friction, body_mass, dof_frictionloss, spare)
+constexpr int QPOS = PTRS + 8;
 constexpr int QVEL = QPOS + NQ;
 constexpr int CTRL = QVEL + NV;
 constexpr int WARM = CTRL + NU;
 constexpr int DAMP = WARM + NV;
-constexpr int FLOSS = DAMP + NV;
-constexpr int BMASS = FLOSS + NV;
-constexpr int GFRIC = BMASS + NB;
-constexpr int XPOS = GFRIC + NG * 3;
+constexpr int XPOS = DAMP + NV;
 constexpr int XQUAT = XPOS + NB * 3;
-constexpr int XMAT = XQUAT + NB * 4;
-constexpr int XIPOS = XMAT + NB * 9;
-constexpr int XANCHOR = XIPOS + NB * 3;
-constexpr int XAXIS = XANCHOR + NJ * 3;
-constexpr int GXPOS = XAXIS + NJ * 3;
-constexpr int GXMAT = GXPOS + NG * 3;
-constexpr int SXPOS = GXMAT + NG * 9;
-constexpr int SCOM = SXPOS + NS * 3;
-constexpr int CINERT = SCOM + NB * 3;
-constexpr int CRB = CINERT + NB * 10;  // crb, later cacc/cfrc scratch
-constexpr int CDOF = CRB + NB * 10;
-constexpr int CDOFDOT = CDOF + NV * 6;  // crb_cdof while building M, then cdof_dot
-constexpr int CVEL = CDOFDOT + NV * 6;
-constexpr int MM = CVEL + NB * 6;
-constexpr int HH = MM + NV * LD;
+constexpr int SXPOS = XQUAT + NB * 4;
+constexpr int SCOM = SXPOS + NS * 3;       // subtree com of each kinematic tree root
+constexpr int CDOF = SCOM + MAXTREE * 3;
+constexpr int MM = CDOF + NV * 6;          // lower triangle, packed: M[i][j] at i (i + 1) / 2 + j
+constexpr int HH = MM + NTRI;              // dense, leading dim LD, block-permuted order; also scratch
 // nv-vectors
-constexpr int V_BIAS = HH + NV * LD;
-constexpr int V_PASSIVE = V_BIAS + NV;
-constexpr int V_ACT = V_PASSIVE + NV;
-constexpr int V_SMOOTH = V_ACT + NV;
+constexpr int V_SMOOTH = HH + NV * LD;
 constexpr int V_QACCS = V_SMOOTH + NV;
 constexpr int V_QACC = V_QACCS + NV;
 constexpr int V_QFRCC = V_QACC + NV;
@@ -124,20 +117,16 @@ constexpr int V_SEARCH = V_MGRAD + NV;
 constexpr int V_MV = V_SEARCH + NV;
 constexpr int V_TMP = V_MV + NV;
 constexpr int V_RDIAG = V_TMP + NV;  // 1 / L_kk of the factor in HH
+constexpr int V_ACT = V_TMP;          // qfrc_actuator (debug dump only) shares V_TMP (integration scratch)
 // contacts
-constexpr int CSTRIDE = 24;
+constexpr int CSTRIDE = 21;
 constexpr int CON = V_RDIAG + NV;
-constexpr int BROW = CON + MAXC * CSTRIDE;  // [c][4][nv]
-constexpr int UB = BROW + MAXC * 4 * NV;    // [c][4] base-row scratch
-constexpr int CW = UB + MAXC * 4;           // [c][8] per-contact Hessian weights
+constexpr int BROW = CON + MAXC * CSTRIDE;  // [c][4][NCOL]
 // efc rows
-constexpr int E_D = CW + MAXC * 8;
-constexpr int E_AREF = E_D + MAXROW;
-constexpr int E_JAREF = E_AREF + MAXROW;
-constexpr int E_JV = E_JAREF + MAXROW;
-constexpr int E_ACT = E_JV + MAXROW;
+constexpr int E_AREF = BROW + MAXC * 4 * NCOL;
+constexpr int E_DS = E_AREF + MAXROW;     // D of the sparse rows (contact rows: D in the contact record)
 // sparse-row meta
-constexpr int SR_DOFA = E_ACT + MAXROW;  // int
+constexpr int SR_DOFA = E_DS + MAXSR;     // int
 constexpr int SR_DOFB = SR_DOFA + MAXSR;  // int (-1 = none)
 constexpr int SR_CA = SR_DOFB + MAXSR;
 constexpr int SR_CB = SR_CA + MAXSR;
@@ -145,12 +134,31 @@ constexpr int SR_FLOSS = SR_CB + MAXSR;
 constexpr int SR_TYPE = SR_FLOSS + MAXSR;  // int: 0 equality, 1 friction, 2 limit
 constexpr int SR_RF = SR_TYPE + MAXSR;     // R * frictionloss
 constexpr int OBSBUF = SR_RF + MAXSR;
-constexpr int TOTAL = OBSBUF + OBS_STRIDE;
+constexpr int V_BIAS = OBSBUF;             // qfrc_bias (debug dump only) shares the obs staging buffer
+// ---- union: region P (alive until velocity_and_forces is done) ...
+constexpr int U = OBSBUF + OBS_STRIDE;
+constexpr int XANCHOR = U;
+constexpr int XAXIS = XANCHOR + NJ * 3;
+constexpr int CINERT = XAXIS + NJ * 3;
+constexpr int CRB = CINERT + NB * 10;     // crb while building M, then cacc
+constexpr int CDOFDOT = CRB + NB * 10;    // crb_cdof while building M, then cdof_dot
+constexpr int CVEL = CDOFDOT + NV * 6;
+constexpr int P_END = CVEL + NB * 6;
+// ---- ... and region S (alive from make_constraint's contact pass to the end of the solver)
+constexpr int E_JAREF = U;
+constexpr int E_JV = E_JAREF + MAXROW;
+constexpr int E_ACT = E_JV + MAXROW;
+constexpr int UB = E_ACT + MAXROW;         // [c][4] base-row scratch ...
+constexpr int CW = UB;                     // ... / [c][8] per-contact Hessian weights (never live together)
+constexpr int S_END = CW + MAXC * 8;
+constexpr int TOTAL = (P_END > S_END ? P_END : S_END);
 }  // namespace ar
 
 // contact record fields
 namespace cf {
-constexpr int POS = 0, FRAME = 3, DIST = 12, MU = 13, KIMPD = 16, B = 17, D = 18, BODIES = 19, MASK = 20, ROOTS = 21;
+constexpr int POS = 0, FRAME = 3, DIST = 12, MU = 13, KIMPD = 16, B = 17, D = 18, BODIES = 19, COLS = 20;  // MU: mu, mu, torsion
+// COLS packs the dof ranges of the two kinematic trees the contact joins: a0 | na << 8 | b0 << 16 | nb << 24;
+// Jacobian column c is dof a0 + c (c < na) or b0 + c - na.
 }
 
 // ---- debug dump layout (floats per env) -----------------------------------------

@@ -14,21 +14,28 @@ struct PerEnv {
   const float* dof_frictionloss;
 };
 
-// load per-env model arrays + the dynamic state of env `e` into the arena
+// load the dynamic state of env `e` into the arena; per-env model arrays stay in global memory and
+// are reached through pointers (pre-offset to this env) kept at ar::PTRS
 __device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, int lane, int e, const float* __restrict__ row,
-                         const PerEnv& pe) {
+                                      const PerEnv& pe) {
   const rsrx_layout& L = dm->lay;
+#pragma unroll 1
   for (int i = lane; i < dm->nq; i += 32) sm[ar::QPOS + i] = row[L.qpos + i];
+#pragma unroll 1
   for (int i = lane; i < dm->nv; i += 32) {
     sm[ar::QVEL + i] = row[L.qvel + i];
     sm[ar::WARM + i] = row[L.qacc_warmstart + i];
     sm[ar::DAMP + i] = pe.dof_damping ? pe.dof_damping[(size_t)e * dm->nv + i] : dm->dof_damping[i];
-    sm[ar::FLOSS + i] = pe.dof_frictionloss ? pe.dof_frictionloss[(size_t)e * dm->nv + i] : dm->dof_frictionloss[i];
   }
+#pragma unroll 1
   for (int i = lane; i < dm->nu; i += 32) sm[ar::CTRL + i] = row[L.ctrl + i];
-  for (int i = lane; i < dm->nbody; i += 32) sm[ar::BMASS + i] = pe.body_mass ? pe.body_mass[(size_t)e * dm->nbody + i] : dm->body_mass[i];
-  for (int i = lane; i < dm->ngeom * 3; i += 32)
-    sm[ar::GFRIC + i] = pe.geom_friction ? pe.geom_friction[(size_t)e * dm->ngeom * 3 + i] : dm->geom_friction[i / 3][i % 3];
+  if (lane == 0) {
+    const float** ptrs = reinterpret_cast<const float**>(sm + ar::PTRS);
+    ptrs[0] = pe.geom_friction ? pe.geom_friction + (size_t)e * dm->ngeom * 3 : nullptr;
+    ptrs[1] = pe.body_mass ? pe.body_mass + (size_t)e * dm->nbody : nullptr;
+    ptrs[2] = pe.dof_frictionloss ? pe.dof_frictionloss + (size_t)e * dm->nv : nullptr;
+    ptrs[3] = nullptr;
+  }
   RSRX_SYNC();
 }
 
@@ -42,7 +49,11 @@ __device__ __noinline__ void store_env(const DModel* __restrict__ dm, const floa
   for (int i = lane; i < dm->nbody * 3; i += 32) row[L.xpos + i] = sm[ar::XPOS + i];
   for (int i = lane; i < dm->nbody * 4; i += 32) row[L.xquat + i] = sm[ar::XQUAT + i];
   for (int i = lane; i < dm->nsite * 3; i += 32) row[L.site_xpos + i] = sm[ar::SXPOS + i];
-  for (int i = lane; i < dm->ngeom * 3; i += 32) row[L.geom_xpos + i] = sm[ar::GXPOS + i];
+  for (int g = lane; g < dm->ngeom; g += 32) {
+    float gp[3];
+    geom_pose(dm, sm, g, gp, nullptr);
+    row[L.geom_xpos + g * 3] = gp[0]; row[L.geom_xpos + g * 3 + 1] = gp[1]; row[L.geom_xpos + g * 3 + 2] = gp[2];
+  }
 }
 
 // _get_obs into the arena's OBSBUF (lane 0); info = this env's info row
@@ -52,9 +63,12 @@ __device__ void get_obs(const DModel* __restrict__ dm, float* sm, const float* i
   for (int i = 0; i < 6; i++) obs[n++] = sm[ar::QPOS + dm->joint_qadr[i]];
   const float* site = sm + ar::SXPOS + dm->site_endpoint * 3;
   if (dm->env_kind == RSRX_ENV_T) {
+    float gb[3], gv[3];
+    geom_pose(dm, sm, dm->geom_base, gb, nullptr);
+    geom_pose(dm, sm, dm->geom_vertical, gv, nullptr);
     obs[n++] = site[2];
-    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET + i] - sm[ar::GXPOS + dm->geom_base * 3 + i];
-    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET2 + i] - sm[ar::GXPOS + dm->geom_vertical * 3 + i];
+    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET + i] - gb[i];
+    for (int i = 0; i < 3; i++) obs[n++] = info[RSRX_INFO_TARGET2 + i] - gv[i];
     obs[n++] = info[RSRX_INFO_XITA];
     for (int i = 0; i < 2; i++) obs[n++] = info[RSRX_INFO_NEWPOS + i] - site[i];
   } else {
@@ -74,7 +88,7 @@ __device__ void get_obs(const DModel* __restrict__ dm, float* sm, const float* i
 // idle — so a CTA carries WPB envs; with the per-substep phase barrier (rsrx_physics.cuh) WPB = 8 = one CTA
 // per SM keeps all resident warps in the same code region (measured 9.5 -> 6.3 ms at 8192 envs).
 #ifndef RSRX_WPB
-#define RSRX_WPB 8
+#define RSRX_WPB 7
 #endif
 constexpr int WPB = RSRX_WPB;
 
@@ -115,10 +129,10 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
     for (int i = 0; i < 3; i++) { info[RSRX_INFO_SITE + i] = site[i]; info[RSRX_INFO_OBJ + i] = sm[ar::XPOS + dm->cube_body * 3 + i]; }
     if (dm->env_kind == RSRX_ENV_T) {
       info[RSRX_INFO_NEWPOS] = 0.24739072f; info[RSRX_INFO_NEWPOS + 1] = -0.00496255f;
-      for (int i = 0; i < 3; i++) {
-        info[RSRX_INFO_TARGET + i] = sm[ar::GXPOS + dm->geom_target_base * 3 + i];
-        info[RSRX_INFO_TARGET2 + i] = sm[ar::GXPOS + dm->geom_target_vertical * 3 + i];
-      }
+      float gb[3], gv[3];
+      geom_pose(dm, sm, dm->geom_target_base, gb, nullptr);
+      geom_pose(dm, sm, dm->geom_target_vertical, gv, nullptr);
+      for (int i = 0; i < 3; i++) { info[RSRX_INFO_TARGET + i] = gb[i]; info[RSRX_INFO_TARGET2 + i] = gv[i]; }
       info[RSRX_INFO_TARGET_W] = sm[ar::XQUAT + dm->target_body * 4] * 10.f;
       info[RSRX_INFO_XITA] = 0.2876f;
     } else {
@@ -202,11 +216,13 @@ __global__ void __launch_bounds__(32 * WPB) step_kernel(const DModel* __restrict
     const float W = dm->siet_to_box_reward_weight;
     float* met = st.metrics + (size_t)e * METRICS_STRIDE;
     if (kind == RSRX_ENV_T) {
-      float db[3], dv[3], box[3], tgt[3];
+      float db[3], dv[3], box[3], tgt[3], gb[3], gv[3];
+      geom_pose(dm, sm, dm->geom_base, gb, nullptr);
+      geom_pose(dm, sm, dm->geom_vertical, gv, nullptr);
       for (int i = 0; i < 3; i++) {
-        db[i] = info[RSRX_INFO_TARGET + i] - sm[ar::GXPOS + dm->geom_base * 3 + i];
-        dv[i] = info[RSRX_INFO_TARGET2 + i] - sm[ar::GXPOS + dm->geom_vertical * 3 + i];
-        box[i] = sm[ar::GXPOS + dm->geom_vertical * 3 + i] - sm[ar::GXPOS + dm->geom_base * 3 + i];
+        db[i] = info[RSRX_INFO_TARGET + i] - gb[i];
+        dv[i] = info[RSRX_INFO_TARGET2 + i] - gv[i];
+        box[i] = gv[i] - gb[i];
         tgt[i] = info[RSRX_INFO_TARGET2 + i] - info[RSRX_INFO_TARGET + i];
       }
       float disb = sqrtf(dot3(db, db)), disv = sqrtf(dot3(dv, dv));
@@ -329,7 +345,10 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
     if (dump) {
       float* dp = dump + (size_t)e * dbg::STRIDE;
       const int nv = dm->nv;
-      for (int i = lane; i < nv * nv; i += 32) dp[dbg::M + i] = sm[ar::MM + (i / nv) * LD + (i % nv)];
+      for (int i = lane; i < nv * nv; i += 32) {
+        const int r = i / nv, c = i % nv, hi = r > c ? r : c, lo = r > c ? c : r;
+        dp[dbg::M + i] = sm[ar::MM + ((hi * (hi + 1)) >> 1) + lo];
+      }
       for (int i = lane; i < nv; i += 32) {
         dp[dbg::BIAS + i] = sm[ar::V_BIAS + i];
         dp[dbg::QACC_SMOOTH + i] = sm[ar::V_QACCS + i];

@@ -70,34 +70,6 @@ __device__ __noinline__ void kinematics(const DModel* __restrict__ dm, float* sm
     }
     RSRX_SYNC();
   }
-  if (lane < nbody) {
-    const int b = lane;
-    float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
-    float m[9], t[3];
-    quat_to_mat(m, q);
-    for (int i = 0; i < 9; i++) sm[ar::XMAT + b * 9 + i] = m[i];
-    float ip[3] = {dm->body_ipos[b][0], dm->body_ipos[b][1], dm->body_ipos[b][2]};
-    rotate(t, ip, q);
-    for (int i = 0; i < 3; i++) sm[ar::XIPOS + b * 3 + i] = sm[ar::XPOS + b * 3 + i] + t[i];
-  }
-  if (lane < dm->ngeom) {
-    const int g = lane;
-    if (dm->geom_static[g]) {
-      for (int i = 0; i < 3; i++) sm[ar::GXPOS + g * 3 + i] = dm->geom_static_xpos[g][i];
-      for (int i = 0; i < 9; i++) sm[ar::GXMAT + g * 9 + i] = dm->geom_static_xmat[g][i];
-    } else {
-      const int b = dm->geom_bodyid[g];
-      float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
-      float gp[3] = {dm->geom_pos[g][0], dm->geom_pos[g][1], dm->geom_pos[g][2]};
-      float gq[4] = {dm->geom_quat[g][0], dm->geom_quat[g][1], dm->geom_quat[g][2], dm->geom_quat[g][3]};
-      float t[3], q2[4], m[9];
-      rotate(t, gp, q);
-      for (int i = 0; i < 3; i++) sm[ar::GXPOS + g * 3 + i] = sm[ar::XPOS + b * 3 + i] + t[i];
-      quat_mul(q2, q, gq);
-      quat_to_mat(m, q2);
-      for (int i = 0; i < 9; i++) sm[ar::GXMAT + g * 9 + i] = m[i];
-    }
-  }
   if (lane < dm->nsite) {
     const int s = lane, b = dm->site_bodyid[s];
     float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
@@ -108,31 +80,65 @@ __device__ __noinline__ void kinematics(const DModel* __restrict__ dm, float* sm
   RSRX_SYNC();
 }
 
+// world position of a body's inertial frame origin (xipos), recomputed on demand
+__device__ __forceinline__ void body_xipos(const DModel* __restrict__ dm, const float* sm, int b, float* out) {
+  float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
+  float ip[3] = {dm->body_ipos[b][0], dm->body_ipos[b][1], dm->body_ipos[b][2]}, t[3];
+  rotate(t, ip, q);
+  for (int i = 0; i < 3; i++) out[i] = sm[ar::XPOS + b * 3 + i] + t[i];
+}
+
+// world pose of a geom, recomputed on demand (static geoms come precomputed from the host)
+__device__ __noinline__ void geom_pose(const DModel* __restrict__ dm, const float* sm, int g, float* pos, float* mat) {
+  if (dm->geom_static[g]) {
+    for (int i = 0; i < 3; i++) pos[i] = dm->geom_static_xpos[g][i];
+    if (mat) for (int i = 0; i < 9; i++) mat[i] = dm->geom_static_xmat[g][i];
+    return;
+  }
+  const int b = dm->geom_bodyid[g];
+  float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
+  float gp[3] = {dm->geom_pos[g][0], dm->geom_pos[g][1], dm->geom_pos[g][2]}, t[3];
+  rotate(t, gp, q);
+  for (int i = 0; i < 3; i++) pos[i] = sm[ar::XPOS + b * 3 + i] + t[i];
+  if (mat) {
+    float gq[4] = {dm->geom_quat[g][0], dm->geom_quat[g][1], dm->geom_quat[g][2], dm->geom_quat[g][3]}, q2[4];
+    quat_mul(q2, q, gq);
+    quat_to_mat(mat, q2);
+  }
+}
+
 // smooth.py::com_pos — subtree_com of tree roots, cinert, cdof
 __device__ __noinline__ void com_pos(const DModel* __restrict__ dm, float* sm, int lane) {
   const int nbody = dm->nbody;
+  const float* bmass_e = reinterpret_cast<const float* const*>(sm + ar::PTRS)[1];
   // a root's subtree is the contiguous body range [b, subtree_end)
   if (lane < nbody && lane > 0 && dm->body_rootid[lane] == lane) {
     const int b = lane;
-    float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f;
+    float px = 0.f, py = 0.f, pz = 0.f, ms = 0.f, xi[3];
+#pragma unroll 1
     for (int c = dm->body_subtree_end[b] - 1; c >= b; --c) {  // leaves first, like the reverse tree scan
-      const float mc = sm[ar::BMASS + c];
-      px += sm[ar::XIPOS + c * 3] * mc; py += sm[ar::XIPOS + c * 3 + 1] * mc; pz += sm[ar::XIPOS + c * 3 + 2] * mc;
+      const float mc = bmass_e ? bmass_e[c] : dm->body_mass[c];
+      body_xipos(dm, sm, c, xi);
+      px += xi[0] * mc; py += xi[1] * mc; pz += xi[2] * mc;
       ms += mc;
     }
+    float* sc = sm + ar::SCOM + dm->body_treeid[b] * 3;
     if (ms < MJ_MINVAL) {
-      for (int i = 0; i < 3; i++) sm[ar::SCOM + b * 3 + i] = sm[ar::XIPOS + b * 3 + i];
+      body_xipos(dm, sm, b, xi);
+      sc[0] = xi[0]; sc[1] = xi[1]; sc[2] = xi[2];
     } else {
       const float d = fmaxf(ms, MJ_MINVAL);
-      sm[ar::SCOM + b * 3] = px / d; sm[ar::SCOM + b * 3 + 1] = py / d; sm[ar::SCOM + b * 3 + 2] = pz / d;
+      sc[0] = px / d; sc[1] = py / d; sc[2] = pz / d;
     }
   }
   RSRX_SYNC();
   if (lane < nbody && lane > 0 && !dm->body_static[lane]) {
-    const int b = lane, r = dm->body_rootid[b];
-    float off[3] = {sm[ar::XIPOS + b * 3] - sm[ar::SCOM + r * 3], sm[ar::XIPOS + b * 3 + 1] - sm[ar::SCOM + r * 3 + 1],
-                    sm[ar::XIPOS + b * 3 + 2] - sm[ar::SCOM + r * 3 + 2]};
-    const float ms = sm[ar::BMASS + b];
+    const int b = lane;
+    const float* sc = sm + ar::SCOM + dm->body_treeid[b] * 3;
+    float xi[3];
+    body_xipos(dm, sm, b, xi);
+    float off[3] = {xi[0] - sc[0], xi[1] - sc[1], xi[2] - sc[2]};
+    const float ms = bmass_e ? bmass_e[b] : dm->body_mass[b];
     float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]};
     float iq[4] = {dm->body_iquat[b][0], dm->body_iquat[b][1], dm->body_iquat[b][2], dm->body_iquat[b][3]};
     float q2[4], R[9];
@@ -159,16 +165,18 @@ __device__ __noinline__ void com_pos(const DModel* __restrict__ dm, float* sm, i
   }
   if (lane < dm->nv) {
     const int d = lane, j = dm->dof_jntid[d], b = dm->jnt_bodyid[j], k = d - dm->jnt_dofadr[j];
-    const int r = dm->body_rootid[b], jt = dm->jnt_type[j];
-    float off[3] = {sm[ar::SCOM + r * 3] - sm[ar::XANCHOR + j * 3], sm[ar::SCOM + r * 3 + 1] - sm[ar::XANCHOR + j * 3 + 1],
-                    sm[ar::SCOM + r * 3 + 2] - sm[ar::XANCHOR + j * 3 + 2]};
+    const int jt = dm->jnt_type[j];
+    const float* sc = sm + ar::SCOM + dm->body_treeid[b] * 3;
+    float off[3] = {sc[0] - sm[ar::XANCHOR + j * 3], sc[1] - sm[ar::XANCHOR + j * 3 + 1], sc[2] - sm[ar::XANCHOR + j * 3 + 2]};
     float* cd = sm + ar::CDOF + d * 6;
     if (jt == RSRX_JNT_FREE) {
       if (k < 3) {
         for (int i = 0; i < 6; i++) cd[i] = (i == 3 + k) ? 1.f : 0.f;
       } else {
         const int a = k - 3;
-        float ax[3] = {sm[ar::XMAT + b * 9 + a], sm[ar::XMAT + b * 9 + 3 + a], sm[ar::XMAT + b * 9 + 6 + a]}, c[3];
+        float q[4] = {sm[ar::XQUAT + b * 4], sm[ar::XQUAT + b * 4 + 1], sm[ar::XQUAT + b * 4 + 2], sm[ar::XQUAT + b * 4 + 3]}, m[9];
+        quat_to_mat(m, q);
+        float ax[3] = {m[a], m[3 + a], m[6 + a]}, c[3];
         cross3(c, ax, off);
         cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = c[0]; cd[4] = c[1]; cd[5] = c[2];
       }
@@ -256,8 +264,8 @@ __device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, floa
 __device__ __noinline__ void copy_M_permuted(const DModel* __restrict__ dm, float* sm, int lane, const float* damp, float dt) {
 #pragma unroll 1
   for (int e = lane; e < dm->ntri; e += 32) {
-    const int src = dm->tri_src[e], dst = dm->tri_dst[e];
-    float v = sm[ar::MM + src];
+    const int dst = dm->tri_dst[e];
+    float v = sm[ar::MM + e];  // packed lower triangle: entry e = (tri_i, tri_j)
     if (damp && dm->tri_i[e] == dm->tri_j[e]) v += dt * damp[dm->tri_i[e]];
     sm[ar::HH + dst] = v;
   }
@@ -275,7 +283,7 @@ __device__ __noinline__ void crb_and_factor(const DModel* __restrict__ dm, float
       for (int i = 0; i < 10; i++) acc[i] += sm[ar::CINERT + c * 10 + i];
     for (int i = 0; i < 10; i++) sm[ar::CRB + b * 10 + i] = acc[i];
   }
-  for (int e = lane; e < nv * LD; e += 32) sm[ar::MM + e] = 0.f;
+  for (int e = lane; e < dm->ntri; e += 32) sm[ar::MM + e] = 0.f;
   RSRX_SYNC();
   if (lane < nv) {
     float f[6];
@@ -283,13 +291,13 @@ __device__ __noinline__ void crb_and_factor(const DModel* __restrict__ dm, float
     for (int k = 0; k < 6; k++) sm[ar::CDOFDOT + lane * 6 + k] = f[k];
   }
   RSRX_SYNC();
+#pragma unroll 1
   for (int e = lane; e < dm->nment; e += 32) {
-    const int i = dm->ment_i[e], j = dm->ment_j[e];
+    const int i = dm->ment_i[e], j = dm->ment_j[e];  // j is an ancestor dof of i (j <= i)
     float s = 0.f;
     for (int k = 0; k < 6; k++) s += sm[ar::CDOF + j * 6 + k] * sm[ar::CDOFDOT + i * 6 + k];
     if (i == j) s += dm->dof_armature[i];
-    sm[ar::MM + i * LD + j] = s;
-    sm[ar::MM + j * LD + i] = s;
+    sm[ar::MM + ((i * (i + 1)) >> 1) + j] = s;
   }
   RSRX_SYNC();
 }
@@ -561,8 +569,8 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
       margin = dm->pair_margin[p];
       float s2[3] = {dm->geom_size[g2][0], dm->geom_size[g2][1], dm->geom_size[g2][2]};
       float p1[3], m1[9], p2[3], m2[9];
-      for (int i = 0; i < 3; i++) { p1[i] = sm[ar::GXPOS + g1 * 3 + i]; p2[i] = sm[ar::GXPOS + g2 * 3 + i]; }
-      for (int i = 0; i < 9; i++) { m1[i] = sm[ar::GXMAT + g1 * 9 + i]; m2[i] = sm[ar::GXMAT + g2 * 9 + i]; }
+      geom_pose(dm, sm, g1, p1, m1);
+      geom_pose(dm, sm, g2, p2, m2);
       if (dm->geom_type[g1] == RSRX_GEOM_PLANE) {
         plane_box(p1, m1, p2, m2, s2, dist, pos, nrm);
       } else {
@@ -585,7 +593,13 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
       make_frame(frame, nrm);
       const int b1 = dm->geom_bodyid[g1], b2 = dm->geom_bodyid[g2];
       float mu[3];
-      for (int i = 0; i < 3; i++) mu[i] = fmaxf(sm[ar::GFRIC + g1 * 3 + i], sm[ar::GFRIC + g2 * 3 + i]);
+      const float* gfric_e = reinterpret_cast<const float* const*>(sm + ar::PTRS)[0];
+      for (int i = 0; i < 3; i++)
+        mu[i] = gfric_e ? fmaxf(gfric_e[g1 * 3 + i], gfric_e[g2 * 3 + i]) : fmaxf(dm->geom_friction[g1][i], dm->geom_friction[g2][i]);
+      // dof ranges of the two trees this pair joins (a static body contributes no columns)
+      const int t1 = dm->body_treeid[b1], t2 = dm->body_treeid[b2];
+      const int na = dm->body_dofmask[b1] ? dm->tree_dofnum[t1] : 0, nb = dm->body_dofmask[b2] ? dm->tree_dofnum[t2] : 0;
+      const int cols = (na ? dm->tree_dofadr[t1] : 0) | (na << 8) | ((nb ? dm->tree_dofadr[t2] : 0) << 16) | (nb << 24);
       float solref[2] = {dm->pair_solref[p][0], dm->pair_solref[p][1]}, solimp[5];
       for (int i = 0; i < 5; i++) solimp[i] = dm->pair_solimp[p][i];
       const float tran = dm->pair_tran[p];
@@ -607,7 +621,7 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
         cr[cf::B] = b;
         cr[cf::D] = 1.f / rr;
         cr[cf::BODIES] = __int_as_float(b1 | (b2 << 8) | (g1 << 16) | (g2 << 24));
-        cr[cf::MASK] = __int_as_float((int)(dm->body_dofmask[b1] | dm->body_dofmask[b2]));
+        cr[cf::COLS] = __int_as_float(cols);
         slot++;
       }
     }
@@ -616,6 +630,29 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
   }
   if (ncon > MAXC) ncon = MAXC;
   return ncon;
+}
+
+// UB[c][p] = B[c][p][:] . x over the contact's dof columns (x: nv-vector in shared memory)
+__device__ __noinline__ void mul_B(float* sm, int lane, int ncon, const float* x) {
+#pragma unroll 1
+  for (int t = lane; t < ncon * 4; t += 32) {
+    const int c = t >> 2;
+    const int cols = __float_as_int(sm[ar::CON + c * ar::CSTRIDE + cf::COLS]);
+    const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
+    const float* Bp = sm + ar::BROW + t * NCOL;
+    float s = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < na; i++) s += Bp[i] * x[a0 + i];
+#pragma unroll 1
+    for (int i = 0; i < nb; i++) s += Bp[na + i] * x[b0 + i];
+    sm[ar::UB + t] = s;
+  }
+  RSRX_SYNC();
+}
+
+// D of constraint row r
+__device__ __forceinline__ float row_D(const float* sm, int r, int nsr) {
+  return r < nsr ? sm[ar::E_DS + r] : sm[ar::CON + ((r - nsr) / 6) * ar::CSTRIDE + cf::D];
 }
 
 // ----------------------------------------------------------------- constraints
@@ -658,7 +695,8 @@ __device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float
     const int d = cand - neq;
     if (dm->dof_hasfriction[d]) {
       have = true; type = 1; dofa = d; ca = 1.f; pos = 0.f; invw = dm->dof_invweight0[d];
-      floss = sm[ar::FLOSS + d];
+      const float* floss_e = reinterpret_cast<const float* const*>(sm + ar::PTRS)[2];
+      floss = floss_e ? floss_e[d] : dm->dof_frictionloss[d];
       solref[0] = dm->dof_solref[d][0]; solref[1] = dm->dof_solref[d][1];
       for (int i = 0; i < 5; i++) solimp[i] = dm->dof_solimp[d][i];
     }
@@ -696,7 +734,7 @@ __device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float
     if (dofb >= 0) vel += cb * sm[ar::QVEL + dofb];
     // oracle sums J[d]*qvel[d] in dof order
     if (dofb >= 0 && dofb < dofa) vel = cb * sm[ar::QVEL + dofb] + ca * sm[ar::QVEL + dofa];
-    sm[ar::E_D + r] = 1.f / rr;
+    sm[ar::E_DS + r] = 1.f / rr;
     sm[ar::E_AREF + r] = -b * vel - k * imp * (pos - margin);
     sr_dofa[r] = dofa; sr_dofb[r] = dofb; sr_type[r] = type;
     sm[ar::SR_CA + r] = ca; sm[ar::SR_CB + r] = cb; sm[ar::SR_FLOSS + r] = floss; sm[ar::SR_RF + r] = floss * rr;
@@ -708,53 +746,52 @@ __device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float
     float rr = invw2 * (1.f - imp) / imp;
     if (rr < MJ_MINVAL) rr = MJ_MINVAL;
     const float vel = ca2 * sm[ar::QVEL + dofa2];
-    sm[ar::E_D + r] = 1.f / rr;
+    sm[ar::E_DS + r] = 1.f / rr;
     sm[ar::E_AREF + r] = -b * vel - k * imp * pos2;
     sr_dofa[r] = dofa2; sr_dofb[r] = -1; sr_type[r] = 2;
     sm[ar::SR_CA + r] = ca2; sm[ar::SR_CB + r] = 0.f; sm[ar::SR_FLOSS + r] = 0.f; sm[ar::SR_RF + r] = 0.f;
   }
-  // --- contact base rows B[c][p][dof] (support.jac + frame rotation)
-  for (int t = lane; t < ncon * nv; t += 32) {
-    const int c = t / nv, d = t - c * nv;
+  // --- contact base rows B[c][p][col] (support.jac + frame rotation); column -> dof through cf::COLS
+#pragma unroll 1
+  for (int t = lane; t < ncon * NCOL; t += 32) {
+    const int c = t / NCOL, col = t - c * NCOL;
     const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    const int cols = __float_as_int(cr[cf::COLS]);
+    const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
+    float* B = sm + ar::BROW + c * 4 * NCOL;
+    if (col >= na + nb) { B[col] = B[NCOL + col] = B[2 * NCOL + col] = B[3 * NCOL + col] = 0.f; continue; }
+    const int d = col < na ? a0 + col : b0 + col - na;
     const int bodies = __float_as_int(cr[cf::BODIES]);
     const int b1 = bodies & 0xff, b2 = (bodies >> 8) & 0xff;
     const bool in1 = (dm->body_dofmask[b1] >> d) & 1u, in2 = (dm->body_dofmask[b2] >> d) & 1u;
     float dp[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f};
     const float* cd = sm + ar::CDOF + d * 6;
     if (in2) {
-      const int r2 = dm->body_rootid[b2];
-      float off[3] = {cr[0] - sm[ar::SCOM + r2 * 3], cr[1] - sm[ar::SCOM + r2 * 3 + 1], cr[2] - sm[ar::SCOM + r2 * 3 + 2]}, x[3];
+      const float* sc = sm + ar::SCOM + dm->body_treeid[b2] * 3;
+      float off[3] = {cr[0] - sc[0], cr[1] - sc[1], cr[2] - sc[2]}, x[3];
       cross3(x, cd, off);
       for (int i = 0; i < 3; i++) { dp[i] = cd[3 + i] + x[i]; dr[i] = cd[i]; }
     }
     if (in1) {
-      const int r1 = dm->body_rootid[b1];
-      float off[3] = {cr[0] - sm[ar::SCOM + r1 * 3], cr[1] - sm[ar::SCOM + r1 * 3 + 1], cr[2] - sm[ar::SCOM + r1 * 3 + 2]}, x[3];
+      const float* sc = sm + ar::SCOM + dm->body_treeid[b1] * 3;
+      float off[3] = {cr[0] - sc[0], cr[1] - sc[1], cr[2] - sc[2]}, x[3];
       cross3(x, cd, off);
       for (int i = 0; i < 3; i++) { dp[i] -= cd[3 + i] + x[i]; dr[i] -= cd[i]; }
     }
-    float* B = sm + ar::BROW + c * 4 * nv;
-    B[0 * nv + d] = dot3(cr + cf::FRAME, dp);
-    B[1 * nv + d] = dot3(cr + cf::FRAME + 3, dp);
-    B[2 * nv + d] = dot3(cr + cf::FRAME + 6, dp);
-    B[3 * nv + d] = dot3(cr + cf::FRAME, dr);
+    B[col] = dot3(cr + cf::FRAME, dp);
+    B[NCOL + col] = dot3(cr + cf::FRAME + 3, dp);
+    B[2 * NCOL + col] = dot3(cr + cf::FRAME + 6, dp);
+    B[3 * NCOL + col] = dot3(cr + cf::FRAME, dr);
   }
   RSRX_SYNC();
-  // --- contact rows: D, aref
-  for (int t = lane; t < ncon * 4; t += 32) {  // base velocities u_p = B_p . qvel
-    const float* Bp = sm + ar::BROW + t * nv;
-    float s = 0.f;
-    for (int d = 0; d < nv; d++) s += Bp[d] * sm[ar::QVEL + d];
-    sm[ar::UB + t] = s;
-  }
-  RSRX_SYNC();
+  // --- contact rows: aref (D lives in the contact record)
+  mul_B(sm, lane, ncon, sm + ar::QVEL);  // base velocities u_p = B_p . qvel -> UB
+#pragma unroll 1
   for (int t = lane; t < ncon * 6; t += 32) {
     const int c = t / 6, e = t - c * 6, k = e >> 1;
     const float* cr = sm + ar::CON + c * ar::CSTRIDE;
     const float f = (e & 1) ? -cr[cf::MU + k] : cr[cf::MU + k];
     const float vel = sm[ar::UB + c * 4] + sm[ar::UB + c * 4 + 1 + k] * f;
-    sm[ar::E_D + nsr + t] = cr[cf::D];
     sm[ar::E_AREF + nsr + t] = -cr[cf::B] * vel - cr[cf::KIMPD];
   }
   RSRX_SYNC();
@@ -830,7 +867,6 @@ __device__ __noinline__ void velocity_and_forces(const DModel* __restrict__ dm, 
     float s = 0.f;
     for (int i = 0; i < 6; i++) s += sm[ar::CDOF + d * 6 + i] * acc[i];
     sm[ar::V_BIAS + d] = s;
-    sm[ar::V_PASSIVE + d] = -sm[ar::DAMP + d] * sm[ar::QVEL + d];
     sm[ar::V_ACT + d] = 0.f;
   }
   RSRX_SYNC();
@@ -851,7 +887,7 @@ __device__ __noinline__ void velocity_and_forces(const DModel* __restrict__ dm, 
     float fa = sm[ar::V_ACT + d];
     if (dm->dof_actfrclimited[d]) fa = clipf(fa, dm->dof_actfrcrange[d][0], dm->dof_actfrcrange[d][1]);
     sm[ar::V_ACT + d] = fa;
-    const float fs = sm[ar::V_PASSIVE + d] - sm[ar::V_BIAS + d] + fa;
+    const float fs = -sm[ar::DAMP + d] * sm[ar::QVEL + d] - sm[ar::V_BIAS + d] + fa;
     sm[ar::V_SMOOTH + d] = fs;
     sm[ar::V_QACCS + d] = fs;
   }
@@ -867,7 +903,6 @@ struct SolverDims { int nsr, ncon, nrow; };
 // out[r] = J[r] . x for every row (x: nv-vector in shared memory)
 __device__ __noinline__ void mul_J(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon, const float* x,
                                    float* out) {
-  const int nv = dm->nv;
   const int* sr_dofa = reinterpret_cast<const int*>(sm + ar::SR_DOFA);
   const int* sr_dofb = reinterpret_cast<const int*>(sm + ar::SR_DOFB);
   if (lane < nsr) {
@@ -876,15 +911,7 @@ __device__ __noinline__ void mul_J(const DModel* __restrict__ dm, float* sm, int
     if (b >= 0) s = (b < a) ? sm[ar::SR_CB + lane] * x[b] + s : s + sm[ar::SR_CB + lane] * x[b];
     out[lane] = s;
   }
-#pragma unroll 1
-  for (int t = lane; t < ncon * 4; t += 32) {
-    const float* Bp = sm + ar::BROW + t * nv;
-    float s = 0.f;
-#pragma unroll 4
-    for (int d = 0; d < nv; d++) s += Bp[d] * x[d];
-    sm[ar::UB + t] = s;
-  }
-  RSRX_SYNC();
+  mul_B(sm, lane, ncon, x);
 #pragma unroll 1
   for (int t = lane; t < ncon * 6; t += 32) {
     const int c = t / 6, e = t - c * 6, k = e >> 1;
@@ -900,7 +927,10 @@ __device__ __noinline__ void mul_M(const DModel* __restrict__ dm, const float* s
   if (lane < nv) {
     float s = 0.f;
 #pragma unroll 4
-    for (int j = 0; j < nv; j++) s += sm[ar::MM + lane * LD + j] * x[j];
+    for (int j = 0; j < nv; j++) {
+      const int hi = lane > j ? lane : j, lo = lane > j ? j : lane;
+      s += sm[ar::MM + ((hi * (hi + 1)) >> 1) + lo] * x[j];
+    }
     out[lane] = s;
   }
 }
@@ -930,7 +960,7 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
   bool changed = false;
 #pragma unroll 1
   for (int r = lane; r < nrow; r += 32) {
-    const float ja = sm[ar::E_JAREF + r], D = sm[ar::E_D + r];
+    const float ja = sm[ar::E_JAREF + r], D = row_D(sm, r, nsr);
     const RowShape s = row_shape(sm, r, nsr);
     const bool quad = ja > s.lo && ja < s.hi;
     const bool below = ja <= s.lo;
@@ -967,12 +997,15 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
   if (lane < nv) {
     const int d = lane;
     float s = sm[ar::V_QFRCC + d];
-    const int nv4 = 4 * nv;
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {
-      const float* B = sm + ar::BROW + c * nv4;
+      const int cols = __float_as_int(sm[ar::CON + c * ar::CSTRIDE + cf::COLS]);
+      const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
+      const int col = (d >= a0 && d < a0 + na) ? d - a0 : ((d >= b0 && d < b0 + nb) ? na + d - b0 : -1);
+      if (col < 0) continue;
+      const float* B = sm + ar::BROW + c * 4 * NCOL + col;
       const float* g = sm + ar::UB + c * 4;
-      s += B[d] * g[0] + B[nv + d] * g[1] + B[2 * nv + d] * g[2] + B[3 * nv + d] * g[3];
+      s += B[0] * g[0] + B[NCOL] * g[1] + B[2 * NCOL] * g[2] + B[3 * NCOL] * g[3];
     }
     sm[ar::V_QFRCC + d] = s;
     gpart = (sm[ar::V_MA + d] - sm[ar::V_SMOOTH + d]) * (sm[ar::V_QACC + d] - sm[ar::V_QACCS + d]);
@@ -1020,7 +1053,7 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
   RSRX_SYNC();
   if (lane < nsr && sm[ar::E_ACT + lane] != 0.f) {  // sparse rows touch one diagonal entry (equality: a 2x2 block)
     const int a = reinterpret_cast<const int*>(sm + ar::SR_DOFA)[lane], b = reinterpret_cast<const int*>(sm + ar::SR_DOFB)[lane];
-    const float ca = sm[ar::SR_CA + lane], cb = sm[ar::SR_CB + lane], D = sm[ar::E_D + lane];
+    const float ca = sm[ar::SR_CA + lane], cb = sm[ar::SR_CB + lane], D = sm[ar::E_DS + lane];
     const int pa = dm->pos_of_dof[a];
     atomicAdd(sm + ar::HH + pa * LD + pa, ca * D * ca);
     if (b >= 0) {
@@ -1030,23 +1063,24 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
     }
   }
   RSRX_SYNC();
-  const int nv4 = 4 * nv;
 #pragma unroll 1
   for (int e = lane; e < dm->nhent; e += 32) {  // structurally non-zero entries only
     const int i = dm->hent_i[e], j = dm->hent_j[e];  // dofs, i >= j
     float h = 0.f;
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {
-      const float* cr = sm + ar::CON + c * ar::CSTRIDE;
-      const unsigned mask = (unsigned)__float_as_int(cr[cf::MASK]);
-      if (!(((mask >> i) & 1u) && ((mask >> j) & 1u))) continue;
-      const float* B = sm + ar::BROW + c * nv4;
+      const int cols = __float_as_int(sm[ar::CON + c * ar::CSTRIDE + cf::COLS]);
+      const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
+      const int ci = (i >= a0 && i < a0 + na) ? i - a0 : ((i >= b0 && i < b0 + nb) ? na + i - b0 : -1);
+      const int cj = (j >= a0 && j < a0 + na) ? j - a0 : ((j >= b0 && j < b0 + nb) ? na + j - b0 : -1);
+      if (ci < 0 || cj < 0) continue;
+      const float* B = sm + ar::BROW + c * 4 * NCOL;
       const float* W = sm + ar::CW + c * 8;
-      const float b0i = B[i], b0j = B[j];
+      const float b0i = B[ci], b0j = B[cj];
       float acc = W[0] * b0i * b0j;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const float bki = B[(1 + k) * nv + i], bkj = B[(1 + k) * nv + j];
+        const float bki = B[(1 + k) * NCOL + ci], bkj = B[(1 + k) * NCOL + cj];
         acc += W[1 + k] * (b0i * bkj + bki * b0j) + W[4 + k] * bki * bkj;
       }
       h += acc;
@@ -1102,7 +1136,7 @@ __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm,
   float s_ja = 0.f, s_jv = 0.f, s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_lm = 0.f, s_lp = 0.f, s_l1 = 0.f;
   float s_lo = 0.f, s_hi = 0.f;  // empty quadratic zone
   if (lane < nsr) {
-    const float ja = sm[ar::E_JAREF + lane], jv = sm[ar::E_JV + lane], D = sm[ar::E_D + lane];
+    const float ja = sm[ar::E_JAREF + lane], jv = sm[ar::E_JV + lane], D = sm[ar::E_DS + lane];
     const RowShape s = row_shape(sm, lane, nsr);
     s_ja = ja; s_jv = jv; s_lo = s.lo; s_hi = s.hi;
     s_c0 = 0.5f * ja * ja * D; s_c1 = jv * ja * D; s_c2 = 0.5f * jv * jv * D;
@@ -1127,7 +1161,7 @@ __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm,
     }
 #pragma unroll 1
     for (int r = nsr + lane; r < nrow; r += 32) {
-      const float ja = sm[ar::E_JAREF + r], jv = sm[ar::E_JV + r], D = sm[ar::E_D + r];
+      const float ja = sm[ar::E_JAREF + r], jv = sm[ar::E_JV + r], D = row_D(sm, r, nsr);
       const float c0 = 0.5f * ja * ja * D, c1 = jv * ja * D, c2 = 0.5f * jv * jv * D;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
@@ -1264,13 +1298,13 @@ __device__ __forceinline__ int forward(const DModel* __restrict__ dm, float* sm,
   kinematics(dm, sm, lane);
   com_pos(dm, sm, lane);
   crb_and_factor(dm, sm, lane);
+  phase_barrier<SYNC>(3);
+  velocity_and_forces(dm, sm, lane);  // before collision: its scratch (region P) is reused by the constraint rows
   phase_barrier<SYNC>(1);
   const int ncon = collision(dm, sm, lane, status);
   phase_barrier<SYNC>(2);
   const int nsr = make_constraint(dm, sm, lane, ncon);
   sd->nsr = nsr; sd->ncon = ncon; sd->nrow = nsr + 6 * ncon;
-  phase_barrier<SYNC>(3);
-  velocity_and_forces(dm, sm, lane);
   phase_barrier<SYNC>(4);
   const int r = solve(dm, sm, lane, nsr, ncon, status);
   phase_barrier<SYNC>(5);
