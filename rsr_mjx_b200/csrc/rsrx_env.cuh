@@ -85,10 +85,11 @@ __device__ void get_obs(const DModel* __restrict__ dm, float* sm, const float* i
 
 // Warps per CTA: one env per warp, warps are independent (only __syncwarp).  Single-warp CTAs all land on
 // the same SM sub-partition (warp id within the CTA selects the scheduler), leaving 3 of the 4 schedulers
-// idle — so a CTA carries WPB envs; with the per-substep phase barrier (rsrx_physics.cuh) WPB = 8 = one CTA
-// per SM keeps all resident warps in the same code region (measured 9.5 -> 6.3 ms at 8192 envs).
+// idle — so a CTA carries WPB envs; with the per-substep phase barrier (rsrx_physics.cuh) ONE CTA of
+// WPB = 14 warps per SM (the 16.3 KB arena allows 14) keeps every resident warp in the same code region
+// (measured at 8192 envs: 1 x 14 warps 4.9 ms, 2 x 7 warps 5.6 ms, 8 warps 6.3 ms, no barrier 9.5 ms).
 #ifndef RSRX_WPB
-#define RSRX_WPB 7
+#define RSRX_WPB 14
 #endif
 constexpr int WPB = RSRX_WPB;
 
