@@ -45,10 +45,10 @@ def read_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def read_traffic(kind):
-    """dram bytes per launch of step_kernel from the committed ncu summary, if any"""
+def read_traffic(kind, n_envs):
+    """dram bytes per launch of step_kernel from the committed ncu summary (captured at 8192 envs), if any"""
     p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-    if os.path.exists(p):
+    if os.path.exists(p) and n_envs == 8192:
         with open(p) as f:
             return json.load(f).get(kind)
     return None
@@ -89,6 +89,8 @@ def cpu_oracle_rate(kind, n_envs, n_steps, dense, threads=0, precision="f32"):
     from rsr_mjx_b200 import airbot_spec as A, prng
     from rsr_mjx_b200.model import pack_model
     O.build()
+    if threads <= 0:
+        threads = os.cpu_count() or 1  # all host threads (torchrun exports OMP_NUM_THREADS=1; do not inherit that)
     m = A.load_model(kind)
     blob, cfg = pack_model(m), A.make_env_cfg(m, kind, episode_length=1200)
     keys = prng.split(prng.PRNGKey(0), n_envs)
@@ -102,7 +104,7 @@ def cpu_oracle_rate(kind, n_envs, n_steps, dense, threads=0, precision="f32"):
     t0 = time.perf_counter()
     O.rollout(blob, cfg, states, actions, precision=precision, dense=dense, nthreads=threads)
     dt = time.perf_counter() - t0
-    return n_envs * n_steps / dt, dt, O.max_threads() if threads == 0 else threads
+    return n_envs * n_steps / dt, dt, threads
 
 
 def run_reference(args):
@@ -237,13 +239,13 @@ def main():
                     "h2d_bytes_per_step": N * env.action_size * 4, "d2h_bytes_per_step": N * (env.observation_size + 2) * 4},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": read_traffic(args.kind), "peak_source": peak_src,
+                         "traffic": read_traffic(args.kind, N), "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES[args.kind],
                          "note": "scan-like state-in/state-out step: far below the HBM roof by design (SURVEY.md §8d); "
                                  "issue/latency-bound, see profiles/"},
             "status_flagged_envs": status_bad,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             rate, dt, thr = cpu_oracle_rate(args.kind, args.cpu_envs, 100, dense=False)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": thr, "kind": "port",
                                     "sample": f"{args.cpu_envs} envs x 100 steps, oracle port (C float32, OpenMP), active-set rows; {dt:.1f} s"}
