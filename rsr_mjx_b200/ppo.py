@@ -1,0 +1,343 @@
+"""PPO with the RSR transition-distribution term, on the batched CUDA env.
+
+Mirrors the reference's fork of brax PPO:
+  RSR/train.py:76-503   `train(environment, num_timesteps, episode_length, past_data, ...)`
+  RSR/losses.py:39-205  `compute_gae`, `compute_ppo_loss` (+ `rsr.compute_rsr_loss` on `mode(logits)`)
+with the same hyper-parameter names, data flow (unroll -> [B*M, T] batch -> normaliser update ->
+num_updates_per_batch x shuffled minibatches) and metrics keys.  Differences, all on the caller side of the hot
+path: torch instead of jax; the env is already the wrapped, batched stack (no `envs.training.wrap`); data
+parallelism is one process per GPU with envs sharded across ranks, the gradient `pmean`
+(`gradients.gradient_update_fn(..., pmap_axis_name)`, RSR/train.py:261-262) is ONE `all_reduce` of a flat gradient
+buffer per minibatch step and the normaliser `psum` (train.py:333-336) one small all-reduce per training step.
+The launch-bound minibatch step (two tiny MLPs) can be captured in a CUDA graph (`use_cuda_graph`).
+
+[upstream-recall] brax 0.12.1 details restated here: MLP with swish activations and lecun-uniform kernels,
+policy (32,)*4 / value (256,)*5 by default, NormalTanhDistribution(min_std=0.001) with entropy evaluated at one
+sample, running_statistics normaliser (std clipped to [1e-6, 1e6]).
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Any, Callable, Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import rsr_loss as rsr
+
+
+# ------------------------------------------------------------------------ networks
+class MLP(nn.Module):
+    def __init__(self, sizes: Sequence[int]):
+        super().__init__()
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:]))
+        for l in self.layers:  # flax lecun_uniform kernel, zero bias
+            bound = math.sqrt(3.0 / l.in_features)
+            nn.init.uniform_(l.weight, -bound, bound)
+            nn.init.zeros_(l.bias)
+
+    def forward(self, x):
+        for i, l in enumerate(self.layers):
+            x = l(x)
+            if i + 1 < len(self.layers):
+                x = F.silu(x)
+        return x
+
+
+class PPONetworks(nn.Module):
+    def __init__(self, obs_size: int, action_size: int, policy_hidden=(32,) * 4, value_hidden=(256,) * 5):
+        super().__init__()
+        self.policy = MLP([obs_size, *policy_hidden, 2 * action_size])
+        self.value = MLP([obs_size, *value_hidden, 1])
+        self.action_size = action_size
+
+
+class NormalTanh:
+    """brax NormalTanhDistribution: raw ~ N(loc, softplus(s) + min_std), action = tanh(raw)."""
+    min_std = 0.001
+
+    @staticmethod
+    def params(logits):
+        loc, s = torch.chunk(logits, 2, dim=-1)
+        return loc, F.softplus(s) + NormalTanh.min_std
+
+    @staticmethod
+    def _log_det_jac(x):
+        return 2.0 * (math.log(2.0) - x - F.softplus(-2.0 * x))
+
+    @classmethod
+    def sample_raw(cls, logits, gen=None):
+        loc, scale = cls.params(logits)
+        return loc + scale * torch.randn(loc.shape, device=loc.device, dtype=loc.dtype, generator=gen)
+
+    @classmethod
+    def log_prob(cls, logits, raw):
+        loc, scale = cls.params(logits)
+        lp = -0.5 * ((raw - loc) / scale) ** 2 - 0.5 * math.log(2 * math.pi) - torch.log(scale)
+        return (lp - cls._log_det_jac(raw)).sum(-1)
+
+    @classmethod
+    def entropy(cls, logits, noise):
+        loc, scale = cls.params(logits)
+        ent = 0.5 + 0.5 * math.log(2 * math.pi) + torch.log(scale)
+        return (ent + cls._log_det_jac(loc + scale * noise)).sum(-1)
+
+    @classmethod
+    def mode(cls, logits):
+        return torch.tanh(cls.params(logits)[0])
+
+
+# ---------------------------------------------------------------------- normaliser
+class RunningStatistics:
+    """brax.training.acme.running_statistics (count / mean / summed variance / std)."""
+
+    def __init__(self, size: int, device):
+        self.count = torch.zeros((), device=device)
+        self.mean = torch.zeros(size, device=device)
+        self.summed_variance = torch.zeros(size, device=device)
+        self.std = torch.ones(size, device=device)
+
+    def update(self, batch: torch.Tensor, std_min=1e-6, std_max=1e6):
+        x = batch.reshape(-1, batch.shape[-1]).float()
+        n = torch.tensor(float(x.shape[0]), device=x.device)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(n)
+        count = self.count + n
+        diff = x - self.mean
+        s1 = diff.sum(0)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(s1)
+        mean = self.mean + s1 / count
+        s2 = (diff * (x - mean)).sum(0)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(s2)
+        # in place: a captured CUDA graph keeps reading these tensors
+        self.summed_variance.add_(s2)
+        self.mean.copy_(mean)
+        self.count.copy_(count)
+        self.std.copy_(torch.sqrt(torch.clamp(self.summed_variance, min=0) / count).clamp(std_min, std_max))
+
+    def normalize(self, x):
+        return (x - self.mean) / self.std
+
+
+# ----------------------------------------------------------------------- GAE / loss
+def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambda_: float = 1.0, discount: float = 0.99):
+    """RSR/losses.py:39-95; all inputs [T, B], bootstrap_value [B]. Returns (vs, advantages), detached."""
+    truncation_mask = 1 - truncation
+    values_t_plus_1 = torch.cat([values[1:], bootstrap_value[None]], 0)
+    deltas = (rewards + discount * (1 - termination) * values_t_plus_1 - values) * truncation_mask
+    acc = torch.zeros_like(bootstrap_value)
+    out = []
+    for t in range(truncation.shape[0] - 1, -1, -1):
+        acc = deltas[t] + discount * (1 - termination[t]) * truncation_mask[t] * lambda_ * acc
+        out.append(acc)
+    vs_minus_v_xs = torch.stack(out[::-1], 0)
+    vs = vs_minus_v_xs + values
+    vs_t_plus_1 = torch.cat([vs[1:], bootstrap_value[None]], 0)
+    advantages = (rewards + discount * (1 - termination) * vs_t_plus_1 - values) * truncation_mask
+    return vs.detach(), advantages.detach()
+
+
+def compute_ppo_loss(net: PPONetworks, normalize: Callable, data: Dict[str, torch.Tensor], noise: torch.Tensor,
+                     past_data: Any = None, entropy_cost: float = 1e-4, discounting: float = 0.9,
+                     reward_scaling: float = 1.0, gae_lambda: float = 0.95, clipping_epsilon: float = 0.3,
+                     normalize_advantage: bool = True, rsr_loss_scale: float = 1.0):
+    """RSR/losses.py:98-205.  `data` leaves have leading dims [B, T]."""
+    d = {k: v.transpose(0, 1) for k, v in data.items()}  # time first
+    obs_n = normalize(d["observation"])
+    policy_logits = net.policy(obs_n)
+    baseline = net.value(obs_n).squeeze(-1)
+    bootstrap_value = net.value(normalize(d["next_observation"][-1])).squeeze(-1)
+    rewards = d["reward"] * reward_scaling
+    truncation = d["truncation"]
+    termination = (1 - d["discount"]) * (1 - truncation)
+    target_lp = NormalTanh.log_prob(policy_logits, d["raw_action"])
+    vs, advantages = compute_gae(truncation, termination, rewards, baseline, bootstrap_value, gae_lambda, discounting)
+    if normalize_advantage:
+        advantages = (advantages - advantages.mean()) / (advantages.std(unbiased=False) + 1e-8)
+    rho_s = torch.exp(target_lp - d["log_prob"])
+    policy_loss = -torch.mean(torch.minimum(rho_s * advantages,
+                                            torch.clamp(rho_s, 1 - clipping_epsilon, 1 + clipping_epsilon) * advantages))
+    v_error = vs - baseline
+    v_loss = torch.mean(v_error * v_error) * 0.5 * 0.5
+    entropy_loss = entropy_cost * -torch.mean(NormalTanh.entropy(policy_logits, noise))
+    task_loss = policy_loss + v_loss + entropy_loss
+    # the RSR term uses the action of the policy being optimised (raw, unnormalised observations)
+    sim2real_loss, distance = rsr.compute_rsr_loss(d["observation"], NormalTanh.mode(policy_logits), d["next_observation"],
+                                                   past_data, loss_scale=rsr_loss_scale)
+    total = task_loss + sim2real_loss
+    return total, {"total_loss": total, "task_loss": task_loss, "policy_loss": policy_loss, "v_loss": v_loss,
+                   "entropy_loss": entropy_loss, "sim2real_loss": sim2real_loss, "rsr_distribution_distance": distance}
+
+
+# ----------------------------------------------------------------------- training
+def _flat_allreduce_mean(params):
+    """gradient pmean: one all-reduce of a flat buffer"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat /= dist.get_world_size()
+    o = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[o:o + n].view_as(g))
+        o += n
+
+
+def train(environment, num_timesteps: int, episode_length: int, past_data: Any = None, action_repeat: int = 1,
+          num_envs: int = 1, num_eval_envs: int = 128, learning_rate: float = 1e-4, entropy_cost: float = 1e-4,
+          discounting: float = 0.9, seed: int = 0, unroll_length: int = 10, batch_size: int = 32,
+          num_minibatches: int = 16, num_updates_per_batch: int = 2, num_evals: int = 1,
+          normalize_observations: bool = False, reward_scaling: float = 1.0, clipping_epsilon: float = 0.3,
+          gae_lambda: float = 0.95, rsr_loss_scale: float = 1.0, normalize_advantage: bool = True,
+          policy_hidden=(32,) * 4, value_hidden=(256,) * 5,
+          progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None,
+          use_cuda_graph: bool = True, max_training_steps: Optional[int] = None, **unused):
+    """PPO training (RSR/train.py:76).  `environment` is an `AirbotPlayBase` with `num_envs` envs on this rank
+    (under torch.distributed every rank passes its shard; `num_envs` is the per-rank count here).
+    Returns (make_policy, (normalizer, networks), metrics)."""
+    env = environment
+    if env.num_envs != num_envs:
+        raise ValueError(f"environment has {env.num_envs} envs, num_envs={num_envs}")
+    if env.episode_length != episode_length:
+        raise ValueError("environment.episode_length differs from episode_length (the env is already wrapped)")
+    assert batch_size * num_minibatches % num_envs == 0
+    dev = env.device
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    env_step_per_training_step = batch_size * unroll_length * num_minibatches * action_repeat * world
+    num_training_steps = int(math.ceil(num_timesteps / env_step_per_training_step))
+    if max_training_steps is not None:
+        num_training_steps = min(num_training_steps, max_training_steps)
+
+    torch.manual_seed(seed)  # networks identical on every rank (key_policy / key_value are global in the reference)
+    net = PPONetworks(env.observation_size, env.action_size, policy_hidden, value_hidden).to(dev)
+    params = list(net.parameters())
+    opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8, capturable=bool(use_cuda_graph))
+    norm = RunningStatistics(env.observation_size, dev)
+    normalize = norm.normalize if normalize_observations else (lambda x: x)
+    gen = torch.Generator(device=dev).manual_seed(seed * 7919 + rank + 1)
+
+    from . import sharding
+    state = env.reset(sharding.shard_keys(seed, num_envs, rank, world))
+    T, n_unrolls = unroll_length, batch_size * num_minibatches // num_envs
+    B = batch_size * num_minibatches
+    obs_size, act_size = env.observation_size, env.action_size
+    buf = {k: torch.empty(n_unrolls, T, num_envs, *s, device=dev) for k, s in
+           dict(observation=(obs_size,), next_observation=(obs_size,), raw_action=(act_size,), log_prob=(), reward=(),
+                discount=(), truncation=()).items()}
+
+    @torch.no_grad()
+    def collect():
+        for u in range(n_unrolls):
+            for t in range(T):
+                obs = state.obs
+                buf["observation"][u, t].copy_(obs)
+                logits = net.policy(normalize(obs))
+                raw = NormalTanh.sample_raw(logits, gen)
+                buf["raw_action"][u, t].copy_(raw)
+                buf["log_prob"][u, t].copy_(NormalTanh.log_prob(logits, raw))
+                env.step(state, torch.tanh(raw))
+                buf["next_observation"][u, t].copy_(state.obs)
+                buf["reward"][u, t].copy_(state.reward)
+                buf["discount"][u, t].copy_(1 - state.done)
+                buf["truncation"][u, t].copy_(state.info["truncation"])
+        # [n_unrolls, T, N, ...] -> [B = n_unrolls * N, T, ...]
+        return {k: v.permute(0, 2, 1, *range(3, v.dim())).reshape(B, T, *v.shape[3:]) for k, v in buf.items()}
+
+    mb = B // num_minibatches
+    static = {k: torch.empty(mb, T, *v.shape[3:], device=dev) for k, v in buf.items()}
+    static_noise = torch.empty(T, mb, act_size, device=dev)
+    loss_kw = dict(past_data=past_data, entropy_cost=entropy_cost, discounting=discounting, reward_scaling=reward_scaling,
+                   gae_lambda=gae_lambda, clipping_epsilon=clipping_epsilon, normalize_advantage=normalize_advantage,
+                   rsr_loss_scale=rsr_loss_scale)
+    last_metrics: Dict[str, torch.Tensor] = {}
+
+    def fwd_bwd():
+        opt.zero_grad(set_to_none=False)
+        loss, metrics = compute_ppo_loss(net, normalize, static, static_noise, **loss_kw)
+        loss.backward()
+        return metrics
+
+    graph_bwd = graph_opt = None
+    if use_cuda_graph:
+        # warm-up on a side stream (allocator, cuBLAS handles, Adam state), roll the warm-up's parameter / optimizer
+        # changes back, then capture forward+backward and the Adam step as two graphs; the (NCCL) gradient
+        # all-reduce runs between them
+        for p in params:
+            p.grad = torch.zeros_like(p)
+        for k in static:
+            static[k].zero_()
+        static["discount"].fill_(1.0)
+        static_noise.zero_()
+        saved = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fwd_bwd()
+                opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        net.load_state_dict(saved)
+        for st_ in opt.state.values():
+            for v in st_.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+        graph_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_bwd):
+            last_metrics = fwd_bwd()
+        graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_opt):
+            opt.step()
+
+    def minibatch_step(batch, idx):
+        nonlocal last_metrics
+        for k in static:
+            static[k].copy_(batch[k][idx])
+        static_noise.normal_(generator=gen)
+        if graph_bwd is not None:
+            graph_bwd.replay()
+            _flat_allreduce_mean(params)
+            graph_opt.replay()
+        else:
+            last_metrics = fwd_bwd()
+            _flat_allreduce_mean(params)
+            opt.step()
+
+    metrics_out: Dict[str, float] = {}
+    t_start = time.time()
+    env_steps = 0
+    for it in range(num_training_steps):
+        t0 = time.time()
+        data = collect()
+        if normalize_observations:
+            norm.update(data["observation"])
+        for _ in range(num_updates_per_batch):
+            perm = torch.randperm(B, device=dev, generator=gen)
+            for m_ in range(num_minibatches):
+                minibatch_step(data, perm[m_ * mb:(m_ + 1) * mb])
+        torch.cuda.synchronize(dev)
+        dt = time.time() - t0
+        env_steps += env_step_per_training_step
+        metrics_out = {f"training/{k}": float(v) for k, v in last_metrics.items()}
+        metrics_out["training/sps"] = env_step_per_training_step / dt
+        metrics_out["training/walltime"] = time.time() - t_start
+        metrics_out["training/reward_mean"] = float(data["reward"].mean())
+        if num_evals > 0 and (it + 1) % max(num_training_steps // max(num_evals, 1), 1) == 0:
+            progress_fn(env_steps, metrics_out)
+
+    def make_policy(deterministic: bool = False):
+        @torch.no_grad()
+        def policy(obs, generator=None):
+            logits = net.policy(normalize(obs))
+            return NormalTanh.mode(logits) if deterministic else torch.tanh(NormalTanh.sample_raw(logits, generator))
+        return policy
+
+    return make_policy, (norm, net), metrics_out

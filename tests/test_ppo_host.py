@@ -1,0 +1,115 @@
+"""Host-side PPO pieces against NumPy transcriptions of the reference formulas
+(RSR/losses.py:39-95 GAE; brax NormalTanhDistribution), CPU only."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rsr_mjx_b200 import ppo
+
+
+def _np_gae(truncation, termination, rewards, values, bootstrap, lam, disc):
+    T = rewards.shape[0]
+    mask = 1 - truncation
+    v1 = np.concatenate([values[1:], bootstrap[None]], 0)
+    deltas = (rewards + disc * (1 - termination) * v1 - values) * mask
+    acc = np.zeros_like(bootstrap)
+    out = np.zeros_like(values)
+    for t in reversed(range(T)):
+        acc = deltas[t] + disc * (1 - termination[t]) * mask[t] * lam * acc
+        out[t] = acc
+    vs = out + values
+    vs1 = np.concatenate([vs[1:], bootstrap[None]], 0)
+    adv = (rewards + disc * (1 - termination) * vs1 - values) * mask
+    return vs, adv
+
+
+def test_gae_matches_reference_formula():
+    rng = np.random.default_rng(0)
+    T, B = 10, 7
+    trunc = (rng.random((T, B)) < 0.1).astype(np.float64)
+    term = (rng.random((T, B)) < 0.1).astype(np.float64) * (1 - trunc)
+    r, v, bs = rng.normal(size=(T, B)), rng.normal(size=(T, B)), rng.normal(size=B)
+    vs, adv = ppo.compute_gae(*[torch.from_numpy(x) for x in (trunc, term, r, v, bs)], lambda_=0.95, discount=0.96)
+    vs_ref, adv_ref = _np_gae(trunc, term, r, v, bs, 0.95, 0.96)
+    np.testing.assert_allclose(vs.numpy(), vs_ref, rtol=1e-12)
+    np.testing.assert_allclose(adv.numpy(), adv_ref, rtol=1e-12)
+
+
+def test_normal_tanh_distribution():
+    torch.manual_seed(0)
+    logits = torch.randn(5, 10, dtype=torch.float64)
+    raw = torch.randn(5, 5, dtype=torch.float64)
+    loc, scale = ppo.NormalTanh.params(logits)
+    assert (scale > 0.001).all()
+    base = torch.distributions.Normal(loc, scale)
+    ref = (base.log_prob(raw) - torch.log(1 - torch.tanh(raw) ** 2)).sum(-1)
+    np.testing.assert_allclose(ppo.NormalTanh.log_prob(logits, raw).numpy(), ref.numpy(), rtol=1e-9)
+    noise = torch.randn(5, 5, dtype=torch.float64)
+    x = loc + scale * noise
+    ent_ref = (base.entropy() + torch.log(1 - torch.tanh(x) ** 2)).sum(-1)
+    np.testing.assert_allclose(ppo.NormalTanh.entropy(logits, noise).numpy(), ent_ref.numpy(), rtol=1e-8)
+    np.testing.assert_allclose(ppo.NormalTanh.mode(logits).numpy(), torch.tanh(loc).numpy())
+
+
+def test_running_statistics_matches_numpy():
+    rs = ppo.RunningStatistics(3, "cpu")
+    rng = np.random.default_rng(1)
+    chunks = [rng.normal(2.0, 3.0, (50, 4, 3)) for _ in range(4)]
+    for c in chunks:
+        rs.update(torch.from_numpy(c))
+    allx = np.concatenate([c.reshape(-1, 3) for c in chunks])
+    np.testing.assert_allclose(rs.mean.numpy(), allx.mean(0), rtol=1e-5)
+    np.testing.assert_allclose(rs.std.numpy(), allx.std(0), rtol=1e-4)
+    np.testing.assert_allclose(rs.normalize(torch.from_numpy(allx[:5]).float()).numpy(), (allx[:5] - allx.mean(0)) / allx.std(0), rtol=1e-3, atol=1e-4)
+
+
+def test_ppo_loss_runs_on_cpu_without_rsr_term():
+    torch.manual_seed(0)
+    net = ppo.PPONetworks(23, 5)
+    assert sum(p.numel() for p in net.policy.parameters()) == 23 * 32 + 32 + 3 * (32 * 32 + 32) + 32 * 10 + 10
+    B, T = 12, 10
+    data = dict(observation=torch.randn(B, T, 23), next_observation=torch.randn(B, T, 23), raw_action=torch.randn(B, T, 5),
+                log_prob=torch.randn(B, T), reward=torch.randn(B, T), discount=torch.ones(B, T), truncation=torch.zeros(B, T))
+    loss, m = ppo.compute_ppo_loss(net, lambda x: x, data, torch.randn(T, B, 5), past_data=None, entropy_cost=2e-2,
+                                   discounting=0.96, reward_scaling=0.1)
+    loss.backward()
+    assert torch.isfinite(loss) and m["sim2real_loss"].item() == 0.0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    assert set(m) == {"total_loss", "task_loss", "policy_loss", "v_loss", "entropy_loss", "sim2real_loss", "rsr_distribution_distance"}
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = ppo.PPONetworks(6, 2, (8, 8), (8,))
+        x = torch.randn(4, 6, generator=torch.Generator().manual_seed(100 + rank))
+        (net.policy(x).sum() + net.value(x).sum()).backward()
+        local = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+        ppo._flat_allreduce_mean(list(net.parameters()))
+        q.put((rank, local.numpy(), torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_pmean_world2():
+    world, port = 2, 29617 + os.getpid() % 300
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted([q.get(timeout=90) for _ in range(world)], key=lambda r: r[0])
+    for p in ps:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    mean = (res[0][1] + res[1][1]) / 2
+    assert not np.allclose(res[0][1], res[1][1])
+    np.testing.assert_allclose(res[0][2], mean, rtol=1e-6)
+    np.testing.assert_allclose(res[1][2], mean, rtol=1e-6)
