@@ -326,7 +326,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         torch.cuda.synchronize(dev)
         dt = time.time() - t0
         env_steps += env_step_per_training_step
-        metrics_out = {f"training/{k}": float(v) for k, v in last_metrics.items()}
+        metrics_out = {f"training/{k}": float(v.detach()) for k, v in last_metrics.items()}
         metrics_out["training/sps"] = env_step_per_training_step / dt
         metrics_out["training/walltime"] = time.time() - t_start
         metrics_out["training/reward_mean"] = float(data["reward"].mean())

@@ -153,15 +153,41 @@ def build_policy_rsr_data(past_states: Any, past_actions: Any, past_next_states_
                                    bandwidth=bandwidth, seed=seed, device=device)
 
 
-def policy_params_training(env, *args, algorithm: str = "ppo", **kwargs):
-    """PPO/SAC policy training with the RSR term (rsr_pipeline.py:274-436).
+def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, policy_params_fn=None, network_factory=None,
+                           progress_fn=None, past_states: Any = None, past_actions: Any = None,
+                           past_next_states_real: Any = None, past_next_states_sim: Any = None,
+                           current_next_states_sim: Any = None, algorithm: str = "ppo", num_samples: int = 10,
+                           min_val: float = -3.0, max_val: float = 3.0, bandwidth: float = 0.1, rsr_loss_scale: float = 1.0,
+                           num_timesteps: int = 5_000_000, num_evals: int = 10, reward_scaling: float = 0.1,
+                           episode_length: int = 1200, normalize_observations: bool = True, action_repeat: int = 1,
+                           discounting: float = 0.96, learning_rate: float = 1e-4, num_envs: int = 512, batch_size: int = 128,
+                           seed: int = 0, num_eval_envs: int = 128, deterministic_eval: bool = False,
+                           max_devices_per_host: Optional[int] = None, unroll_length: int = 10, num_minibatches: int = 32,
+                           num_updates_per_batch: int = 8, entropy_cost: float = 2e-2, num_resets_per_eval: int = 0,
+                           **sac_and_extra_options):
+    """Trains an RSR policy (reference signature and defaults, rsr_pipeline.py:274-319).
 
-    The trainer is a *caller* of the hot path; the
-    torch PPO loop lives in rsr_mjx_b200.ppo when present."""
-    try:
-        from . import ppo
-    except ImportError as e:  # pragma: no cover
-        raise NotImplementedError("policy_params_training: the torch PPO/SAC trainers are SURVEY.md §8f 'next' rows") from e
-    if algorithm.lower() != "ppo":
+    `env` is a batched `AirbotPlayBase` whose `num_envs` / `episode_length` match the arguments.  Only
+    ``algorithm='ppo'`` is available (SAC is SURVEY.md §8f row N3); Orbax checkpoints are out of scope, so
+    `restore_checkpoint_path` must be None.  Returns ``(make_inference_fn, (normalizer, networks))``."""
+    from . import ppo
+    if rsr_loss_scale < 0:
+        raise ValueError(f'rsr_loss_scale must be non-negative, got {rsr_loss_scale}')
+    required = (past_states, past_actions, past_next_states_real, past_next_states_sim, current_next_states_sim)
+    if any(v is None for v in required):
+        raise ValueError('all five RSR policy datasets are required')
+    if algorithm.strip().lower() != "ppo":
         raise NotImplementedError("only algorithm='ppo' is available (SAC: SURVEY.md §8f N3)")
-    return ppo.train(env, *args, **kwargs)
+    if restore_checkpoint_path:
+        raise NotImplementedError("Orbax checkpoint restore is out of scope (SURVEY.md §5)")
+    past_data = build_policy_rsr_data(past_states, past_actions, past_next_states_real, past_next_states_sim,
+                                      current_next_states_sim, num_samples=num_samples, min_val=min_val, max_val=max_val,
+                                      bandwidth=bandwidth, seed=seed, device=env.device)
+    make_inference_fn, params, _ = ppo.train(
+        environment=env, past_data=past_data, num_timesteps=num_timesteps, num_evals=num_evals, num_eval_envs=num_eval_envs,
+        reward_scaling=reward_scaling, episode_length=episode_length, normalize_observations=normalize_observations,
+        action_repeat=action_repeat, unroll_length=unroll_length, num_minibatches=num_minibatches,
+        num_updates_per_batch=num_updates_per_batch, discounting=discounting, learning_rate=learning_rate,
+        entropy_cost=entropy_cost, num_envs=num_envs, batch_size=batch_size, progress_fn=progress_fn or (lambda *a: None),
+        rsr_loss_scale=rsr_loss_scale, seed=seed, **{k: v for k, v in sac_and_extra_options.items() if k in ("use_cuda_graph", "max_training_steps")})
+    return make_inference_fn, params

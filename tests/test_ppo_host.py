@@ -113,3 +113,22 @@ def test_gradient_pmean_world2():
     assert not np.allclose(res[0][1], res[1][1])
     np.testing.assert_allclose(res[0][2], mean, rtol=1e-6)
     np.testing.assert_allclose(res[1][2], mean, rtol=1e-6)
+
+
+def test_policy_params_training_validation_matches_reference():
+    """rsr_pipeline.py:335-347 — checked before any device work"""
+    from rsr_mjx_b200 import rsr_pipeline as RP
+    with pytest.raises(ValueError, match="rsr_loss_scale must be non-negative"):
+        RP.policy_params_training(None, rsr_loss_scale=-1.0)
+    with pytest.raises(ValueError, match="all five RSR policy datasets are required"):
+        RP.policy_params_training(None, past_states=np.zeros((3, 23)))
+    z = np.zeros((3, 23))
+    with pytest.raises(NotImplementedError):
+        RP.policy_params_training(None, past_states=z, past_actions=np.zeros((3, 5)), past_next_states_real=z,
+                                  past_next_states_sim=z, current_next_states_sim=z, algorithm="sac")
+    with pytest.raises(ValueError, match="RSR datasets must have equal lengths"):
+        RP.build_policy_rsr_data(z, np.zeros((4, 5)), z, z, z)
+    with pytest.raises(ValueError, match="real next-state width must match state width"):
+        RP.build_policy_rsr_data(z, np.zeros((3, 5)), np.zeros((3, 22)), z, z)
+    with pytest.raises(ValueError, match="all RSR datasets must be rank 2"):
+        RP.build_policy_rsr_data(np.zeros(3), np.zeros((3, 5)), z, z, z)
