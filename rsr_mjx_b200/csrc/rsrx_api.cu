@@ -237,6 +237,12 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
       d.tri_src[e] = (unsigned short)(i * LD + j);
       d.tri_dst[e] = (unsigned short)((pi > pj ? pi : pj) * LD + (pi > pj ? pj : pi));
     }
+    for (int q = 0; q < b.nv; q++) {  // per-tree sub-blocks inside the permuted order
+      int t = d.body_treeid[b.dof_bodyid[d.dof_of_pos[q]]], lo = q, hi = q;
+      while (lo > 0 && d.body_treeid[b.dof_bodyid[d.dof_of_pos[lo - 1]]] == t) lo--;
+      while (hi + 1 < b.nv && d.body_treeid[b.dof_bodyid[d.dof_of_pos[hi + 1]]] == t) hi++;
+      d.tblk_start[q] = lo; d.tblk_end[q] = hi;
+    }
     d.nhent = 0;
     for (int i = 0; i < b.nv; i++)
       for (int j = 0; j <= i; j++)

@@ -34,7 +34,7 @@ __device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, 
     ptrs[0] = pe.geom_friction ? pe.geom_friction + (size_t)e * dm->ngeom * 3 : nullptr;
     ptrs[1] = pe.body_mass ? pe.body_mass + (size_t)e * dm->nbody : nullptr;
     ptrs[2] = pe.dof_frictionloss ? pe.dof_frictionloss + (size_t)e * dm->nv : nullptr;
-    ptrs[3] = nullptr;
+    reinterpret_cast<int*>(sm + ar::PTRS)[6] = 1;
   }
   RSRX_SYNC();
 }

@@ -203,14 +203,16 @@ __device__ __noinline__ void com_pos(const DModel* __restrict__ dm, float* sm, i
 // only; whatever crosses lanes (pivot, column k) travels by shuffle, so there are
 // no barriers in the dependency chain; the pivot column is scaled by one rsqrt
 // (no IEEE sqrt / division subroutines).
-__device__ __noinline__ void warp_chol_factor(const DModel* __restrict__ dm, float* sm, int lane) {
+__device__ __noinline__ void warp_chol_factor(const DModel* __restrict__ dm, float* sm, int lane, bool tree_blocks) {
   constexpr unsigned FULL = 0xffffffffu;
   float* A = sm + ar::HH;
   const int n = dm->nv;
   const bool own = lane < n;
   const int p = own ? lane : n - 1;  // surplus lanes shadow the last row (reads only)
   float* row = A + p * LD;
-  const int pend = dm->blk_end[p];
+  // tree_blocks: no contact couples two kinematic trees right now (always true for M itself), so the blocks are
+  // the trees (8 | 6 | 6 instead of 14 | 6 for the cube model)
+  const int pend = tree_blocks ? dm->tblk_end[p] : dm->blk_end[p];
   float rdiag = 1.f;
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
@@ -234,13 +236,14 @@ __device__ __noinline__ void warp_chol_factor(const DModel* __restrict__ dm, flo
 
 // x <- (L L^T)^-1 x with the factor left in ar::HH by warp_chol_factor; x is an
 // nv-vector in dof order.
-__device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, float* sm, float* x, int lane) {
+__device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, float* sm, float* x, int lane, bool tree_blocks) {
   constexpr unsigned FULL = 0xffffffffu;
   const float* A = sm + ar::HH;
   const int n = dm->nv;
   const bool own = lane < n;
   const int p = own ? lane : n - 1;
-  const int pstart = dm->blk_start[p], pend = dm->blk_end[p], dof = dm->dof_of_pos[p];
+  const int pstart = tree_blocks ? dm->tblk_start[p] : dm->blk_start[p], pend = tree_blocks ? dm->tblk_end[p] : dm->blk_end[p];
+  const int dof = dm->dof_of_pos[p];
   const float rdiag = sm[ar::V_RDIAG + p];
   const float* row = A + p * LD;
   float xi = x[dof];
@@ -784,6 +787,15 @@ __device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float
     B[3 * NCOL + col] = dot3(cr + cf::FRAME, dr);
   }
   RSRX_SYNC();
+  {  // does any contact couple two kinematic trees?  (selects the Cholesky block structure of H)
+    bool cpl = false;
+    for (int c = lane; c < ncon; c += 32) {
+      const int cols = __float_as_int(sm[ar::CON + c * ar::CSTRIDE + cf::COLS]);
+      cpl |= ((cols >> 8) & 0xff) != 0 && ((cols >> 24) & 0xff) != 0;
+    }
+    const bool any = __any_sync(0xffffffffu, cpl);
+    if (lane == 0) reinterpret_cast<int*>(sm + ar::PTRS)[6] = any ? 1 : 0;
+  }
   // --- contact rows: aref (D lives in the contact record)
   mul_B(sm, lane, ncon, sm + ar::QVEL);  // base velocities u_p = B_p . qvel -> UB
 #pragma unroll 1
@@ -893,8 +905,8 @@ __device__ __noinline__ void velocity_and_forces(const DModel* __restrict__ dm, 
   }
   // factor_m + solve_m: qacc_smooth = M^-1 qfrc_smooth (factor a scratch copy of M; H is rebuilt later)
   copy_M_permuted(dm, sm, lane, nullptr, 0.f);
-  warp_chol_factor(dm, sm, lane);
-  warp_chol_solve(dm, sm, sm + ar::V_QACCS, lane);
+  warp_chol_factor(dm, sm, lane, true);
+  warp_chol_solve(dm, sm, sm + ar::V_QACCS, lane, true);
 }
 
 // ---------------------------------------------------------------------- solver
@@ -1022,6 +1034,7 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
 __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon,
                                              bool reuse_factor) {
   const int nv = dm->nv;
+  const bool tree_blocks = reinterpret_cast<const int*>(sm + ar::PTRS)[6] == 0;  // set by make_constraint
   if (lane < nv) {
     const float g = sm[ar::V_MA + lane] - sm[ar::V_SMOOTH + lane] - sm[ar::V_QFRCC + lane];
     sm[ar::V_GRAD + lane] = g;
@@ -1029,7 +1042,7 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
   }
   if (reuse_factor) {  // same active set as the previous iteration: H, hence its factor in ar::HH, is unchanged
     RSRX_SYNC();
-    warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane);
+    warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane, tree_blocks);
     return;
   }
   copy_M_permuted(dm, sm, lane, nullptr, 0.f);
@@ -1089,8 +1102,8 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
     sm[ar::HH + max(pi, pj) * LD + min(pi, pj)] += h;
   }
   RSRX_SYNC();
-  warp_chol_factor(dm, sm, lane);
-  warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane);
+  warp_chol_factor(dm, sm, lane, tree_blocks);
+  warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane, tree_blocks);
 }
 
 // _Context.create: qacc <- src, Jaref, Ma, constraint update.  Returns cost.
@@ -1317,8 +1330,8 @@ __device__ __noinline__ void implicit_advance(const DModel* __restrict__ dm, flo
   const float dt = dm->timestep;
   if (lane < nv) sm[ar::V_TMP + lane] = sm[ar::V_SMOOTH + lane] + sm[ar::V_QFRCC + lane];
   copy_M_permuted(dm, sm, lane, sm + ar::DAMP, dt);
-  warp_chol_factor(dm, sm, lane);
-  warp_chol_solve(dm, sm, sm + ar::V_TMP, lane);
+  warp_chol_factor(dm, sm, lane, true);
+  warp_chol_solve(dm, sm, sm + ar::V_TMP, lane, true);
   if (lane < nv) sm[ar::QVEL + lane] += sm[ar::V_TMP + lane] * dt;
   RSRX_SYNC();
   if (lane < dm->njnt) {
