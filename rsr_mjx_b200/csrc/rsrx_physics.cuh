@@ -1158,7 +1158,9 @@ __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm,
   LSPoint p0, lo, hi;
   p0.alpha = p0.cost = p0.d0 = p0.d1 = 0.f;
   lo = hi = p0;
-  LSPoint lo1 = p0, hi1 = p0, lo2 = p0, hi2 = p0;  // bracket one and two iterations ago
+  float anchor_lo = -1e30f, anchor_hi = -1e30f;  // cycle detection, see below
+  int anchor_it = 0;
+  bool jumped = false;
   float al[3] = {0.f, 0.f, 0.f};
   int phase = 0, it = 0;
 #pragma unroll 1
@@ -1226,17 +1228,20 @@ __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm,
       if (swap_hi_mid) hi = mid;
       swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
       it++;
-      // MJX's bracketing often falls into an exact 2-cycle (lo and hi trade places every iteration, e.g. across a
-      // kink of the piecewise-linear derivative or between two neighbouring floats) and then runs to ls_iterations.
-      // Once state(it) == state(it - 2) bit for bit, every later state is known: jump to the state the loop would
-      // hold at ls_iterations.  Identical result, ~3x fewer line-search iterations (profiles/README.md).
-      if (swap && it >= 3 && it < dm->ls_iterations && lo.alpha == lo2.alpha && hi.alpha == hi2.alpha &&
-          lo.d0 == lo2.d0 && hi.d0 == hi2.d0) {
-        if ((dm->ls_iterations - it) & 1) { lo = lo1; hi = hi1; }
-        it = dm->ls_iterations;
+      // MJX's bracketing often falls into an exact cycle (lo and hi trade places across a kink of the piecewise-
+      // linear derivative, or hop between neighbouring floats; periods 2, 3 and 4 all occur) and then runs to
+      // ls_iterations.  A bracket is a pure function of (lo.alpha, hi.alpha), so once the pair equals an anchor taken
+      // at a power-of-two iteration (Brent) every later state is known: skip whole periods and run only the remainder.
+      // Bit-identical result, 11.3 -> 3.3 evaluated iterations per line search (profiles/README.md).
+      if (swap && !jumped && it < dm->ls_iterations) {
+        if (lo.alpha == anchor_lo && hi.alpha == anchor_hi) {
+          it = dm->ls_iterations - (dm->ls_iterations - it) % (it - anchor_it);
+          jumped = true;
+        } else if ((it & (it - 1)) == 0) {
+          anchor_lo = lo.alpha; anchor_hi = hi.alpha; anchor_it = it;
+        }
       }
     }
-    lo2 = lo1; hi2 = hi1; lo1 = lo; hi1 = hi;
     bool done = it >= dm->ls_iterations;
     done |= !swap;
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
