@@ -165,6 +165,7 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
     d.geom_static[g] = d.body_static[bd];
     for (int k = 0; k < 3; k++) { d.geom_pos[g][k] = (float)b.geom_pos[g][k]; d.geom_size[g][k] = (float)b.geom_size[g][k]; d.geom_friction[g][k] = (float)b.geom_friction[g][k]; }
     for (int k = 0; k < 4; k++) d.geom_quat[g][k] = (float)b.geom_quat[g][k];
+    d.geom_rbound[g] = std::sqrt(d.geom_size[g][0] * d.geom_size[g][0] + d.geom_size[g][1] * d.geom_size[g][1] + d.geom_size[g][2] * d.geom_size[g][2]);
     if (d.geom_static[g]) {
       double t[3], q[4], m[9];
       hq_rot(t, b.geom_pos[g], sq[bd]);

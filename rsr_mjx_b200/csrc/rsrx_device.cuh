@@ -64,6 +64,7 @@ struct DModel {
   int geom_type[NG], geom_bodyid[NG], geom_static[NG];
   float geom_pos[NG][3], geom_quat[NG][4], geom_size[NG][3], geom_friction[NG][3];
   float geom_static_xpos[NG][3], geom_static_xmat[NG][9];
+  float geom_rbound[NG];  // radius of the bounding sphere (|size| of a box)
   // sites
   int site_bodyid[NS];
   float site_pos[NS][3];
@@ -144,6 +145,10 @@ constexpr int CRB = CINERT + NB * 10;     // crb while building M, then cacc
 constexpr int CDOFDOT = CRB + NB * 10;    // crb_cdof while building M, then cdof_dot
 constexpr int CVEL = CDOFDOT + NV * 6;
 constexpr int P_END = CVEL + NB * 6;
+// ---- ... region C (collision only; P is dead by then, S not yet alive): world poses of all geoms + surviving pairs
+constexpr int GPOSE = U;                   // [g][12]: pos(3), mat(9)
+constexpr int PLIST = GPOSE + NG * 12;     // int [MAXPAIR]
+constexpr int C_END = PLIST + RSRX_MAXPAIR;
 // ---- ... and region S (alive from make_constraint's contact pass to the end of the solver)
 constexpr int E_JAREF = U;
 constexpr int E_JV = E_JAREF + MAXROW;
@@ -152,6 +157,7 @@ constexpr int UB = E_ACT + MAXROW;         // [c][4] base-row scratch ...
 constexpr int CW = UB;                     // ... / [c][8] per-contact Hessian weights (never live together)
 constexpr int S_END = CW + MAXC * 8;
 constexpr int TOTAL = (P_END > S_END ? P_END : S_END);
+static_assert(C_END <= TOTAL, "collision scratch must fit the union region");
 }  // namespace ar
 
 // contact record fields

@@ -556,29 +556,69 @@ __device__ __noinline__ void kbi(const DModel* __restrict__ dm, const float* sol
   *imp = clipf(dmin + y * (dmax - dmin), dmin, dmax);
 }
 
-// collision_driver.py::collision: one lane per geom pair (narrow phase in
-// registers/local memory), warp prefix-sum compaction of the active contacts
-// into the shared-memory contact list in (pair, slot) order.  Contacts that MJX
-// would keep as zeroed rows (dist >= 0) are dropped.  Returns ncon.
+// collision_driver.py::collision in three warp passes:
+//  0. one lane per geom: world pose into shared memory (region C);
+//  1. one lane per geom pair: conservative bounding test (box centre + bounding radius against the plane / against the
+//     other box's faces).  A culled pair is one the narrow phase would report no contact for (a separating face axis
+//     exists), so the contact list is unchanged; survivors are compacted in pair order;
+//  2. one lane per surviving pair: narrow phase in registers/local memory, warp prefix-sum compaction of the active
+//     contacts into the shared-memory contact list in (pair, slot) order.  Contacts that MJX would keep as zeroed rows
+//     (dist >= 0) are dropped.  Returns ncon.
 __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, int lane, int* status) {
-  int ncon = 0;
+  for (int g = lane; g < dm->ngeom; g += 32) {
+    float pos[3], mat[9];
+    geom_pose(dm, sm, g, pos, mat);
+    float* gp = sm + ar::GPOSE + g * 12;
+    for (int i = 0; i < 3; i++) gp[i] = pos[i];
+    for (int i = 0; i < 9; i++) gp[3 + i] = mat[i];
+  }
+  RSRX_SYNC();
+  int* plist = reinterpret_cast<int*>(sm + ar::PLIST);
+  int nsurv = 0;
   for (int base = 0; base < dm->npair; base += 32) {
     const int p = base + lane;
-    float dist[4] = {1.f, 1.f, 1.f, 1.f}, pos[4][3], nrm[3] = {0.f, 0.f, 1.f};
-    int cnt = 0, g1 = 0, g2 = 0;
-    float margin = 0.f;
+    bool keep = false;
     if (p < dm->npair) {
+      const int g1 = dm->pair_g1[p], g2 = dm->pair_g2[p];
+      const float slack = dm->pair_margin[p] + 1e-4f;
+      const float* a = sm + ar::GPOSE + g1 * 12;
+      const float* b = sm + ar::GPOSE + g2 * 12;
+      const float t[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+      if (dm->geom_type[g1] == RSRX_GEOM_PLANE) {
+        keep = a[3 + 2] * t[0] + a[3 + 5] * t[1] + a[3 + 8] * t[2] - dm->geom_rbound[g2] <= slack;
+      } else {
+        keep = true;
+        const float r1 = dm->geom_rbound[g1] + slack, r2 = dm->geom_rbound[g2] + slack;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const float ta = a[3 + i] * t[0] + a[6 + i] * t[1] + a[9 + i] * t[2];
+          const float tb = b[3 + i] * t[0] + b[6 + i] * t[1] + b[9 + i] * t[2];
+          if (fabsf(ta) > dm->geom_size[g1][i] + r2 || fabsf(tb) > dm->geom_size[g2][i] + r1) keep = false;
+        }
+      }
+    }
+    const unsigned kept = __ballot_sync(0xffffffffu, keep);
+    if (keep) plist[nsurv + __popc(kept & ((1u << lane) - 1u))] = p;
+    nsurv += __popc(kept);
+  }
+  RSRX_SYNC();
+  int ncon = 0;
+  for (int base = 0; base < nsurv; base += 32) {
+    float dist[4] = {1.f, 1.f, 1.f, 1.f}, pos[4][3], nrm[3] = {0.f, 0.f, 1.f};
+    int cnt = 0, g1 = 0, g2 = 0, p = 0;
+    float margin = 0.f;
+    if (base + lane < nsurv) {
+      p = plist[base + lane];
       g1 = dm->pair_g1[p]; g2 = dm->pair_g2[p];
       margin = dm->pair_margin[p];
       float s2[3] = {dm->geom_size[g2][0], dm->geom_size[g2][1], dm->geom_size[g2][2]};
-      float p1[3], m1[9], p2[3], m2[9];
-      geom_pose(dm, sm, g1, p1, m1);
-      geom_pose(dm, sm, g2, p2, m2);
+      const float* a = sm + ar::GPOSE + g1 * 12;
+      const float* b = sm + ar::GPOSE + g2 * 12;
       if (dm->geom_type[g1] == RSRX_GEOM_PLANE) {
-        plane_box(p1, m1, p2, m2, s2, dist, pos, nrm);
+        plane_box(a, a + 3, b, b + 3, s2, dist, pos, nrm);
       } else {
         float s1[3] = {dm->geom_size[g1][0], dm->geom_size[g1][1], dm->geom_size[g1][2]};
-        box_box(p1, m1, s1, p2, m2, s2, dist, pos, nrm);
+        box_box(a, a + 3, s1, b, b + 3, s2, dist, pos, nrm);
       }
       for (int c = 0; c < 4; c++) cnt += (dist[c] - margin < 0.f) ? 1 : 0;
     }

@@ -58,6 +58,7 @@ def main():
     by_line = collections.defaultdict(lambda: [0.0, 0.0])
     by_func = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
     stalls = collections.defaultdict(float)
+    fstall = collections.defaultdict(lambda: collections.defaultdict(float))
     tab = func_table(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "rsr_mjx_b200", "csrc"))
     tot_s = tot_i = 0.0
     for r in data:
@@ -70,6 +71,7 @@ def main():
         by_func[fn][0] += s; by_func[fn][1] += n; by_func[fn][2] += n * float(r[ithr] or 0)
         for i, h in stall_cols:
             stalls[h] += float(r[i] or 0)
+            fstall[h][fn] += float(r[i] or 0)
     print(f"total samples {tot_s:.0f}, warp instructions {tot_i:.3e}")
     print("--- by function (samples%, inst%, avg active threads)")
     for fn, (s, n, t) in sorted(by_func.items(), key=lambda kv: -kv[1][0]):
@@ -79,6 +81,10 @@ def main():
     ts = sum(stalls.values())
     for h, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:8]:
         print(f"  {100*v/ts:5.1f}%  {h}")
+    for h in ("stall_long_sb", "stall_short_sb", "stall_wait", "stall_branch_resolving"):
+        tot = sum(fstall[h].values()) or 1.0
+        best = sorted(fstall[h].items(), key=lambda kv: -kv[1])[:8]
+        print(f"--- {h} by function: " + ", ".join(f"{fn} {100*v/tot:.0f}%" for fn, v in best))
     print(f"--- top {top} lines")
     for key, (s, n) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:
         print(f"  {100*s/tot_s:5.2f}% samp {100*n/tot_i:5.2f}% inst  {key}")
