@@ -1,5 +1,6 @@
 // rsrx_api.cu — C-ABI of librsrx.so (include/rsrx.h): model upload and kernel
 // launches.  No torch types; the caller owns every state buffer.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -243,6 +244,11 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
       while (lo > 0 && d.body_treeid[b.dof_bodyid[d.dof_of_pos[lo - 1]]] == t) lo--;
       while (hi + 1 < b.nv && d.body_treeid[b.dof_bodyid[d.dof_of_pos[hi + 1]]] == t) hi++;
       d.tblk_start[q] = lo; d.tblk_end[q] = hi;
+    }
+    d.blk_max = d.tblk_max = 1;
+    for (int q = 0; q < b.nv; q++) {
+      d.blk_max = std::max(d.blk_max, d.blk_end[q] - d.blk_start[q] + 1);
+      d.tblk_max = std::max(d.tblk_max, d.tblk_end[q] - d.tblk_start[q] + 1);
     }
     d.nhent = 0;
     for (int i = 0; i < b.nv; i++)

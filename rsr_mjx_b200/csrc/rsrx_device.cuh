@@ -58,6 +58,7 @@ struct DModel {
   unsigned char tri_i[NTRI], tri_j[NTRI];
   // block permutation for the Cholesky factorisations + structurally non-zero entries of H
   int pos_of_dof[NV], dof_of_pos[NV], blk_start[NV], blk_end[NV], tblk_start[NV], tblk_end[NV], nhent;
+  int blk_max, tblk_max;  // size of the largest block / tree block
   unsigned char hent_i[NTRI], hent_j[NTRI];
   unsigned short tri_src[NTRI], tri_dst[NTRI];  // M[i][j] offset -> permuted H offset, per lower-triangle entry
   // geoms

@@ -211,22 +211,29 @@ __device__ __noinline__ void warp_chol_factor(const DModel* __restrict__ dm, flo
   const int p = own ? lane : n - 1;  // surplus lanes shadow the last row (reads only)
   float* row = A + p * LD;
   // tree_blocks: no contact couples two kinematic trees right now (always true for M itself), so the blocks are
-  // the trees (8 | 6 | 6 instead of 14 | 6 for the cube model)
+  // the trees (8 | 6 | 6 instead of 14 | 6 for the cube model).  The diagonal blocks are independent, so they are
+  // factored SIDE BY SIDE: in round kk every block eliminates its own kk-th column (pivot lane pstart + kk), and the
+  // dependency chain is as long as the largest block, not nv.  Per element the arithmetic is the sequential one.
+  const int pstart = tree_blocks ? dm->tblk_start[p] : dm->blk_start[p];
   const int pend = tree_blocks ? dm->tblk_end[p] : dm->blk_end[p];
+  const int rounds = tree_blocks ? dm->tblk_max : dm->blk_max;
   float rdiag = 1.f;
 #pragma unroll 1
-  for (int k = 0; k < n; ++k) {
-    const int kend = __shfl_sync(FULL, pend, k);
-    const float aik = row[k];
-    const float akk = __shfl_sync(FULL, aik, k);
+  for (int kk = 0; kk < rounds; ++kk) {
+    const int k = pstart + kk;
+    const bool act = own && k <= pend;  // my block still has a column kk
+    const int kc = act ? k : p;
+    const float aik = row[kc];
+    const float akk = __shfl_sync(FULL, aik, kc);
     const float rd = rsqrtf(akk > MJ_MINVAL ? akk : MJ_MINVAL);
-    const bool in = own && lane > k && lane <= kend;
+    const bool in = act && lane > k;
     const float l = in ? aik * rd : 0.f;
     if (in) row[k] = l;
-    if (own && lane == k) { row[k] = akk * rd; rdiag = rd; }
+    if (act && lane == k) { row[k] = akk * rd; rdiag = rd; }
 #pragma unroll 2
-    for (int j = k + 1; j <= kend; ++j) {
-      const float lj = __shfl_sync(FULL, l, j);
+    for (int jj = kk + 1; jj < rounds; ++jj) {
+      const int j = pstart + jj;
+      const float lj = __shfl_sync(FULL, l, j <= pend ? j : p);
       if (in && j <= lane) row[j] -= l * lj;
     }
   }
@@ -235,7 +242,7 @@ __device__ __noinline__ void warp_chol_factor(const DModel* __restrict__ dm, flo
 }
 
 // x <- (L L^T)^-1 x with the factor left in ar::HH by warp_chol_factor; x is an
-// nv-vector in dof order.
+// nv-vector in dof order.  Blocks side by side, as in the factorisation.
 __device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, float* sm, float* x, int lane, bool tree_blocks) {
   constexpr unsigned FULL = 0xffffffffu;
   const float* A = sm + ar::HH;
@@ -243,21 +250,26 @@ __device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, floa
   const bool own = lane < n;
   const int p = own ? lane : n - 1;
   const int pstart = tree_blocks ? dm->tblk_start[p] : dm->blk_start[p], pend = tree_blocks ? dm->tblk_end[p] : dm->blk_end[p];
+  const int rounds = tree_blocks ? dm->tblk_max : dm->blk_max;
   const int dof = dm->dof_of_pos[p];
   const float rdiag = sm[ar::V_RDIAG + p];
   const float* row = A + p * LD;
   float xi = x[dof];
 #pragma unroll 1
-  for (int k = 0; k < n; ++k) {  // forward: L y = b (row-oriented, own row)
-    const float yk = __shfl_sync(FULL, xi * rdiag, k);
-    if (own && lane == k) xi = yk;
-    else if (own && lane > k && k >= pstart) xi -= row[k] * yk;
+  for (int kk = 0; kk < rounds; ++kk) {  // forward: L y = b (row-oriented, own row)
+    const int k = pstart + kk;
+    const bool act = own && k <= pend;
+    const float yk = __shfl_sync(FULL, xi * rdiag, act ? k : p);
+    if (act && lane == k) xi = yk;
+    else if (act && lane > k) xi -= row[k] * yk;
   }
 #pragma unroll 1
-  for (int k = n - 1; k >= 0; --k) {  // backward: L^T x = y (column-oriented: row k is contiguous over lanes)
-    const float xk = __shfl_sync(FULL, xi * rdiag, k);
-    if (own && lane == k) xi = xk;
-    else if (own && lane < k && k <= pend) xi -= A[k * LD + p] * xk;
+  for (int kk = rounds - 1; kk >= 0; --kk) {  // backward: L^T x = y (column-oriented: row k is contiguous over lanes)
+    const int k = pstart + kk;
+    const bool act = own && k <= pend;
+    const float xk = __shfl_sync(FULL, xi * rdiag, act ? k : p);
+    if (act && lane == k) xi = xk;
+    else if (act && lane < k) xi -= A[k * LD + p] * xk;
   }
   if (own) x[dof] = xi;
   RSRX_SYNC();
