@@ -149,7 +149,8 @@ constexpr int P_END = CVEL + NB * 6;
 // ---- ... region C (collision only; P is dead by then, S not yet alive): world poses of all geoms + surviving pairs
 constexpr int GPOSE = U;                   // [g][12]: pos(3), mat(9)
 constexpr int PLIST = GPOSE + NG * 12;     // int [MAXPAIR]
-constexpr int C_END = PLIST + RSRX_MAXPAIR;
+constexpr int CSCRATCH = PLIST + RSRX_MAXPAIR;  // 8 clipped polygon vertices per half warp
+constexpr int C_END = CSCRATCH + 2 * 24;
 // ---- ... and region S (alive from make_constraint's contact pass to the end of the solver)
 constexpr int E_JAREF = U;
 constexpr int E_JV = E_JAREF + MAXROW;

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(32 * WPB) step_kernel(const DModel* __restrict
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * WPB + wib;
   float* sm = smem + wib * ar::TOTAL;
   if (e >= N) {
-    for (int f = 0; f < dm->n_frames * kPhaseBarriers; ++f) __syncthreads();  // shadow the phase barriers
+    for (int f = 0; f < dm->n_frames * kPhaseBarriers; ++f) phase_barrier<true>(__builtin_ctz(RSRX_SYNC_MASK));  // shadow the phase barriers
     return;
   }
   const rsrx_layout& L = dm->lay;

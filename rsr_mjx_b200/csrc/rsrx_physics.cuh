@@ -318,231 +318,283 @@ __device__ __noinline__ void crb_and_factor(const DModel* __restrict__ dm, float
 }
 
 // ------------------------------------------------------------------- collision
-// collision_convex.py::_manifold_points with deterministic tie-breaking (see
-// oracle/rsr_oracle.c and DESIGN.md): a taken vertex scores like a masked one.
-__device__ void manifold_points(const float (*poly)[3], const bool* mask, int n, const float* nrm, int idx[4]) {
-  float dmk[8];
-  int a = 0, b = 0, c = 0, d = 0;
-  for (int i = 0; i < n; i++) dmk[i] = mask[i] ? 0.f : -1e6f;
-  float best = dmk[0];
-  for (int i = 1; i < n; i++) if (dmk[i] > best) { best = dmk[i]; a = i; }
-  dmk[a] = -1e6f;
-  best = -1e30f;
-  for (int i = 0; i < n; i++) {
-    float t[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]};
-    float v = dot3(t, t) + dmk[i];
-    if (v > best) { best = v; b = i; }
+// The narrow phase is WARP-COOPERATIVE: after the bounding cull one or two pairs survive per env, so instead of one
+// lane per pair (a single lane walking 15 SAT axes through local memory) the whole warp works on one pair: one lane
+// per SAT axis / polygon vertex / contact slot, arg-min/max by redux + ballot (first index wins, like the sequential
+// scans of the oracle), everything in registers.
+constexpr unsigned FULLM = 0xffffffffu;
+// order-preserving float -> int (NaN lowest; -0 == +0)
+__device__ __forceinline__ int fkey(float f) {
+  f += 0.f;
+  const int b = __float_as_int(f);
+  return f != f ? INT_MIN : (b ^ ((b >> 31) & 0x7fffffff));
+}
+// A half warp (16 lanes) works on one geom pair; the two halves run side by side on two pairs.
+struct Half {
+  unsigned mask;  // member mask of this half
+  int shift;      // 0 or 16
+  int l;          // lane within the half
+  __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & 0xffffu; }
+  __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(mask, v, src, 16); }
+  __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, src, 16); }
+  __device__ __forceinline__ void shfl3(float* o, const float* v, int src) const {
+    o[0] = shfl(v[0], src); o[1] = shfl(v[1], src); o[2] = shfl(v[2], src);
   }
-  dmk[b] = -1e6f;
-  float ab[3], amb[3] = {poly[a][0] - poly[b][0], poly[a][1] - poly[b][1], poly[a][2] - poly[b][2]};
+  // first lane (of the half) holding the largest / smallest v among the valid lanes (0 if there is none)
+  __device__ __forceinline__ int argmax_first(float v, bool valid) const {
+    const int k = valid ? fkey(v) : INT_MIN;
+    const int m = __reduce_max_sync(mask, k);
+    return __ffs(ballot(k == m)) - 1;
+  }
+  __device__ __forceinline__ int argmin_first(float v, bool valid) const {
+    const int k = (valid && v == v) ? fkey(v) : INT_MAX;
+    const int m = __reduce_min_sync(mask, k);
+    return __ffs(ballot(k == m)) - 1;
+  }
+};
+__device__ __forceinline__ float sel3(const float* v, int k) { return k == 0 ? v[0] : (k == 1 ? v[1] : v[2]); }
+// column k of a row-major 3x3 / unit vector k, k a run-time index (selects, no local memory)
+__device__ __forceinline__ void col3(float* o, const float* R, int k) {
+  o[0] = k == 0 ? R[0] : (k == 1 ? R[1] : R[2]);
+  o[1] = k == 0 ? R[3] : (k == 1 ? R[4] : R[5]);
+  o[2] = k == 0 ? R[6] : (k == 1 ? R[7] : R[8]);
+}
+__device__ __forceinline__ void unit3(float* o, int k) { o[0] = k == 0 ? 1.f : 0.f; o[1] = k == 1 ? 1.f : 0.f; o[2] = k == 2 ? 1.f : 0.f; }
+
+// collision_convex.py::_manifold_points with deterministic tie-breaking (see oracle/rsr_oracle.c and DESIGN.md: a
+// taken vertex scores like a masked one).  Lane i < n holds vertex i (P, mask); idx[] comes back in every lane.
+__device__ void manifold_points(const float* P, bool mask, int n, const float* nrm, const Half& hw, int idx[4]) {
+  const bool has = hw.l < n;
+  float dmk = mask ? 0.f : -1e6f;
+  const int a = hw.argmax_first(dmk, has);
+  if (hw.l == a) dmk = -1e6f;
+  float A[3], B[3], C[3];
+  hw.shfl3(A, P, a);
+  const float ap[3] = {A[0] - P[0], A[1] - P[1], A[2] - P[2]};
+  const int b = hw.argmax_first(dot3(ap, ap) + dmk, has);
+  if (hw.l == b) dmk = -1e6f;
+  hw.shfl3(B, P, b);
+  float ab[3];
+  const float amb[3] = {A[0] - B[0], A[1] - B[1], A[2] - B[2]};
   cross3(ab, nrm, amb);
-  best = -1e30f;
-  for (int i = 0; i < n; i++) {
-    float ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]};
-    float v = fabsf(dot3(ap, ab)) + dmk[i];
-    if (v > best) { best = v; c = i; }
-  }
-  dmk[c] = -1e6f;
+  const int c = hw.argmax_first(fabsf(dot3(ap, ab)) + dmk, has);
+  if (hw.l == c) dmk = -1e6f;
+  hw.shfl3(C, P, c);
   float ac[3], bc[3];
-  float amc[3] = {poly[a][0] - poly[c][0], poly[a][1] - poly[c][1], poly[a][2] - poly[c][2]};
-  float bmc[3] = {poly[b][0] - poly[c][0], poly[b][1] - poly[c][1], poly[b][2] - poly[c][2]};
+  const float amc[3] = {A[0] - C[0], A[1] - C[1], A[2] - C[2]};
+  const float bmc[3] = {B[0] - C[0], B[1] - C[1], B[2] - C[2]};
   cross3(ac, nrm, amc);
   cross3(bc, nrm, bmc);
-  best = -1e30f;
-  for (int i = 0; i < n; i++) {
-    float bp[3] = {poly[b][0] - poly[i][0], poly[b][1] - poly[i][1], poly[b][2] - poly[i][2]};
-    float v = fabsf(dot3(bp, bc)) + dmk[i];
-    if (v > best) { best = v; d = i; }
-  }
-  for (int i = 0; i < n; i++) {
-    float ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]};
-    float v = fabsf(dot3(ap, ac)) + dmk[i];
-    if (v > best) { best = v; d = i; }
-  }
-  idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = d;
+  const float bp[3] = {B[0] - P[0], B[1] - P[1], B[2] - P[2]};
+  const float v1 = fabsf(dot3(bp, bc)) + dmk, v2 = fabsf(dot3(ap, ac)) + dmk;
+  const int d1 = hw.argmax_first(v1, has), d2 = hw.argmax_first(v2, has);
+  const float best1 = hw.shfl(v1, d1), best2 = hw.shfl(v2, d2);
+  idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = best2 > best1 ? d2 : d1;
 }
 
-// collision_convex.py::plane_convex on the 8 box vertices
+// Result of a narrow phase: lane c < 4 of the half holds contact slot c (dist >= 0: none); nrm is uniform.
+struct Manifold { float dist, pos[3], nrm[3]; };
+
+// collision_convex.py::plane_convex on the 8 box vertices (lane k < 8 of the half: vertex k)
 __device__ void plane_box(const float* ppos, const float* pmat, const float* bpos, const float* bmat, const float* size,
-                          float dist[4], float pos[4][3], float nrm[3]) {
-  float vert[8][3], support[8], n[3], pp[3], d[3];
-  float pn[3] = {pmat[2], pmat[5], pmat[8]};
+                          const Half& hw, Manifold* out) {
+  float n[3], pp[3], d[3];
+  const float pn[3] = {pmat[2], pmat[5], pmat[8]};
   for (int i = 0; i < 3; i++) d[i] = ppos[i] - bpos[i];
   matT_vec(pp, bmat, d);
   matT_vec(n, bmat, pn);
-  float smax = -1e30f;
-  for (int k = 0; k < 8; k++) {
-    vert[k][0] = (k & 1) ? size[0] : -size[0];
-    vert[k][1] = (k & 2) ? size[1] : -size[1];
-    vert[k][2] = (k & 4) ? size[2] : -size[2];
-    float t[3] = {pp[0] - vert[k][0], pp[1] - vert[k][1], pp[2] - vert[k][2]};
-    support[k] = dot3(t, n);
-    if (support[k] > smax) smax = support[k];
-  }
-  bool mask[8];
+  const float vert[3] = {(hw.l & 1) ? size[0] : -size[0], (hw.l & 2) ? size[1] : -size[1], (hw.l & 4) ? size[2] : -size[2]};
+  const float tv[3] = {pp[0] - vert[0], pp[1] - vert[1], pp[2] - vert[2]};
+  const float support = dot3(tv, n);
+  const float smax = hw.shfl(support, hw.argmax_first(support, hw.l < 8));
   float thr = smax - 1e-3f;
   if (thr < 0.f) thr = 0.f;
-  for (int k = 0; k < 8; k++) mask[k] = support[k] > thr;
   int idx[4];
-  manifold_points(vert, mask, 8, n, idx);
-  for (int c = 0; c < 4; c++) {
-    bool unique = true;
-    for (int e = 0; e < c; e++) if (idx[e] == idx[c]) unique = false;
-    float wp[3];
-    mat_vec(wp, bmat, vert[idx[c]]);
-    dist[c] = unique ? -support[idx[c]] : 1.f;
-    for (int i = 0; i < 3; i++) pos[c][i] = bpos[i] + wp[i] - 0.5f * dist[c] * pn[i];
-  }
-  for (int i = 0; i < 3; i++) nrm[i] = pn[i];
+  manifold_points(vert, support > thr, 8, n, hw, idx);
+  const int c = hw.l & 3;
+  const int k = c == 0 ? idx[0] : c == 1 ? idx[1] : c == 2 ? idx[2] : idx[3];
+  bool unique = true;
+  if (c > 0 && idx[0] == k) unique = false;
+  if (c > 1 && idx[1] == k) unique = false;
+  if (c > 2 && idx[2] == k) unique = false;
+  float vk[3], wp[3];
+  hw.shfl3(vk, vert, k);
+  const float sk = hw.shfl(support, k);
+  mat_vec(wp, bmat, vk);
+  out->dist = unique ? -sk : 1.f;
+  for (int i = 0; i < 3; i++) { out->pos[i] = bpos[i] + wp[i] - 0.5f * out->dist * pn[i]; out->nrm[i] = pn[i]; }
 }
 
-__device__ int clip_halfspace(float (*poly)[3], int n, const float* pn, float h, float (*out)[3]) {
-  int no = 0;
-  for (int i = 0; i < n; i++) {
-    const float* a = poly[i];
-    const float* b = poly[(i + 1) % n];
-    float da = dot3(a, pn) - h, db = dot3(b, pn) - h;
-    if (da <= 0.f) { out[no][0] = a[0]; out[no][1] = a[1]; out[no][2] = a[2]; no++; }
-    if ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f)) {
-      float t = da / (da - db);
-      out[no][0] = a[0] + t * (b[0] - a[0]); out[no][1] = a[1] + t * (b[1] - a[1]); out[no][2] = a[2] + t * (b[2] - a[2]);
-      no++;
-    }
-  }
-  return no;
-}
-
-// SAT + face clipping / edge-edge; same rules as the oracle
+// SAT + face clipping / edge-edge; same rules as the oracle.  Works in box 2's frame, where
+// box 2's axes are the unit vectors and box 1's are the columns of R.  scratch: 24 floats of shared memory.
 __device__ void box_box(const float* p1, const float* m1, const float* s1, const float* p2, const float* m2,
-                        const float* s2, float dist[4], float pos[4][3], float nrm[3]) {
+                        const float* s2, float* scratch, const Half& hw, Manifold* out) {
   float R[9], t[3], d[3];
   for (int i = 0; i < 3; i++) d[i] = p1[i] - p2[i];
   matT_vec(t, m2, d);
   for (int r = 0; r < 3; r++)
     for (int c = 0; c < 3; c++) R[r * 3 + c] = m2[r] * m1[c] + m2[3 + r] * m1[3 + c] + m2[6 + r] * m1[6 + c];
-  float axA[3][3], axB[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
-  for (int a = 0; a < 3; a++) for (int i = 0; i < 3; i++) axA[a][i] = R[i * 3 + a];
-  float bestf = 1e30f, beste = 1e30f, sgnf = 1.f, sgne = 1.f;
-  int bf = 0, be = 6;
-  float axf[3] = {0.f, 0.f, 0.f}, axe[3] = {0.f, 0.f, 0.f};
-  for (int k = 0; k < 15; k++) {
-    float ax[3];
-    bool degenerate = false;
-    if (k < 3) { ax[0] = axA[k][0]; ax[1] = axA[k][1]; ax[2] = axA[k][2]; }
-    else if (k < 6) { ax[0] = axB[k - 3][0]; ax[1] = axB[k - 3][1]; ax[2] = axB[k - 3][2]; }
-    else {
-      cross3(ax, axA[(k - 6) % 3], axB[(k - 6) / 3]);
-      degenerate = dot3(ax, ax) < 1e-6f;
-      normalize3(ax);
-    }
-    float ca = dot3(t, ax);
-    float ra = s1[0] * fabsf(dot3(axA[0], ax)) + s1[1] * fabsf(dot3(axA[1], ax)) + s1[2] * fabsf(dot3(axA[2], ax));
-    float rb = s2[0] * fabsf(ax[0]) + s2[1] * fabsf(ax[1]) + s2[2] * fabsf(ax[2]);
-    float dist1 = (ca + ra) - (-rb);
-    float dist2 = rb - (ca - ra);
-    float sg = dist1 > dist2 ? -1.f : 1.f;
-    float ov = dist1 < dist2 ? dist1 : dist2;
-    if (degenerate) ov = 1e6f;
-    if (k < 6) {
-      if (ov < bestf) { bestf = ov; bf = k; sgnf = sg; axf[0] = ax[0]; axf[1] = ax[1]; axf[2] = ax[2]; }
-    } else {
-      if (ov < beste) { beste = ov; be = k; sgne = sg; axe[0] = ax[0]; axe[1] = ax[1]; axe[2] = ax[2]; }
-    }
+  // --- 15 separating-axis candidates, one per lane
+  const int k = hw.l < 15 ? hw.l : 14;
+  float ax[3];
+  bool degenerate = false;
+  if (k < 3) col3(ax, R, k);
+  else if (k < 6) unit3(ax, k - 3);
+  else {
+    float ea[3], eb[3];
+    col3(ea, R, (k - 6) % 3);
+    unit3(eb, (k - 6) / 3);
+    cross3(ax, ea, eb);
+    degenerate = dot3(ax, ax) < 1e-6f;
+    normalize3(ax);
   }
+  float ov, sg;
+  {
+    const float a0[3] = {R[0], R[3], R[6]}, a1[3] = {R[1], R[4], R[7]}, a2[3] = {R[2], R[5], R[8]};
+    const float ca = dot3(t, ax);
+    const float ra = s1[0] * fabsf(dot3(a0, ax)) + s1[1] * fabsf(dot3(a1, ax)) + s1[2] * fabsf(dot3(a2, ax));
+    const float rb = s2[0] * fabsf(ax[0]) + s2[1] * fabsf(ax[1]) + s2[2] * fabsf(ax[2]);
+    const float dist1 = (ca + ra) - (-rb);
+    const float dist2 = rb - (ca - ra);
+    sg = dist1 > dist2 ? -1.f : 1.f;
+    ov = dist1 < dist2 ? dist1 : dist2;
+    if (degenerate) ov = 1e6f;
+  }
+  const int bf = hw.argmin_first(ov, hw.l < 6), be = hw.argmin_first(ov, hw.l >= 6 && hw.l < 15);
+  const float bestf = hw.shfl(ov, bf), beste = hw.shfl(ov, be);
   const bool is_edge = beste * 1.05f < bestf;
   const int best = is_edge ? be : bf;
   const float bov = is_edge ? beste : bestf;
+  const float sgb = hw.shfl(sg, best);
   float n[3];
-  if (is_edge) { n[0] = axe[0] * sgne; n[1] = axe[1] * sgne; n[2] = axe[2] * sgne; }
-  else { n[0] = axf[0] * sgnf; n[1] = axf[1] * sgnf; n[2] = axf[2] * sgnf; }
-  float lp[4][3];
-  for (int c = 0; c < 4; c++) { dist[c] = 1.f; lp[c][0] = lp[c][1] = lp[c][2] = 0.f; }
+  hw.shfl3(n, ax, best);
+  n[0] *= sgb; n[1] *= sgb; n[2] *= sgb;
+  float dist = 1.f, lp[3] = {0.f, 0.f, 0.f};
   if (bov < 0.f) {
     // separated
   } else if (!is_edge) {
     const bool refA = best < 3;
     const int r = refA ? best : best - 3;
-    const float (*axP)[3] = refA ? axA : axB;
-    const float (*axQ)[3] = refA ? axB : axA;
-    const float* hP = refA ? s1 : s2;
-    const float* hQ = refA ? s2 : s1;
-    float cP[3], cQ[3], nref[3];
-    for (int i = 0; i < 3; i++) { cP[i] = refA ? t[i] : 0.f; cQ[i] = refA ? 0.f : t[i]; nref[i] = refA ? n[i] : -n[i]; }
+    // axP / axQ: axes of the reference / incident box
+    float hP[3], hQ[3], cP[3], cQ[3], nref[3];
+    for (int i = 0; i < 3; i++) {
+      hP[i] = refA ? s1[i] : s2[i]; hQ[i] = refA ? s2[i] : s1[i];
+      cP[i] = refA ? t[i] : 0.f; cQ[i] = refA ? 0.f : t[i]; nref[i] = refA ? n[i] : -n[i];
+    }
     int q = 0;
     float bestd = -1.f;
-    for (int k = 0; k < 3; k++) { float v = fabsf(dot3(axQ[k], nref)); if (v > bestd) { bestd = v; q = k; } }
-    const float sq = dot3(axQ[q], nref) > 0.f ? -1.f : 1.f;
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) {
+      float aq[3];
+      if (refA) unit3(aq, kk); else col3(aq, R, kk);
+      const float v = fabsf(dot3(aq, nref));
+      if (v > bestd) { bestd = v; q = kk; }
+    }
     const int u = (q + 1) % 3, v = (q + 2) % 3;
-    float poly[8][3], tmp[8][3];
-    const float su[4] = {1.f, -1.f, -1.f, 1.f}, sv[4] = {1.f, 1.f, -1.f, -1.f};
-    for (int k = 0; k < 4; k++)
-      for (int i = 0; i < 3; i++)
-        poly[k][i] = cQ[i] + sq * hQ[q] * axQ[q][i] + su[k] * hQ[u] * axQ[u][i] + sv[k] * hQ[v] * axQ[v][i];
+    float aq[3], au[3], av[3];
+    if (refA) { unit3(aq, q); unit3(au, u); unit3(av, v); } else { col3(aq, R, q); col3(au, R, u); col3(av, R, v); }
+    const float sq = dot3(aq, nref) > 0.f ? -1.f : 1.f;
+    const float su = (hw.l == 0 || hw.l == 3) ? 1.f : -1.f, sv = hw.l < 2 ? 1.f : -1.f;
+    const float hq = sel3(hQ, q), hu = sel3(hQ, u), hv = sel3(hQ, v);
+    float P[3];
+    for (int i = 0; i < 3; i++) P[i] = cQ[i] + sq * hq * aq[i] + su * hu * au[i] + sv * hv * av[i];
     int np = 4;
     const int pu = (r + 1) % 3, pv = (r + 2) % 3;
+#pragma unroll 1
     for (int s = 0; s < 4 && np > 0; s++) {
       const int sa = s < 2 ? pu : pv;
-      const float sg = (s & 1) ? -1.f : 1.f;
-      float pn[3] = {sg * axP[sa][0], sg * axP[sa][1], sg * axP[sa][2]};
-      float h = hP[sa] + dot3(cP, pn);
-      np = clip_halfspace(poly, np, pn, h, tmp);
-      for (int k = 0; k < np; k++) { poly[k][0] = tmp[k][0]; poly[k][1] = tmp[k][1]; poly[k][2] = tmp[k][2]; }
+      const float sgn = (s & 1) ? -1.f : 1.f;
+      float pn[3];
+      if (refA) col3(pn, R, sa); else unit3(pn, sa);
+      pn[0] *= sgn; pn[1] *= sgn; pn[2] *= sgn;
+      const float h = sel3(hP, sa) + dot3(cP, pn);
+      // Sutherland-Hodgman against pn . x <= h: lane i owns edge (i, i + 1)
+      const bool has = hw.l < np;
+      const int nxt = hw.l + 1 < np ? hw.l + 1 : 0;
+      const float da = dot3(P, pn) - h;
+      float Q[3];
+      hw.shfl3(Q, P, nxt);
+      const float db = hw.shfl(da, nxt);
+      const bool keep = has && da <= 0.f;
+      const bool cut = has && ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f));
+      const unsigned mk = hw.ballot(keep), mc = hw.ballot(cut), lt = (1u << hw.l) - 1u;
+      const int off = __popc(mk & lt) + __popc(mc & lt);
+      if (keep && off < 8) { scratch[off * 3] = P[0]; scratch[off * 3 + 1] = P[1]; scratch[off * 3 + 2] = P[2]; }
+      if (cut && off + (keep ? 1 : 0) < 8) {
+        const float tt = da / (da - db);
+        float* o = scratch + (off + (keep ? 1 : 0)) * 3;
+        o[0] = P[0] + tt * (Q[0] - P[0]); o[1] = P[1] + tt * (Q[1] - P[1]); o[2] = P[2] + tt * (Q[2] - P[2]);
+      }
+      __syncwarp(hw.mask);
+      np = __popc(mk) + __popc(mc);
+      if (np > 8) np = 8;
+      if (hw.l < np) { P[0] = scratch[hw.l * 3]; P[1] = scratch[hw.l * 3 + 1]; P[2] = scratch[hw.l * 3 + 2]; }
+      __syncwarp(hw.mask);
     }
     if (np > 0) {
-      float depth[8], ref[8][3];
-      bool mask[8];
-      for (int k = 0; k < np; k++) {
-        float rel[3] = {poly[k][0] - cP[0], poly[k][1] - cP[1], poly[k][2] - cP[2]};
-        depth[k] = hP[r] - dot3(rel, nref);
-        mask[k] = depth[k] > 0.f;
-        for (int i = 0; i < 3; i++) ref[k][i] = poly[k][i] + depth[k] * nref[i];
-      }
+      const float rel[3] = {P[0] - cP[0], P[1] - cP[1], P[2] - cP[2]};
+      const float depth = sel3(hP, r) - dot3(rel, nref);
+      const bool mask = depth > 0.f;
+      const float ref[3] = {P[0] + depth * nref[0], P[1] + depth * nref[1], P[2] + depth * nref[2]};
       int idx[4];
-      manifold_points(ref, mask, np, nref, idx);
-      for (int c = 0; c < 4; c++) {
-        bool unique = true;
-        for (int e = 0; e < c; e++) if (idx[e] == idx[c]) unique = false;
-        const int k = idx[c];
-        if (unique && mask[k]) {
-          dist[c] = -depth[k];
-          for (int i = 0; i < 3; i++) lp[c][i] = poly[k][i] + 0.5f * depth[k] * nref[i];
-        }
+      manifold_points(ref, mask, np, nref, hw, idx);
+      const int c = hw.l & 3;
+      const int kx = c == 0 ? idx[0] : c == 1 ? idx[1] : c == 2 ? idx[2] : idx[3];
+      bool unique = true;
+      if (c > 0 && idx[0] == kx) unique = false;
+      if (c > 1 && idx[1] == kx) unique = false;
+      if (c > 2 && idx[2] == kx) unique = false;
+      float Pk[3];
+      hw.shfl3(Pk, P, kx);
+      const float dk = hw.shfl(depth, kx);
+      const bool mk2 = hw.shfl(mask ? 1 : 0, kx) != 0;
+      if (unique && mk2) {
+        dist = -dk;
+        for (int i = 0; i < 3; i++) lp[i] = Pk[i] + 0.5f * dk * nref[i];
       }
     }
   } else {
+    // edge-edge: closest points of the two supporting edges (uniform arithmetic, reported in slot 0)
     const int ia = (best - 6) % 3, jb = (best - 6) / 3;
     float ea[3], eb[3];
     for (int i = 0; i < 3; i++) { ea[i] = t[i]; eb[i] = 0.f; }
-    for (int k = 0; k < 3; k++) {
-      if (k != ia) {
-        float s = dot3(axA[k], n) >= 0.f ? 1.f : -1.f;
-        for (int i = 0; i < 3; i++) ea[i] += s * s1[k] * axA[k][i];
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) {
+      float aA[3], aB[3];
+      col3(aA, R, kk);
+      unit3(aB, kk);
+      if (kk != ia) {
+        const float sA = dot3(aA, n) >= 0.f ? 1.f : -1.f;
+        for (int i = 0; i < 3; i++) ea[i] += sA * s1[kk] * aA[i];
       }
-      if (k != jb) {
-        float s = dot3(axB[k], n) >= 0.f ? 1.f : -1.f;
-        for (int i = 0; i < 3; i++) eb[i] -= s * s2[k] * axB[k][i];
+      if (kk != jb) {
+        const float sB = dot3(aB, n) >= 0.f ? 1.f : -1.f;
+        for (int i = 0; i < 3; i++) eb[i] -= sB * s2[kk] * aB[i];
       }
     }
-    const float* ua = axA[ia];
-    const float* ub = axB[jb];
-    float w0[3] = {ea[0] - eb[0], ea[1] - eb[1], ea[2] - eb[2]};
-    float bb = dot3(ua, ub), dd = dot3(ua, w0), ee = dot3(ub, w0);
-    float den = 1.f - bb * bb;
+    float ua[3], ub[3];
+    col3(ua, R, ia);
+    unit3(ub, jb);
+    const float w0[3] = {ea[0] - eb[0], ea[1] - eb[1], ea[2] - eb[2]};
+    const float bb = dot3(ua, ub), dd = dot3(ua, w0), ee = dot3(ub, w0);
+    const float den = 1.f - bb * bb;
     float sa = den > 1e-12f ? (bb * ee - dd) / den : 0.f;
     float sb = den > 1e-12f ? (ee - bb * dd) / den : 0.f;
-    sa = clipf(sa, -s1[ia], s1[ia]);
-    sb = clipf(sb, -s2[jb], s2[jb]);
+    const float h1 = sel3(s1, ia), h2 = sel3(s2, jb);
+    sa = clipf(sa, -h1, h1);
+    sb = clipf(sb, -h2, h2);
     float pa[3], pb[3], df[3];
     for (int i = 0; i < 3; i++) { pa[i] = ea[i] + sa * ua[i]; pb[i] = eb[i] + sb * ub[i]; df[i] = pb[i] - pa[i]; }
-    dist[0] = dot3(df, n);
-    for (int i = 0; i < 3; i++) lp[0][i] = 0.5f * (pa[i] + pb[i]);
+    if ((hw.l & 3) == 0) {
+      dist = dot3(df, n);
+      for (int i = 0; i < 3; i++) lp[i] = 0.5f * (pa[i] + pb[i]);
+    }
   }
-  for (int c = 0; c < 4; c++) {
-    float wp[3];
-    mat_vec(wp, m2, lp[c]);
-    for (int i = 0; i < 3; i++) pos[c][i] = p2[i] + wp[i];
-  }
-  mat_vec(nrm, m2, n);
+  float wp[3];
+  mat_vec(wp, m2, lp);
+  out->dist = dist;
+  for (int i = 0; i < 3; i++) out->pos[i] = p2[i] + wp[i];
+  mat_vec(out->nrm, m2, n);
 }
 
 // constraint.py::_kbi
@@ -573,8 +625,8 @@ __device__ __noinline__ void kbi(const DModel* __restrict__ dm, const float* sol
 //  1. one lane per geom pair: conservative bounding test (box centre + bounding radius against the plane / against the
 //     other box's faces).  A culled pair is one the narrow phase would report no contact for (a separating face axis
 //     exists), so the contact list is unchanged; survivors are compacted in pair order;
-//  2. one lane per surviving pair: narrow phase in registers/local memory, warp prefix-sum compaction of the active
-//     contacts into the shared-memory contact list in (pair, slot) order.  Contacts that MJX would keep as zeroed rows
+//  2. one half warp per surviving pair (two pairs side by side): cooperative narrow phase in registers, the active
+//     contacts appended to the shared-memory contact list in (pair, slot) order.  Contacts that MJX would keep as zeroed rows
 //     (dist >= 0) are dropped.  Returns ncon.
 __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, int lane, int* status) {
   for (int g = lane; g < dm->ngeom; g += 32) {
@@ -614,38 +666,41 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
     nsurv += __popc(kept);
   }
   RSRX_SYNC();
+#ifdef RSRX_PRINT_NSURV
+  if (lane == 0) { printf("NSURV %d :", nsurv); for (int q = 0; q < nsurv; q++) printf(" %d-%d", dm->pair_g1[plist[q]], dm->pair_g2[plist[q]]); printf("\n"); }
+#endif
   int ncon = 0;
-  for (int base = 0; base < nsurv; base += 32) {
-    float dist[4] = {1.f, 1.f, 1.f, 1.f}, pos[4][3], nrm[3] = {0.f, 0.f, 1.f};
-    int cnt = 0, g1 = 0, g2 = 0, p = 0;
-    float margin = 0.f;
-    if (base + lane < nsurv) {
-      p = plist[base + lane];
-      g1 = dm->pair_g1[p]; g2 = dm->pair_g2[p];
-      margin = dm->pair_margin[p];
-      float s2[3] = {dm->geom_size[g2][0], dm->geom_size[g2][1], dm->geom_size[g2][2]};
+  Half hw;
+  hw.shift = lane & 16; hw.l = lane & 15; hw.mask = 0xffffu << hw.shift;
+#pragma unroll 1
+  for (int sv = 0; sv < nsurv; sv += 2) {
+    const int mine = sv + (lane >> 4);  // the pair this half works on
+    const bool valid = mine < nsurv;
+    const int p = plist[valid ? mine : sv];
+    const int g1 = dm->pair_g1[p], g2 = dm->pair_g2[p];
+    const float margin = dm->pair_margin[p];
+    Manifold mf;
+    mf.dist = 1.f;
+    if (valid) {
+      const float s2[3] = {dm->geom_size[g2][0], dm->geom_size[g2][1], dm->geom_size[g2][2]};
       const float* a = sm + ar::GPOSE + g1 * 12;
       const float* b = sm + ar::GPOSE + g2 * 12;
       if (dm->geom_type[g1] == RSRX_GEOM_PLANE) {
-        plane_box(a, a + 3, b, b + 3, s2, dist, pos, nrm);
+        plane_box(a, a + 3, b, b + 3, s2, hw, &mf);
       } else {
-        float s1[3] = {dm->geom_size[g1][0], dm->geom_size[g1][1], dm->geom_size[g1][2]};
-        box_box(a, a + 3, s1, b, b + 3, s2, dist, pos, nrm);
+        const float s1[3] = {dm->geom_size[g1][0], dm->geom_size[g1][1], dm->geom_size[g1][2]};
+        box_box(a, a + 3, s1, b, b + 3, s2, sm + ar::CSCRATCH + (lane >> 4) * 24, hw, &mf);
       }
-      for (int c = 0; c < 4; c++) cnt += (dist[c] - margin < 0.f) ? 1 : 0;
     }
-    // exclusive prefix sum of cnt over lanes
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int slot = ncon + incl - cnt;
-    if (cnt > 0) {
+    __syncwarp();
+    const bool active = valid && hw.l < 4 && (mf.dist - margin < 0.f);
+    const unsigned am = __ballot_sync(0xffffffffu, active);
+    if (am == 0u) continue;
+    const int slot = ncon + __popc(am & ((1u << lane) - 1u));
+    if (ncon + __popc(am) > MAXC) *status |= RSRX_STATUS_CONTACT_OVERFLOW;
+    if (active && slot < MAXC) {
       float frame[9];
-      make_frame(frame, nrm);
+      make_frame(frame, mf.nrm);
       const int b1 = dm->geom_bodyid[g1], b2 = dm->geom_bodyid[g2];
       float mu[3];
       const float* gfric_e = reinterpret_cast<const float* const*>(sm + ar::PTRS)[0];
@@ -659,30 +714,25 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
       for (int i = 0; i < 5; i++) solimp[i] = dm->pair_solimp[p][i];
       const float tran = dm->pair_tran[p];
       const float invw = (tran + mu[0] * mu[0] * tran) * 2.f * mu[0] * mu[0] / dm->impratio;
-      for (int c = 0; c < 4; c++) {
-        if (!(dist[c] - margin < 0.f)) continue;
-        if (slot >= MAXC) { *status |= RSRX_STATUS_CONTACT_OVERFLOW; break; }
-        float* cr = sm + ar::CON + slot * ar::CSTRIDE;
-        for (int i = 0; i < 3; i++) cr[cf::POS + i] = pos[c][i];
-        for (int i = 0; i < 9; i++) cr[cf::FRAME + i] = frame[i];
-        const float ps = dist[c] - margin;
-        float k, b, imp;
-        kbi(dm, solref, solimp, ps, &k, &b, &imp);
-        float rr = invw * (1.f - imp) / imp;
-        if (rr < MJ_MINVAL) rr = MJ_MINVAL;
-        cr[cf::DIST] = dist[c];
-        cr[cf::MU] = mu[0]; cr[cf::MU + 1] = mu[0]; cr[cf::MU + 2] = mu[1];
-        cr[cf::KIMPD] = k * imp * ps;
-        cr[cf::B] = b;
-        cr[cf::D] = 1.f / rr;
-        cr[cf::BODIES] = __int_as_float(b1 | (b2 << 8) | (g1 << 16) | (g2 << 24));
-        cr[cf::COLS] = __int_as_float(cols);
-        slot++;
-      }
+      float* cr = sm + ar::CON + slot * ar::CSTRIDE;
+      for (int i = 0; i < 3; i++) cr[cf::POS + i] = mf.pos[i];
+      for (int i = 0; i < 9; i++) cr[cf::FRAME + i] = frame[i];
+      const float ps = mf.dist - margin;
+      float k, bb, imp;
+      kbi(dm, solref, solimp, ps, &k, &bb, &imp);
+      float rr = invw * (1.f - imp) / imp;
+      if (rr < MJ_MINVAL) rr = MJ_MINVAL;
+      cr[cf::DIST] = mf.dist;
+      cr[cf::MU] = mu[0]; cr[cf::MU + 1] = mu[0]; cr[cf::MU + 2] = mu[1];
+      cr[cf::KIMPD] = k * imp * ps;
+      cr[cf::B] = bb;
+      cr[cf::D] = 1.f / rr;
+      cr[cf::BODIES] = __int_as_float(b1 | (b2 << 8) | (g1 << 16) | (g2 << 24));
+      cr[cf::COLS] = __int_as_float(cols);
     }
-    ncon += total;
-    RSRX_SYNC();
+    ncon += __popc(am);
   }
+  RSRX_SYNC();
   if (ncon > MAXC) ncon = MAXC;
   return ncon;
 }
@@ -1366,10 +1416,24 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
 #ifndef RSRX_SYNC_MASK
 #define RSRX_SYNC_MASK 1  // measured: the substep-start barrier alone is best (6.30 ms vs 6.46-6.49 with more)
 #endif
+#ifndef RSRX_BAR_GROUPS
+#define RSRX_BAR_GROUPS 1
+#endif
+#ifndef RSRX_WPB
+#define RSRX_WPB 14
+#endif
 constexpr int kPhaseBarriers = __builtin_popcount(RSRX_SYNC_MASK & 0x3f);
 template <bool SYNC>
 __device__ __forceinline__ void phase_barrier(int bit) {
-  if (SYNC && ((RSRX_SYNC_MASK >> bit) & 1)) __syncthreads();
+  if (SYNC && ((RSRX_SYNC_MASK >> bit) & 1)) {
+#if RSRX_BAR_GROUPS == 1
+    __syncthreads();
+#else
+    // experiment: the CTA's warps re-align in RSRX_BAR_GROUPS independent groups (named barriers 1..)
+    constexpr int per = RSRX_WPB / RSRX_BAR_GROUPS;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / per), "n"(32 * per) : "memory");
+#endif
+  }
 }
 
 // forward.py::forward.  Returns niter; fills dims.
