@@ -1287,10 +1287,26 @@ __device__ __noinline__ int linesearch(const DModel* __restrict__ dm, float* sm,
         if (x < 0.f) { q[3 * a] += c0; q[3 * a + 1] += c1; q[3 * a + 2] += c2; }
       }
     }
-#pragma unroll 1
-    for (int o = 16; o; o >>= 1) {
+    // warp sums of the nine partials in 22 shuffles instead of 45: q[0..7] by recursive halving (each step a lane
+    // keeps half of its values and hands the other half to its partner), broadcast back from lanes 0, 4, .., 28;
+    // q[8] by a plain butterfly.  Every lane ends up with the same bits.
+    {
+      constexpr unsigned FULL = 0xffffffffu;
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+      float r4[4], r2[2];
 #pragma unroll
-      for (int i = 0; i < 9; i++) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+      for (int i = 0; i < 4; i++) r4[i] = (b4 ? q[i + 4] : q[i]) + __shfl_xor_sync(FULL, b4 ? q[i] : q[i + 4], 16);
+#pragma unroll
+      for (int i = 0; i < 2; i++) r2[i] = (b3 ? r4[i + 2] : r4[i]) + __shfl_xor_sync(FULL, b3 ? r4[i] : r4[i + 2], 8);
+      float r1 = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 4);
+      r1 += __shfl_xor_sync(FULL, r1, 2);
+      r1 += __shfl_xor_sync(FULL, r1, 1);
+      float q8 = q[8];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) q8 += __shfl_xor_sync(FULL, q8, o);
+#pragma unroll
+      for (int i = 0; i < 8; i++) q[i] = __shfl_sync(FULL, r1, 4 * i);
+      q[8] = q8;
     }
     LSPoint pt[3];
 #pragma unroll
@@ -1376,10 +1392,12 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
     return 0;
   }
   float gauss;
-  const float cw = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::WARM, &gauss);
+  // warm start: whichever of qacc_warmstart / qacc_smooth costs less.  The warm start usually wins, so it is
+  // evaluated last and its context is simply kept.
   const float cs = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::V_QACCS, &gauss);
-  float cost = cs;
-  if (cw < cs) cost = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::WARM, &gauss);
+  const float cw = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::WARM, &gauss);
+  float cost = cw;
+  if (!(cw < cs)) cost = ctx_create(dm, sm, lane, nsr, ncon, sm + ar::V_QACCS, &gauss);
   float prev_cost = INFINITY;
   const float scale = 1.f / (dm->meaninertia * (float)(nv > 1 ? nv : 1));
   int niter = 0, ls_total = 0;

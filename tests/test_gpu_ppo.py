@@ -79,16 +79,22 @@ def test_rsr_term_changes_the_policy_gradient():
 def test_policy_params_training_end_to_end():
     """RSR/rsr_pipeline.py:274-436 with the reference's dataset layout (23-d states, 5-d actions)"""
     from rsr_mjx_b200 import rsr_pipeline as RP
-    g = np.random.default_rng(2)
-    S = g.normal(0, 0.3, (50, 23)).astype(np.float32)
-    Aa = g.uniform(-1, 1, (50, 5)).astype(np.float32)
+    # "real" transitions: 50 (s, a, s') triples rolled out of the env itself, so the policy's own transitions land
+    # inside the support of the reference KDE (rows far from every grid point drop out of the logsumexp exactly)
     env = AirbotPlayBase("sf", num_envs=64, episode_length=1200)
+    st = env.reset(prng.split(prng.PRNGKey(3), 64))
+    gen = torch.Generator("cuda").manual_seed(2)
+    Aa = (torch.rand(64, 5, device="cuda", generator=gen) * 2 - 1)
+    S = st.obs.clone()
+    env.step(st, Aa)
+    S2 = st.obs.clone()
+    S, Aa, S2 = (v[:50].cpu().numpy().astype(np.float32) for v in (S, Aa, S2))
     seen = []
     make_policy, (norm, net) = RP.policy_params_training(
-        env, past_states=S, past_actions=Aa, past_next_states_real=S + 0.01, past_next_states_sim=S + 0.03,
-        current_next_states_sim=S + 0.02, num_envs=64, batch_size=8, num_minibatches=8, unroll_length=4,
+        env, past_states=S, past_actions=Aa, past_next_states_real=S2 + 0.01, past_next_states_sim=S2 + 0.03,
+        current_next_states_sim=S2, num_envs=64, batch_size=8, num_minibatches=8, unroll_length=4,
         num_updates_per_batch=1, num_timesteps=10**9, num_evals=1, progress_fn=lambda n, m: seen.append(m),
-        max_training_steps=1, bandwidth=0.5, min_val=-1.0, max_val=1.0)
+        max_training_steps=1, bandwidth=0.5, min_val=-1.0, max_val=1.5)
     assert len(seen) == 1 and np.isfinite(seen[0]["training/total_loss"]) and seen[0]["training/sim2real_loss"] != 0
     a = make_policy()(env.reset(prng.split(prng.PRNGKey(0), 64)).obs)
     assert a.shape == (64, 5)
