@@ -54,6 +54,27 @@ def read_traffic(kind, n_envs):
     return None
 
 
+def read_compute_view(n_envs):
+    """the compute-side view of step_kernel from the committed `ncu --set full` summary
+    (fp32 pipe, issue slots, IPC, resident warps) — the numbers that actually explain an issue/latency-bound kernel"""
+    p = os.path.join(ROOT, "profiles", "r1_step_kernel_ncu_full_summary.csv")
+    if not os.path.exists(p) or n_envs != 8192:
+        return None
+    want = {"sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "fp32_fma_pipe_pct",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
+            "sm__inst_executed.avg.per_cycle_active": "ipc_per_sm",
+            "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+            "smsp__inst_issued.sum": "warp_instructions_per_launch"}
+    out = {"source": "profiles/r1_step_kernel_ncu_full_summary.csv (ncu --set full, one launch, 8192 envs)"}
+    with open(p) as f:
+        for ln in f:
+            parts = ln.strip().split(",")
+            if len(parts) == 3 and parts[0] in want:
+                out[want[parts[0]]] = float(parts[2])
+    return out
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -241,6 +262,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": read_traffic(args.kind, N), "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES[args.kind],
+                         "compute_view": read_compute_view(N),
                          "note": "scan-like state-in/state-out step: far below the HBM roof by design (SURVEY.md §8d); "
                                  "issue/latency-bound, see profiles/"},
             "status_flagged_envs": status_bad,
