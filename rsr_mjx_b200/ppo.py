@@ -124,6 +124,49 @@ class RunningStatistics:
         return (x - self.mean) / self.std
 
 
+# ----------------------------------------------------------------------- checkpoints
+def save_params(path, params, *, normalize_observations: bool = True, extra: Optional[Dict[str, Any]] = None) -> None:
+    """Writes `(normalizer, networks)` as returned by `train` to one file.  Takes the place of the Orbax checkpoint of
+    test/rsr_policy_training.py:213-222 (`policy_params_fn`); the layout is a plain dict of tensors and ints so it can
+    be read without this package."""
+    norm, net = params
+    pol_sizes = [net.policy.layers[0].in_features] + [l.out_features for l in net.policy.layers]
+    val_sizes = [net.value.layers[0].in_features] + [l.out_features for l in net.value.layers]
+    torch.save({"format": "rsr_mjx_b200.ppo/1", "policy_sizes": pol_sizes, "value_sizes": val_sizes,
+                "normalize_observations": bool(normalize_observations),
+                "normalizer": {k: getattr(norm, k).detach().cpu() for k in ("count", "mean", "summed_variance", "std")},
+                "networks": {k: v.detach().cpu() for k, v in net.state_dict().items()}, "extra": dict(extra or {})}, path)
+
+
+def load_params(path, device="cuda"):
+    """Inverse of `save_params`: returns `((normalizer, networks), meta)` on `device`."""
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    if ck.get("format") != "rsr_mjx_b200.ppo/1":
+        raise ValueError(f"{path}: not a rsr_mjx_b200 PPO checkpoint (format={ck.get('format')!r})")
+    pol, val = ck["policy_sizes"], ck["value_sizes"]
+    net = PPONetworks(pol[0], pol[-1] // 2, tuple(pol[1:-1]), tuple(val[1:-1]))
+    net.load_state_dict(ck["networks"])
+    net = net.to(device)
+    norm = RunningStatistics(pol[0], device)
+    for k, v in ck["normalizer"].items():
+        getattr(norm, k).copy_(v.to(device))
+    return (norm, net), {"normalize_observations": ck["normalize_observations"], "extra": ck["extra"]}
+
+
+def make_inference_fn(params, normalize_observations: bool = True):
+    """`make_policy(deterministic)` over saved parameters (ppo_inference.py:49-69: restore, then act)."""
+    norm, net = params
+    normalize = norm.normalize if normalize_observations else (lambda x: x)
+
+    def make_policy(deterministic: bool = False):
+        @torch.no_grad()
+        def policy(obs, generator=None):
+            logits = net.policy(normalize(obs))
+            return NormalTanh.mode(logits) if deterministic else torch.tanh(NormalTanh.sample_raw(logits, generator))
+        return policy
+    return make_policy
+
+
 # ----------------------------------------------------------------------- GAE / loss
 def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambda_: float = 1.0, discount: float = 0.99):
     """RSR/losses.py:39-95; all inputs [T, B], bootstrap_value [B]. Returns (vs, advantages), detached."""

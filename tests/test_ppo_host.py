@@ -132,3 +132,27 @@ def test_policy_params_training_validation_matches_reference():
         RP.build_policy_rsr_data(z, np.zeros((3, 5)), np.zeros((3, 22)), z, z)
     with pytest.raises(ValueError, match="all RSR datasets must be rank 2"):
         RP.build_policy_rsr_data(np.zeros(3), np.zeros((3, 5)), z, z, z)
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """save_params / load_params / make_inference_fn (the Orbax slot of test/rsr_policy_training.py:213-222)"""
+    torch.manual_seed(3)
+    net = ppo.PPONetworks(23, 5, (32,) * 4, (64,) * 2)
+    norm = ppo.RunningStatistics(23, "cpu")
+    norm.update(torch.randn(100, 23) * 2 + 1)
+    path = tmp_path / "policy.pt"
+    ppo.save_params(path, (norm, net), extra={"step": 7})
+    (norm2, net2), meta = ppo.load_params(path, device="cpu")
+    assert meta["normalize_observations"] is True and meta["extra"] == {"step": 7}
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, net2.state_dict()[k])
+    for k in ("count", "mean", "summed_variance", "std"):
+        assert torch.equal(getattr(norm, k), getattr(norm2, k))
+    obs = torch.randn(9, 23)
+    a1 = ppo.make_inference_fn((norm, net))(deterministic=True)(obs)
+    a2 = ppo.make_inference_fn((norm2, net2))(deterministic=True)(obs)
+    assert a1.shape == (9, 5) and torch.equal(a1, a2) and a1.abs().max() <= 1
+    bad = tmp_path / "bad.pt"
+    torch.save({"format": "other"}, bad)
+    with pytest.raises(ValueError, match="not a rsr_mjx_b200 PPO checkpoint"):
+        ppo.load_params(bad, device="cpu")
