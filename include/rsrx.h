@@ -151,6 +151,20 @@ int rsrx_rsr_loss(const float* grid, int M, int D, const float* reference_data, 
 int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, float bandwidth, float* density_out,
              void* stream);
 
+/* Fused PPO loss head, forward + backward in one launch (RSR/losses.py:39-95 compute_gae, :98-205 compute_ppo_loss
+ * between the network outputs and the scalar task loss; brax NormalTanhDistribution with min_std 0.001).
+ * All arrays are device float32, batch-major: logits [B][T][2A] (loc | pre-softplus scale), baseline / behaviour_log_prob /
+ * reward / discount / truncation [B][T], bootstrap_value [B] (value of the last next_observation), raw_action / noise
+ * [B][T][A] (pre-tanh behaviour action; N(0,1) sample for the entropy estimate).  workspace: 2*B*T floats.
+ * out[4] = task_loss (= policy + value + entropy), policy_loss, v_loss, entropy_loss;
+ * grad_logits [B][T][2A] and grad_baseline [B][T] receive d task_loss / d (logits, baseline); vs and the advantages are
+ * stop-gradient as in the reference, so bootstrap_value has no gradient. */
+int rsrx_ppo_head(const float* logits, const float* baseline, const float* bootstrap_value, const float* raw_action,
+                  const float* behaviour_log_prob, const float* reward, const float* discount, const float* truncation,
+                  const float* noise, int B, int T, int A, float reward_scaling, float discounting, float gae_lambda,
+                  float clipping_epsilon, float entropy_cost, int normalize_advantage, float* workspace, float* out,
+                  float* grad_logits, float* grad_baseline, void* stream);
+
 const char* rsrx_last_error(void);
 const char* rsrx_version(void);
 

@@ -9,6 +9,7 @@
 
 #include "rsrx_env.cuh"
 #include "rsrx_loss.cuh"
+#include "rsrx_ppo.cuh"
 
 using namespace rsrx;
 
@@ -405,6 +406,23 @@ extern "C" int rsrx_kde(const float* grid, int M, int D, const float* data, int 
   return loss::launch(grid, M, D, nullptr, 0, data, Ndata, nullptr, bandwidth, 0.f, 0.f, density_out, nullptr, nullptr,
                       (cudaStream_t)stream)
              ? fail(std::string("rsrx_kde: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+
+extern "C" int rsrx_ppo_head(const float* logits, const float* baseline, const float* bootstrap_value,
+                             const float* raw_action, const float* behaviour_log_prob, const float* reward,
+                             const float* discount, const float* truncation, const float* noise, int B, int T, int A,
+                             float reward_scaling, float discounting, float gae_lambda, float clipping_epsilon,
+                             float entropy_cost, int normalize_advantage, float* workspace, float* out,
+                             float* grad_logits, float* grad_baseline, void* stream) {
+  if (!logits || !baseline || !bootstrap_value || !raw_action || !behaviour_log_prob || !reward || !discount ||
+      !truncation || !noise || !workspace || !out || !grad_logits || !grad_baseline)
+    return fail("rsrx_ppo_head: null argument");
+  if (B <= 0 || T <= 0 || A <= 0 || A > ppo::MAXA) return fail("rsrx_ppo_head: bad sizes (1 <= A <= 16)");
+  ppo::Hyper h{reward_scaling, discounting, gae_lambda, clipping_epsilon, entropy_cost, normalize_advantage};
+  return ppo::launch(logits, baseline, bootstrap_value, raw_action, behaviour_log_prob, reward, discount, truncation,
+                     noise, B, T, A, h, workspace, out, grad_logits, grad_baseline, (cudaStream_t)stream)
+             ? fail(std::string("rsrx_ppo_head: ") + cudaGetErrorString(cudaGetLastError()))
              : 0;
 }
 

@@ -217,6 +217,67 @@ def compute_ppo_loss(net: PPONetworks, normalize: Callable, data: Dict[str, torc
                    "entropy_loss": entropy_loss, "sim2real_loss": sim2real_loss, "rsr_distribution_distance": distance}
 
 
+class _PPOHeadFn(torch.autograd.Function):
+    """Everything between the network outputs and the task loss in one launch (`rsrx_ppo_head`, csrc/rsrx_ppo.cuh).
+    Inputs batch-major [B, T, ...]; returns (task_loss, stats[4] = task/policy/value/entropy losses, detached)."""
+
+    @staticmethod
+    def forward(ctx, logits, baseline, bootstrap, raw_action, log_prob, reward, discount, truncation, noise, hyper):
+        from . import _lib
+        if logits.device.type != "cuda":
+            raise RuntimeError("the fused PPO head runs only on CUDA tensors (no CPU fallback)")
+        B, T, A2 = logits.shape
+        A = A2 // 2
+        f = lambda x: x.detach().float().contiguous()
+        logits_c, baseline_c, args = f(logits), f(baseline), [f(v) for v in (bootstrap, raw_action, log_prob, reward,
+                                                                           discount, truncation, noise)]
+        if tuple(baseline_c.shape) != (B, T) or tuple(args[1].shape) != (B, T, A) or tuple(args[6].shape) != (B, T, A):
+            raise ValueError("rsrx_ppo_head: expected baseline [B,T], raw_action/noise [B,T,A], logits [B,T,2A]")
+        dev = logits.device
+        ws = torch.empty(2 * B * T, device=dev)
+        out = torch.empty(4, device=dev)
+        g_logits = torch.empty(B, T, A2, device=dev)
+        g_base = torch.empty(B, T, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rsrx_ppo_head(
+                logits_c.data_ptr(), baseline_c.data_ptr(), *[a.data_ptr() for a in args], B, T, A,
+                float(hyper["reward_scaling"]), float(hyper["discounting"]), float(hyper["gae_lambda"]),
+                float(hyper["clipping_epsilon"]), float(hyper["entropy_cost"]), int(bool(hyper["normalize_advantage"])),
+                ws.data_ptr(), out.data_ptr(), g_logits.data_ptr(), g_base.data_ptr(),
+                torch.cuda.current_stream(dev).cuda_stream), "rsrx_ppo_head")
+        ctx.save_for_backward(g_logits, g_base)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        g_logits, g_base = ctx.saved_tensors
+        return (g_logits * g_loss, g_base * g_loss) + (None,) * 8
+
+
+def compute_ppo_loss_fused(net: PPONetworks, normalize: Callable, data: Dict[str, torch.Tensor], noise: torch.Tensor,
+                           past_data: Any = None, entropy_cost: float = 1e-4, discounting: float = 0.9,
+                           reward_scaling: float = 1.0, gae_lambda: float = 0.95, clipping_epsilon: float = 0.3,
+                           normalize_advantage: bool = True, rsr_loss_scale: float = 1.0):
+    """`compute_ppo_loss` with the loss head in one CUDA launch.  `data` leaves [B, T, ...], `noise` [B, T, A].
+    The value network sees the T observations and the bootstrap observation of every sequence in one batch."""
+    obs = data["observation"]
+    B, T, O = obs.shape
+    obs_n = normalize(obs)
+    policy_logits = net.policy(obs_n)
+    values = net.value(torch.cat([obs_n, normalize(data["next_observation"][:, -1:])], dim=1)).squeeze(-1)  # [B, T + 1]
+    baseline, bootstrap = values[:, :T], values[:, T].detach()
+    hyper = dict(reward_scaling=reward_scaling, discounting=discounting, gae_lambda=gae_lambda,
+                 clipping_epsilon=clipping_epsilon, entropy_cost=entropy_cost, normalize_advantage=normalize_advantage)
+    task_loss, stats = _PPOHeadFn.apply(policy_logits, baseline, bootstrap, data["raw_action"], data["log_prob"],
+                                        data["reward"], data["discount"], data["truncation"], noise, hyper)
+    sim2real_loss, distance = rsr.compute_rsr_loss(obs, NormalTanh.mode(policy_logits), data["next_observation"],
+                                                   past_data, loss_scale=rsr_loss_scale)
+    total = task_loss + sim2real_loss
+    return total, {"total_loss": total, "task_loss": task_loss, "policy_loss": stats[1], "v_loss": stats[2],
+                   "entropy_loss": stats[3], "sim2real_loss": sim2real_loss, "rsr_distribution_distance": distance}
+
+
 # ----------------------------------------------------------------------- training
 def _flat_allreduce_mean(params):
     """gradient pmean: one all-reduce of a flat buffer"""
@@ -241,7 +302,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           gae_lambda: float = 0.95, rsr_loss_scale: float = 1.0, normalize_advantage: bool = True,
           policy_hidden=(32,) * 4, value_hidden=(256,) * 5,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None,
-          use_cuda_graph: bool = True, max_training_steps: Optional[int] = None, **unused):
+          use_cuda_graph: bool = True, fused_head: bool = True, max_training_steps: Optional[int] = None, **unused):
     """PPO training (RSR/train.py:76).  `environment` is an `AirbotPlayBase` with `num_envs` envs on this rank
     (under torch.distributed every rank passes its shard; `num_envs` is the per-rank count here).
     Returns (make_policy, (normalizer, networks), metrics)."""
@@ -262,7 +323,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     torch.manual_seed(seed)  # networks identical on every rank (key_policy / key_value are global in the reference)
     net = PPONetworks(env.observation_size, env.action_size, policy_hidden, value_hidden).to(dev)
     params = list(net.parameters())
-    opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8, capturable=bool(use_cuda_graph))
+    opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8, capturable=bool(use_cuda_graph), fused=True)
     norm = RunningStatistics(env.observation_size, dev)
     normalize = norm.normalize if normalize_observations else (lambda x: x)
     gen = torch.Generator(device=dev).manual_seed(seed * 7919 + rank + 1)
@@ -296,7 +357,9 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
 
     mb = B // num_minibatches
     static = {k: torch.empty(mb, T, *v.shape[3:], device=dev) for k, v in buf.items()}
-    static_noise = torch.empty(T, mb, act_size, device=dev)
+    # entropy-estimate noise: [B, T, A] for the fused head, time-major for the eager reference path
+    static_noise = torch.empty(*((mb, T) if fused_head else (T, mb)), act_size, device=dev)
+    loss_fn = compute_ppo_loss_fused if fused_head else compute_ppo_loss
     loss_kw = dict(past_data=past_data, entropy_cost=entropy_cost, discounting=discounting, reward_scaling=reward_scaling,
                    gae_lambda=gae_lambda, clipping_epsilon=clipping_epsilon, normalize_advantage=normalize_advantage,
                    rsr_loss_scale=rsr_loss_scale)
@@ -304,7 +367,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
 
     def fwd_bwd():
         opt.zero_grad(set_to_none=False)
-        loss, metrics = compute_ppo_loss(net, normalize, static, static_noise, **loss_kw)
+        loss, metrics = loss_fn(net, normalize, static, static_noise, **loss_kw)
         loss.backward()
         return metrics
 
@@ -359,19 +422,25 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     env_steps = 0
     for it in range(num_training_steps):
         t0 = time.time()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
         data = collect()
+        ev[1].record()
         if normalize_observations:
             norm.update(data["observation"])
         for _ in range(num_updates_per_batch):
             perm = torch.randperm(B, device=dev, generator=gen)
             for m_ in range(num_minibatches):
                 minibatch_step(data, perm[m_ * mb:(m_ + 1) * mb])
+        ev[2].record()
         torch.cuda.synchronize(dev)
         dt = time.time() - t0
         env_steps += env_step_per_training_step
         metrics_out = {f"training/{k}": float(v.detach()) for k, v in last_metrics.items()}
         metrics_out["training/sps"] = env_step_per_training_step / dt
         metrics_out["training/walltime"] = time.time() - t_start
+        metrics_out["training/collect_s"] = ev[0].elapsed_time(ev[1]) * 1e-3  # device time of the unrolls
+        metrics_out["training/update_s"] = ev[1].elapsed_time(ev[2]) * 1e-3   # ... of the SGD epochs
         metrics_out["training/reward_mean"] = float(data["reward"].mean())
         if num_evals > 0 and (it + 1) % max(num_training_steps // max(num_evals, 1), 1) == 0:
             progress_fn(env_steps, metrics_out)
