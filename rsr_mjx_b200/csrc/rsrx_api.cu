@@ -17,7 +17,22 @@ struct rsrx_model {
   DModel host;
   DModel* dev;
   int smem_bytes;
+  int num_sms;
 };
+
+// Launch shape for N envs: one CTA per SM per round, the rounds as evenly filled as possible.  8192 envs on 148 SMs:
+// 4 rounds of 14 envs per CTA; 1024 envs: one round of 147 CTAs x 7 envs instead of 74 CTAs x 14 on half the SMs.
+struct LaunchCfg { int grid, block; size_t smem; };
+static LaunchCfg launch_cfg(const rsrx_model* m, int N) {
+  const int per_round = m->num_sms * WPB;
+  const int rounds = (N + per_round - 1) / per_round;
+  int w = (N + m->num_sms * rounds - 1) / (m->num_sms * rounds);
+  static const int forced = getenv("RSRX_FORCE_WPB") ? atoi(getenv("RSRX_FORCE_WPB")) : 0;  // experiments only
+  if (forced > 0) w = forced;
+  w = w < 1 ? 1 : (w > WPB ? WPB : w);
+  const size_t pad = (size_t)(m->smem_bytes - WPB * ar::TOTAL * (int)sizeof(float));
+  return {(N + w - 1) / w, 32 * w, (size_t)w * ar::TOTAL * sizeof(float) + pad};
+}
 
 static thread_local std::string g_err;
 static int fail(const std::string& s) { g_err = s; return 1; }
@@ -315,6 +330,11 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
   rsrx_model* m = new rsrx_model();
   if (build_dmodel(*reinterpret_cast<const rsrx_model_blob*>(blob_host), *cfg_host, m->host)) { delete m; return 1; }
   m->smem_bytes = WPB * ar::TOTAL * (int)sizeof(float);
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || m->num_sms <= 0)
+      m->num_sms = 148;
+  }
   if (const char* pad = getenv("RSRX_SMEM_PAD")) m->smem_bytes += atoi(pad);  // occupancy experiments only
   cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
@@ -365,7 +385,8 @@ extern "C" int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, con
   if (!m || !qpos || !qvel || !ctrl) return fail("rsrx_env_reset: null argument");
   if (N <= 0) return fail("rsrx_env_reset: N must be positive");
   if (check_state(st)) return 1;
-  reset_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(per_env), to_sp(st));
+  const LaunchCfg lc = launch_cfg(m, N);
+  reset_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -375,7 +396,8 @@ extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const fl
   if (!m || !action) return fail("rsrx_env_step: null argument");
   if (N <= 0) return fail("rsrx_env_step: N must be positive");
   if (check_state(st)) return 1;
-  step_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(per_env), to_sp(st));
+  const LaunchCfg lc = launch_cfg(m, N);
+  step_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -384,7 +406,8 @@ extern "C" int rsrx_physics_step(const rsrx_model* m, int N, float* data, int ns
                                  int32_t* status, void* stream) {
   if (!m || !data) return fail("rsrx_physics_step: null argument");
   if (N <= 0 || nsteps < 0) return fail("rsrx_physics_step: bad N / nsteps");
-  physics_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(per_env), status, nullptr);
+  const LaunchCfg lc = launch_cfg(m, N);
+  physics_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(per_env), status, nullptr);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -393,7 +416,8 @@ extern "C" int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, 
                                        void* stream) {
   if (!m || !data || !dump) return fail("rsrx_physics_step_debug: null argument");
   if (N <= 0) return fail("rsrx_physics_step_debug: bad N");
-  physics_kernel<<<(N + WPB - 1) / WPB, 32 * WPB, m->smem_bytes, (cudaStream_t)stream>>>(m->dev, N, data, 1, to_pe(per_env), nullptr, dump);
+  const LaunchCfg lc = launch_cfg(m, N);
+  physics_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, data, 1, to_pe(per_env), nullptr, dump);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
                                                   const float* __restrict__ qvel, const float* __restrict__ ctrl,
                                                   PerEnv pe, StatePtrs st) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * WPB + wib;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   float* sm = smem + wib * ar::TOTAL;
   if (e >= N) return;
   const rsrx_layout& L = dm->lay;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
 __global__ void __launch_bounds__(32 * WPB) step_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ action,
                                                  PerEnv pe, StatePtrs st) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * WPB + wib;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   float* sm = smem + wib * ar::TOTAL;
   if (e >= N) {
     for (int f = 0; f < dm->n_frames * kPhaseBarriers; ++f) phase_barrier<true>(__builtin_ctz(RSRX_SYNC_MASK));  // shadow the phase barriers
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
                                                     int nsteps, PerEnv pe, int* __restrict__ status_out,
                                                     float* __restrict__ dump) {
   extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * WPB + wib;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   float* sm = smem + wib * ar::TOTAL;
   if (e >= N) return;
   const rsrx_layout& L = dm->lay;
