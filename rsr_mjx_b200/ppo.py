@@ -302,11 +302,15 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           gae_lambda: float = 0.95, rsr_loss_scale: float = 1.0, normalize_advantage: bool = True,
           policy_hidden=(32,) * 4, value_hidden=(256,) * 5,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None,
-          use_cuda_graph: bool = True, fused_head: bool = True, max_training_steps: Optional[int] = None, **unused):
+          use_cuda_graph: bool = True, fused_head: bool = True, allow_tf32: bool = True,
+          max_training_steps: Optional[int] = None, **unused):
     """PPO training (RSR/train.py:76).  `environment` is an `AirbotPlayBase` with `num_envs` envs on this rank
     (under torch.distributed every rank passes its shard; `num_envs` is the per-rank count here).
     Returns (make_policy, (normalizer, networks), metrics)."""
     env = environment
+    # the two MLPs run their matmuls on the tensor cores in TF32, the precision jax gives float32 `dot` on NVIDIA GPUs
+    # by default (the reference never raises `jax_default_matmul_precision`); everything else stays fp32
+    torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
     if env.num_envs != num_envs:
         raise ValueError(f"environment has {env.num_envs} envs, num_envs={num_envs}")
     if env.episode_length != episode_length:

@@ -189,5 +189,5 @@ def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, p
         action_repeat=action_repeat, unroll_length=unroll_length, num_minibatches=num_minibatches,
         num_updates_per_batch=num_updates_per_batch, discounting=discounting, learning_rate=learning_rate,
         entropy_cost=entropy_cost, num_envs=num_envs, batch_size=batch_size, progress_fn=progress_fn or (lambda *a: None),
-        rsr_loss_scale=rsr_loss_scale, seed=seed, **{k: v for k, v in sac_and_extra_options.items() if k in ("use_cuda_graph", "fused_head", "max_training_steps")})
+        rsr_loss_scale=rsr_loss_scale, seed=seed, **{k: v for k, v in sac_and_extra_options.items() if k in ("use_cuda_graph", "fused_head", "allow_tf32", "max_training_steps")})
     return make_inference_fn, params
