@@ -151,6 +151,11 @@ int rsrx_rsr_loss(const float* grid, int M, int D, const float* reference_data, 
 int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, float bandwidth, float* density_out,
              void* stream);
 
+/* Parity/debug: the narrow phase of mjx collision_convex (box_box; plane != 0: plane_convex on a box) on n explicit geom
+ * pairs.  pairs [n][30] = pos1(3) mat1(9, row-major) size1(3) pos2(3) mat2(9) size2(3); out [n][19] = dist(4)
+ * pos(4x3) normal(3), a slot with dist >= 0 holds no contact.  Device pointers. */
+int rsrx_debug_narrowphase(const float* pairs, int n, int plane, float* out, void* stream);
+
 /* Fused PPO loss head, forward + backward in one launch (RSR/losses.py:39-95 compute_gae, :98-205 compute_ppo_loss
  * between the network outputs and the scalar task loss; brax NormalTanhDistribution with min_std 0.001).
  * All arrays are device float32, batch-major: logits [B][T][2A] (loc | pre-softplus scale), baseline / behaviour_log_prob /

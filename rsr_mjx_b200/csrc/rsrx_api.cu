@@ -433,6 +433,13 @@ extern "C" int rsrx_kde(const float* grid, int M, int D, const float* data, int 
              : 0;
 }
 
+extern "C" int rsrx_debug_narrowphase(const float* pairs, int n, int plane, float* out, void* stream) {
+  if (!pairs || !out || n <= 0) return fail("rsrx_debug_narrowphase: bad arguments");
+  narrowphase_kernel<<<(n + 1) / 2, 32, 0, (cudaStream_t)stream>>>(pairs, n, plane, out);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int rsrx_ppo_head(const float* logits, const float* baseline, const float* bootstrap_value,
                              const float* raw_action, const float* behaviour_log_prob, const float* reward,
                              const float* discount, const float* truncation, const float* noise, int B, int T, int A,

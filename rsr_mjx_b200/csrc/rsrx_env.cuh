@@ -375,4 +375,32 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
   if (lane == 0 && status_out) status_out[e] |= status;
 }
 
+// Debug/parity entry: the cooperative narrow phase on a batch of explicit geom pairs (one half warp per pair, as in
+// collision()).  in: [n][30] = p1(3) m1(9) s1(3) p2(3) m2(9) s2(3); plane != 0: geom 1 is a plane (s1 unused).
+// out: [n][19] = dist(4) pos(4x3) nrm(3).
+__global__ void __launch_bounds__(32) narrowphase_kernel(const float* __restrict__ in, int n, int plane, float* __restrict__ out) {
+  __shared__ float scratch[2 * 24];
+  __shared__ float pose[2][30];
+  const int lane = threadIdx.x;
+  Half hw;
+  hw.shift = lane & 16; hw.l = lane & 15; hw.mask = 0xffffu << hw.shift;
+  const int h = lane >> 4, pair = blockIdx.x * 2 + h;
+  const bool valid = pair < n;
+  for (int i = hw.l; i < 30; i += 16) pose[h][i] = in[(size_t)(valid ? pair : 0) * 30 + i];
+  __syncwarp();
+  if (valid) {
+    const float* q = pose[h];
+    const float s1[3] = {q[12], q[13], q[14]}, s2[3] = {q[27], q[28], q[29]};
+    Manifold mf;
+    if (plane) plane_box(q, q + 3, q + 15, q + 18, s2, hw, &mf);
+    else box_box(q, q + 3, s1, q + 15, q + 18, s2, scratch + h * 24, hw, &mf);
+    float* o = out + (size_t)pair * 19;
+    if (hw.l < 4) {
+      o[hw.l] = mf.dist;
+      for (int i = 0; i < 3; i++) o[4 + hw.l * 3 + i] = mf.pos[i];
+    }
+    if (hw.l == 0) for (int i = 0; i < 3; i++) o[16 + i] = mf.nrm[i];
+  }
+}
+
 }  // namespace rsrx
