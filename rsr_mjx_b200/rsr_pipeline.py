@@ -167,22 +167,36 @@ def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, p
                            **sac_and_extra_options):
     """Trains an RSR policy (reference signature and defaults, rsr_pipeline.py:274-319).
 
-    `env` is a batched `AirbotPlayBase` whose `num_envs` / `episode_length` match the arguments.  Only
-    ``algorithm='ppo'`` is available (SAC is SURVEY.md §8f row N3); Orbax checkpoints are out of scope, so
-    `restore_checkpoint_path` must be None.  Returns ``(make_inference_fn, (normalizer, networks))``."""
+    `env` is a batched `AirbotPlayBase` whose `num_envs` / `episode_length` match the arguments.  Orbax checkpoints
+    are out of scope, so `restore_checkpoint_path` must be None.  ``algorithm='sac'`` takes tau / min_replay_size / max_replay_size /
+    grad_updates_per_step through the keyword options, like the reference (rsr_pipeline.py:396-426).
+    Returns ``(make_inference_fn, (normalizer, networks))``."""
     from . import ppo
     if rsr_loss_scale < 0:
         raise ValueError(f'rsr_loss_scale must be non-negative, got {rsr_loss_scale}')
     required = (past_states, past_actions, past_next_states_real, past_next_states_sim, current_next_states_sim)
     if any(v is None for v in required):
         raise ValueError('all five RSR policy datasets are required')
-    if algorithm.strip().lower() != "ppo":
-        raise NotImplementedError("only algorithm='ppo' is available (SAC: SURVEY.md §8f N3)")
+    algorithm = algorithm.strip().lower()
+    if algorithm not in ("ppo", "sac"):
+        raise ValueError(f'unsupported algorithm {algorithm!r}; expected "ppo" or "sac"')
     if restore_checkpoint_path:
         raise NotImplementedError("Orbax checkpoint restore is out of scope (SURVEY.md §5)")
     past_data = build_policy_rsr_data(past_states, past_actions, past_next_states_real, past_next_states_sim,
                                       current_next_states_sim, num_samples=num_samples, min_val=min_val, max_val=max_val,
                                       bandwidth=bandwidth, seed=seed, device=env.device)
+    if algorithm == "sac":
+        from . import sac
+        opts = {k: v for k, v in sac_and_extra_options.items()
+                if k in ("tau", "min_replay_size", "max_replay_size", "grad_updates_per_step", "hidden_layer_sizes",
+                         "use_cuda_graph", "allow_tf32", "max_training_steps")}
+        make_inference_fn, params, _ = sac.train(
+            environment=env, past_data=past_data, num_timesteps=num_timesteps, num_evals=num_evals,
+            num_eval_envs=num_eval_envs, reward_scaling=reward_scaling, episode_length=episode_length,
+            normalize_observations=normalize_observations, action_repeat=action_repeat, discounting=discounting,
+            learning_rate=learning_rate, num_envs=num_envs, batch_size=batch_size, deterministic_eval=deterministic_eval,
+            progress_fn=progress_fn or (lambda *a: None), rsr_loss_scale=rsr_loss_scale, seed=seed, **opts)
+        return make_inference_fn, params
     make_inference_fn, params, _ = ppo.train(
         environment=env, past_data=past_data, num_timesteps=num_timesteps, num_evals=num_evals, num_eval_envs=num_eval_envs,
         reward_scaling=reward_scaling, episode_length=episode_length, normalize_observations=normalize_observations,
