@@ -213,25 +213,20 @@ def main():
     barrier()
     step_ms = np.array([a.elapsed_time(b) for a, b in evs])
     total_ms = float(step_ms.sum())
-    # ---- end-to-end timing: host action buffer in, host obs/reward/done out, every step
+    # ---- end-to-end timing: host action buffer in, host obs/reward/done out, every step, through the host-buffer entry
+    # of the C-ABI (rsrx_env_step_host: H2D action, launch, D2H obs/reward/done queued by one call)
     h_act = torch.empty(K, N, env.action_size, dtype=torch.float32).pin_memory()
     h_act.copy_(actions[W:].cpu())
-    h_out = torch.empty(N, env.observation_size + 2, dtype=torch.float32).pin_memory()
-    d_act = torch.empty(N, env.action_size, device=dev)
-    d_out = torch.empty(N, env.observation_size + 2, device=dev)
+    h_obs = torch.empty(N, env.layout.obs_stride, dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(N, dtype=torch.float32).pin_memory()
     for t in range(3):
-        d_act.copy_(h_act[t], non_blocking=True)
-        env.step(state, d_act)
+        env.step_host(state, h_act[t], h_obs, h_rew, h_done)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(K):
-        d_act.copy_(h_act[t], non_blocking=True)
-        env.step(state, d_act)
-        d_out[:, :env.observation_size] = state.obs
-        d_out[:, env.observation_size] = state.reward
-        d_out[:, env.observation_size + 1] = state.done
-        h_out.copy_(d_out, non_blocking=True)
+        env.step_host(state, h_act[t], h_obs, h_rew, h_done)
         torch.cuda.current_stream().synchronize()  # the caller consumes obs before choosing the next action
     e1.record()
     barrier()
@@ -257,7 +252,7 @@ def main():
                        "l2": "256 MiB flush between timed steps" if flush is not None else "no flush"},
             "clocks": sampler.summary(),
             "e2e": {"value": N * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
-                    "h2d_bytes_per_step": N * env.action_size * 4, "d2h_bytes_per_step": N * (env.observation_size + 2) * 4},
+                    "h2d_bytes_per_step": N * env.action_size * 4, "d2h_bytes_per_step": N * (env.layout.obs_stride + 2) * 4},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": read_traffic(args.kind, N), "peak_source": peak_src,

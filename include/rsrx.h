@@ -122,6 +122,13 @@ int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, const float* q
 int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const float* action, const rsrx_per_env* per_env,
                   void* stream);
 
+/* Same step for a caller whose policy lives on the host: host_action[N][nu] (pinned memory recommended) is copied to
+ * the device buffer `action_staging` [N][nu], the step runs, and obs [N][obs_stride] / reward [N] / done [N] are copied
+ * back into the host buffers that are not NULL — all asynchronously on `stream`; synchronise the stream before reading
+ * them.  One call per step instead of copy + launch + gather + copy. */
+int rsrx_env_step_host(const rsrx_model* m, int N, rsrx_state st, const float* host_action, float* action_staging,
+                       float* host_obs, float* host_reward, float* host_done, const rsrx_per_env* per_env, void* stream);
+
 /* ---- physics only (pipeline_step / mjx.step, mjx_env.py:55-65) ---------------
  * advances data rows by nsteps x mjx.step with the ctrl stored in the rows. */
 int rsrx_physics_step(const rsrx_model* m, int N, float* data, int nsteps, const rsrx_per_env* per_env,

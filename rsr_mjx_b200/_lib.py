@@ -74,6 +74,7 @@ def lib():
     L.rsrx_model_layout.argtypes = [vp, C.POINTER(Layout)]
     L.rsrx_env_reset.argtypes = [vp, i32, vp, vp, vp, C.POINTER(PerEnvC), StateC, vp]
     L.rsrx_env_step.argtypes = [vp, i32, StateC, vp, C.POINTER(PerEnvC), vp]
+    L.rsrx_env_step_host.argtypes = [vp, i32, StateC, vp, vp, vp, vp, vp, C.POINTER(PerEnvC), vp]
     L.rsrx_physics_step.argtypes = [vp, i32, vp, i32, C.POINTER(PerEnvC), vp, vp]
     L.rsrx_physics_step_debug.argtypes = [vp, i32, vp, C.POINTER(PerEnvC), vp, vp]
     L.rsrx_debug_stride.restype = i32
@@ -94,5 +95,5 @@ def check(rc: int, what: str = "rsrx"):
 
 
 EXPORTS = ("rsrx_model_create", "rsrx_model_destroy", "rsrx_model_layout", "rsrx_model_blob_size", "rsrx_env_cfg_size",
-           "rsrx_env_reset", "rsrx_env_step", "rsrx_physics_step", "rsrx_debug_stride", "rsrx_max_contacts", "rsrx_physics_step_debug",
+           "rsrx_env_reset", "rsrx_env_step", "rsrx_env_step_host", "rsrx_physics_step", "rsrx_debug_stride", "rsrx_max_contacts", "rsrx_physics_step_debug",
            "rsrx_rsr_loss", "rsrx_kde", "rsrx_ppo_head", "rsrx_debug_narrowphase", "rsrx_last_error", "rsrx_version")

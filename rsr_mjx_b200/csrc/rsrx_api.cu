@@ -402,6 +402,24 @@ extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const fl
   return 0;
 }
 
+extern "C" int rsrx_env_step_host(const rsrx_model* m, int N, rsrx_state st, const float* host_action,
+                                  float* action_staging, float* host_obs, float* host_reward, float* host_done,
+                                  const rsrx_per_env* per_env, void* stream) {
+  if (!m || !host_action || !action_staging) return fail("rsrx_env_step_host: null argument");
+  if (N <= 0) return fail("rsrx_env_step_host: N must be positive");
+  if (check_state(st)) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const rsrx_layout& L = m->host.lay;
+  CUDA_OK(cudaMemcpyAsync(action_staging, host_action, sizeof(float) * (size_t)N * m->host.nu, cudaMemcpyHostToDevice, s));
+  const LaunchCfg lc = launch_cfg(m, N);
+  step_kernel<<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(per_env), to_sp(st));
+  CUDA_OK(cudaGetLastError());
+  if (host_obs) CUDA_OK(cudaMemcpyAsync(host_obs, st.obs, sizeof(float) * (size_t)N * L.obs_stride, cudaMemcpyDeviceToHost, s));
+  if (host_reward) CUDA_OK(cudaMemcpyAsync(host_reward, st.reward, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
+  if (host_done) CUDA_OK(cudaMemcpyAsync(host_done, st.done, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
 extern "C" int rsrx_physics_step(const rsrx_model* m, int N, float* data, int nsteps, const rsrx_per_env* per_env,
                                  int32_t* status, void* stream) {
   if (!m || !data) return fail("rsrx_physics_step: null argument");

@@ -314,6 +314,30 @@ class AirbotPlayBase:
                                                 C.byref(self._per_env), self._stream()), "rsrx_env_step")
         return state
 
+    def step_host(self, state: State, host_action: torch.Tensor, host_obs: Optional[torch.Tensor] = None,
+                  host_reward: Optional[torch.Tensor] = None, host_done: Optional[torch.Tensor] = None) -> State:
+        """`step` for a host-side caller: `host_action` [N, nu] (CPU float32, ideally pinned) goes in, the optional CPU
+        buffers `host_obs` [N, obs_stride], `host_reward` [N], `host_done` [N] receive the results; copies and launch are
+        queued by one C call (`rsrx_env_step_host`).  Synchronise the stream before reading the host buffers."""
+        N = self.num_envs
+        def chk(t, shape, name):
+            if t is None:
+                return None
+            if t.device.type != "cpu" or t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous CPU float32 tensor of shape {shape}")
+            return t.data_ptr()
+        pa = chk(host_action, (N, self.model.nu), "host_action")
+        if pa is None:
+            raise ValueError("host_action is required")
+        if getattr(self, "_act_staging", None) is None:
+            self._act_staging = torch.empty(N, self.model.nu, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rsrx_env_step_host(
+                self._handle, N, self._cstate(state._buf), pa, self._act_staging.data_ptr(),
+                chk(host_obs, (N, self.layout.obs_stride), "host_obs"), chk(host_reward, (N,), "host_reward"),
+                chk(host_done, (N,), "host_done"), C.byref(self._per_env), self._stream()), "rsrx_env_step_host")
+        return state
+
     def step_raw(self, buf: Dict[str, torch.Tensor], action_ptr: int):
         """Launch-only path for benchmarks / CUDA-graph capture (no tensor checks)."""
         _lib.check(_lib.lib().rsrx_env_step(self._handle, self.num_envs, self._cstate(buf), action_ptr,

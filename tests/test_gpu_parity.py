@@ -299,3 +299,25 @@ def test_friction_sweep_matches_oracle_per_param():
     tuned, log = RP.env_params_tuning(one, 3, {"geom_friction": 0.4}, {"geom_friction": 0.08}, {"geom_friction": 4.0},
                                       obs, actions, true, num_params=16)
     assert 0.08 <= tuned["geom_friction"] <= 4.0 and log["loss"][-1] <= log["loss"][0] + 1e-9 and len(log["params"]) == 3
+
+
+def test_step_host_equals_step():
+    """rsrx_env_step_host (host action in, host obs/reward/done out) is the same step as rsrx_env_step"""
+    env, keys, ic = _mk("sf", 256, seed=5)
+    g = torch.Generator().manual_seed(0)
+    s1, s2 = env.reset_from(*ic), None
+    env2, _, _ = _mk("sf", 256, seed=5)
+    s2 = env2.reset_from(*ic)
+    h_obs = torch.empty(256, env.layout.obs_stride).pin_memory()
+    h_rew, h_done = torch.empty(256).pin_memory(), torch.empty(256).pin_memory()
+    for t in range(5):
+        a = (torch.rand(256, 5, generator=g) * 2 - 1).pin_memory()
+        env.step(s1, a.cuda())
+        env2.step_host(s2, a, h_obs, h_rew, h_done)
+        torch.cuda.synchronize()
+        assert torch.equal(s1._buf["data"], s2._buf["data"])
+        assert torch.equal(h_obs, s1._buf["obs"].cpu()) and torch.equal(h_rew, s1.reward.cpu()) and torch.equal(h_done, s1.done.cpu())
+    with pytest.raises(ValueError):
+        env2.step_host(s2, torch.zeros(255, 5))
+    with pytest.raises(ValueError):
+        env2.step_host(s2, torch.zeros(256, 5), host_obs=torch.zeros(256, 3))
