@@ -630,11 +630,8 @@ __device__ __noinline__ void kbi(const DModel* __restrict__ dm, const float* sol
 //     (dist >= 0) are dropped.  Returns ncon.
 __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, int lane, int* status) {
   for (int g = lane; g < dm->ngeom; g += 32) {
-    float pos[3], mat[9];
-    geom_pose(dm, sm, g, pos, mat);
     float* gp = sm + ar::GPOSE + g * 12;
-    for (int i = 0; i < 3; i++) gp[i] = pos[i];
-    for (int i = 0; i < 9; i++) gp[3 + i] = mat[i];
+    geom_pose(dm, sm, g, gp, gp + 3);
   }
   RSRX_SYNC();
   int* plist = reinterpret_cast<int*>(sm + ar::PLIST);
