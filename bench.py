@@ -67,11 +67,25 @@ def read_compute_view(n_envs):
             "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
             "smsp__inst_issued.sum": "warp_instructions_per_launch"}
     out = {"source": "profiles/r1_step_kernel_ncu_full_summary.csv (ncu --set full, one launch, 8192 envs)"}
+    raw = {}
     with open(p) as f:
         for ln in f:
             parts = ln.strip().split(",")
-            if len(parts) == 3 and parts[0] in want:
-                out[want[parts[0]]] = float(parts[2])
+            if len(parts) == 3:
+                raw[parts[0]] = parts[2]
+                if parts[0] in want:
+                    out[want[parts[0]]] = float(parts[2])
+    # executed fp32 work: thread-level FADD + FMUL + 2 x FFMA per elapsed cycle, summed over the chip
+    try:
+        per_cycle = (float(raw["smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed"])
+                     + float(raw["smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed"])
+                     + 2.0 * float(raw["smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed"]))
+        flop = per_cycle * float(raw["sm__cycles_elapsed.max"])
+        out["fp32_flop_per_env_step"] = flop / n_envs
+        out["fp32_tflops_achieved"] = flop / (float(raw["gpu__time_duration.sum"]) * 1e-3) / 1e12
+        out["fp32_tflops_peak"] = 148 * 128 * 2 * float(raw["sm__cycles_elapsed.avg.per_second"]) * 1e9 / 1e12
+    except (KeyError, ValueError):
+        pass
     return out
 
 
