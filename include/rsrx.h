@@ -163,6 +163,14 @@ int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, floa
  * pos(4x3) normal(3), a slot with dist >= 0 holds no contact.  Device pointers. */
 int rsrx_debug_narrowphase(const float* pairs, int n, int plane, float* out, void* stream);
 
+/* MLP backward helper for the trainers' networks: grad_z = grad_y * act'(z) (activation 0 none, 1 silu, 2 relu;
+ * grad_z may be NULL when activation is 0) and grad_bias[c] = sum over rows of grad_z[r][c], one deterministic launch.
+ * Row-major [rows][cols] device arrays; workspace: rsrx_act_bias_backward_workspace(rows, cols) floats whose FIRST
+ * word is zero before the first call (the kernel leaves it zero). */
+size_t rsrx_act_bias_backward_workspace(int rows, int cols);
+int rsrx_act_bias_backward(const float* grad_y, const float* z, int rows, int cols, int activation, float* grad_z,
+                           float* grad_bias, float* workspace, void* stream);
+
 /* Fused PPO loss head, forward + backward in one launch (RSR/losses.py:39-95 compute_gae, :98-205 compute_ppo_loss
  * between the network outputs and the scalar task loss; brax NormalTanhDistribution with min_std 0.001).
  * All arrays are device float32, batch-major: logits [B][T][2A] (loc | pre-softplus scale), baseline / behaviour_log_prob /

@@ -458,6 +458,17 @@ extern "C" int rsrx_debug_narrowphase(const float* pairs, int n, int plane, floa
   return 0;
 }
 
+extern "C" size_t rsrx_act_bias_backward_workspace(int rows, int cols) { return mlp::workspace_floats(rows, cols); }
+
+extern "C" int rsrx_act_bias_backward(const float* grad_y, const float* z, int rows, int cols, int activation, float* grad_z,
+                                      float* grad_bias, float* workspace, void* stream) {
+  if (!grad_y || !grad_bias || !workspace || (activation != 0 && !z)) return fail("rsrx_act_bias_backward: null argument");
+  if (rows <= 0 || cols <= 0 || activation < 0 || activation > 2) return fail("rsrx_act_bias_backward: bad sizes / activation");
+  return mlp::launch(grad_y, z, rows, cols, activation, grad_z, grad_bias, workspace, (cudaStream_t)stream)
+             ? fail(std::string("rsrx_act_bias_backward: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+
 extern "C" int rsrx_ppo_head(const float* logits, const float* baseline, const float* bootstrap_value,
                              const float* raw_action, const float* behaviour_log_prob, const float* reward,
                              const float* discount, const float* truncation, const float* noise, int B, int T, int A,

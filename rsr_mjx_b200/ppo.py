@@ -30,7 +30,62 @@ from . import rsr_loss as rsr
 
 
 # ------------------------------------------------------------------------ networks
+_ACT = {"none": 0, "silu": 1, "relu": 2}
+_FUSED_MIN_ROWS = 512  # below this torch's own reduction is as fast (SAC batches of 128-256 rows)
+
+
+class _LinearActFn(torch.autograd.Function):
+    """y = act(x W^T + b) on CUDA with the backward's activation derivative and bias gradient in one launch
+    (`rsrx_act_bias_backward`) instead of an elementwise kernel plus a dim-0 reduction per layer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act: int, workspace):
+        z = torch.addmm(bias, x, weight.t())
+        y = F.silu(z) if act == 1 else (F.relu(z) if act == 2 else z)
+        ctx.save_for_backward(x, weight, z if act else x.new_empty(0), workspace)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import _lib
+        x, weight, z, workspace = ctx.saved_tensors
+        gy = gy.contiguous()
+        rows, cols = gy.shape
+        gz = torch.empty_like(gy) if ctx.act else gy
+        db = torch.empty(cols, device=gy.device, dtype=gy.dtype)
+        with torch.cuda.device(gy.device):
+            _lib.check(_lib.lib().rsrx_act_bias_backward(
+                gy.data_ptr(), z.data_ptr() if ctx.act else None, rows, cols, ctx.act, gz.data_ptr() if ctx.act else None,
+                db.data_ptr(), workspace.data_ptr(), torch.cuda.current_stream(gy.device).cuda_stream),
+                "rsrx_act_bias_backward")
+        gx = gz @ weight if ctx.needs_input_grad[0] else None
+        gw = gz.t() @ x
+        return gx, gw, db, None, None
+
+
+def linear_act(x, layer: nn.Linear, act: str, workspaces: dict):
+    """act(layer(x)).  CUDA float32 tensors that need gradients go through the fused backward; everything else
+    (CPU tensors in the host tests, no-grad inference, small batches) through plain torch."""
+    rows = x.numel() // max(x.shape[-1], 1)
+    if (x.device.type != "cuda" or rows < _FUSED_MIN_ROWS or not torch.is_grad_enabled()
+            or not (layer.weight.requires_grad or x.requires_grad)):
+        z = layer(x)
+        return F.silu(z) if act == "silu" else (F.relu(z) if act == "relu" else z)
+    from . import _lib
+    x2 = x.reshape(-1, x.shape[-1])
+    key = (x2.shape[0], layer.out_features, id(layer))
+    ws = workspaces.get(key)
+    if ws is None or ws.device != x.device:
+        n = _lib.lib().rsrx_act_bias_backward_workspace(x2.shape[0], layer.out_features)
+        ws = workspaces[key] = torch.zeros(n, device=x.device)
+    y = _LinearActFn.apply(x2, layer.weight, layer.bias, _ACT[act], ws)
+    return y.reshape(*x.shape[:-1], layer.out_features)
+
+
 class MLP(nn.Module):
+    activation = "silu"
+
     def __init__(self, sizes: Sequence[int]):
         super().__init__()
         self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:]))
@@ -38,12 +93,11 @@ class MLP(nn.Module):
             bound = math.sqrt(3.0 / l.in_features)
             nn.init.uniform_(l.weight, -bound, bound)
             nn.init.zeros_(l.bias)
+        self._ws: dict = {}
 
     def forward(self, x):
         for i, l in enumerate(self.layers):
-            x = l(x)
-            if i + 1 < len(self.layers):
-                x = F.silu(x)
+            x = linear_act(x, l, self.activation if i + 1 < len(self.layers) else "none", self._ws)
         return x
 
 

@@ -29,24 +29,12 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import rsr_loss as rsr
-from .ppo import NormalTanh, RunningStatistics, _flat_allreduce_mean
+from .ppo import MLP, NormalTanh, RunningStatistics, _flat_allreduce_mean
 
 
-class _ReluMLP(nn.Module):
-    def __init__(self, sizes: Sequence[int]):
-        super().__init__()
-        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:]))
-        for l in self.layers:  # flax lecun_uniform kernel, zero bias
-            bound = math.sqrt(3.0 / l.in_features)
-            nn.init.uniform_(l.weight, -bound, bound)
-            nn.init.zeros_(l.bias)
-
-    def forward(self, x):
-        for i, l in enumerate(self.layers):
-            x = l(x)
-            if i + 1 < len(self.layers):
-                x = F.relu(x)
-        return x
+class _ReluMLP(MLP):
+    """brax make_sac_networks uses relu (PPO: swish)"""
+    activation = "relu"
 
 
 class SACNetworks(nn.Module):

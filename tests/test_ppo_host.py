@@ -123,9 +123,12 @@ def test_policy_params_training_validation_matches_reference():
     with pytest.raises(ValueError, match="all five RSR policy datasets are required"):
         RP.policy_params_training(None, past_states=np.zeros((3, 23)))
     z = np.zeros((3, 23))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="unsupported algorithm 'td3'"):
         RP.policy_params_training(None, past_states=z, past_actions=np.zeros((3, 5)), past_next_states_real=z,
-                                  past_next_states_sim=z, current_next_states_sim=z, algorithm="sac")
+                                  past_next_states_sim=z, current_next_states_sim=z, algorithm="TD3")
+    with pytest.raises(NotImplementedError, match="Orbax"):
+        RP.policy_params_training(None, past_states=z, past_actions=np.zeros((3, 5)), past_next_states_real=z,
+                                  past_next_states_sim=z, current_next_states_sim=z, restore_checkpoint_path="/x")
     with pytest.raises(ValueError, match="RSR datasets must have equal lengths"):
         RP.build_policy_rsr_data(z, np.zeros((4, 5)), z, z, z)
     with pytest.raises(ValueError, match="real next-state width must match state width"):
