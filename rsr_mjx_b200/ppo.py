@@ -424,7 +424,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     last_metrics: Dict[str, torch.Tensor] = {}
 
     def fwd_bwd():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad(set_to_none=True)
         loss, metrics = loss_fn(net, normalize, static, static_noise, **loss_kw)
         loss.backward()
         return metrics

@@ -219,18 +219,18 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
 
     def grads_alpha_q():
         tr = view(static)
-        opt_alpha.zero_grad(set_to_none=False)
+        opt_alpha.zero_grad(set_to_none=True)
         la = alpha_loss(log_alpha, net, normalize, tr, noise[0], target_entropy)
         la.backward()
         alpha = torch.exp(log_alpha.detach()).clone()  # the OLD alpha feeds critic and actor
-        opt_q.zero_grad(set_to_none=False)
+        opt_q.zero_grad(set_to_none=True)
         lq = critic_loss(net, target, normalize, alpha, tr, noise[1], reward_scaling, discounting)
         lq.backward(inputs=q_params)
         return la, lq, alpha
 
     def grads_actor(alpha):
         tr = view(static)
-        opt_pi.zero_grad(set_to_none=False)
+        opt_pi.zero_grad(set_to_none=True)
         # all three gradients are taken at the OLD parameters and the optimisers step afterwards, which is brax's
         # alpha -> critic -> actor sequence (each of its updates reads `training_state`, not the fresh values)
         lp, s2r, distance = actor_loss(net, net, normalize, alpha, tr, noise[2], past_data, rsr_loss_scale)
