@@ -1132,13 +1132,8 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
 // the block-permuted dof order), Cholesky, Mgrad = H^-1 grad
 __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon,
                                              bool reuse_factor) {
-  const int nv = dm->nv;
   const bool tree_blocks = reinterpret_cast<const int*>(sm + ar::PTRS)[6] == 0;  // set by make_constraint
-  if (lane < nv) {
-    const float g = sm[ar::V_MA + lane] - sm[ar::V_SMOOTH + lane] - sm[ar::V_QFRCC + lane];
-    sm[ar::V_GRAD + lane] = g;
-    sm[ar::V_MGRAD + lane] = g;
-  }
+  // (grad itself is formed by the caller, which tests convergence on it before asking for the Newton direction)
   if (reuse_factor) {  // same active set as the previous iteration: H, hence its factor in ar::HH, is unchanged
     RSRX_SYNC();
     warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane, tree_blocks);
@@ -1398,20 +1393,30 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
   float prev_cost = INFINITY;
   const float scale = 1.f / (dm->meaninertia * (float)(nv > 1 ? nv : 1));
   int niter = 0, ls_total = 0;
-  bool changed = true;
+  bool changed = true, have_factor = false;
 #pragma unroll 1
   for (;;) {
-    update_gradient(dm, sm, lane, nsr, ncon, !changed);
-    if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
-    RSRX_SYNC();
-    const float improvement = (prev_cost - cost) * scale;
+    // _update_gradient, split: the gradient first, on which (with the cost improvement) MJX's loop condition is
+    // tested; the Newton direction (H assembly, Cholesky, solve) only if another iteration follows.  MJX computes it
+    // in the last pass too and throws it away: same qacc, one factorisation + solve less per mjx.step.
     float g = 0.f;
-    if (lane < nv) g = sm[ar::V_GRAD + lane] * sm[ar::V_GRAD + lane];
+    if (lane < nv) {
+      g = sm[ar::V_MA + lane] - sm[ar::V_SMOOTH + lane] - sm[ar::V_QFRCC + lane];
+      sm[ar::V_GRAD + lane] = g;
+      sm[ar::V_MGRAD + lane] = g;
+      g *= g;
+    }
+    const float improvement = (prev_cost - cost) * scale;
     const float gradient = sqrtf(warp_sum(g)) * scale;
     bool done = niter >= dm->iterations;
     done |= improvement < dm->tolerance;
     done |= gradient < dm->tolerance;
     if (done) break;
+    RSRX_SYNC();
+    update_gradient(dm, sm, lane, nsr, ncon, !changed && have_factor);
+    have_factor = true;
+    if (lane < nv) sm[ar::V_SEARCH + lane] = -sm[ar::V_MGRAD + lane];
+    RSRX_SYNC();
     ls_total += linesearch(dm, sm, lane, nsr, ncon, gauss);
     prev_cost = cost;
     cost = update_constraint(dm, sm, lane, nsr, ncon, &gauss, &changed);
