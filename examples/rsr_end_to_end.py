@@ -64,9 +64,10 @@ make_policy, params = rsr_pipeline.policy_params_training(
     train_env, past_states=S, past_actions=A, past_next_states_real=S1_real, past_next_states_sim=S1_past,
     current_next_states_sim=S1_cur, num_envs=512, batch_size=128, num_timesteps=10**9, num_evals=ppo_steps,
     max_training_steps=ppo_steps, progress_fn=lambda steps, m: seen.append((steps, m)))
-for steps, m in seen:
-    print(f"env-steps {steps}: reward {m['training/reward_mean']:.4f} total_loss {m['training/total_loss']:.4f} "
-          f"sim2real_loss {m['training/sim2real_loss']:.3e} sps {m['training/sps']:.0f}")
+for steps, m in seen:  # the first call is the evaluation before training (no training/* keys yet)
+    print(f"env-steps {steps}: eval/episode_reward {m['eval/episode_reward']:.3f} +- {m['eval/episode_reward_std']:.3f}"
+          + (f" | total_loss {m['training/total_loss']:.4f} sim2real_loss {m['training/sim2real_loss']:.3e} "
+             f"sps {m['training/sps']:.0f}" if "training/sps" in m else ""))
 ckpt = os.path.join(out_dir, "policy.pt")
 ppo.save_params(ckpt, params, extra={"tuned_friction": float(tuned)})
 (norm, net), meta = ppo.load_params(ckpt)

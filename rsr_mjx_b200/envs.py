@@ -185,6 +185,8 @@ class AirbotPlayBase:
         self.episode_length = int(episode_length)
         self.action_repeat = int(action_repeat)
         self._params = dict(kwargs)
+        self._model_path = model_path
+        self._randomization_fn = randomization_fn
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("AirbotPlayBase runs only on a CUDA device (no CPU fallback)")
@@ -212,6 +214,13 @@ class AirbotPlayBase:
             self.set_per_env(**{k: sys_v._ov[k] for k in System._PER_ENV if k in sys_v._ov})
         self._lowers = torch.tensor(self.model.act_ctrlrange[:, 0], dtype=torch.float32, device=self.device)
         self._uppers = torch.tensor(self.model.act_ctrlrange[:, 1], dtype=torch.float32, device=self.device)
+
+    def clone(self, num_envs: int, randomization_fn: Optional[Callable] = None, randomization_rng=None) -> "AirbotPlayBase":
+        """A second env of the same kind / reward parameters / wrapper settings with its own batch size (the eval env
+        of RSR/train.py:428-439 is the training env re-wrapped with `num_eval_envs` randomisation keys)."""
+        return AirbotPlayBase(self.kind, num_envs=num_envs, episode_length=self.episode_length,
+                              action_repeat=self.action_repeat, model_path=self._model_path, device=self.device,
+                              randomization_fn=randomization_fn, randomization_rng=randomization_rng, **self._params)
 
     # ------------------------------------------------------------------ properties
     @property

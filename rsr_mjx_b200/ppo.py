@@ -332,6 +332,56 @@ def compute_ppo_loss_fused(net: PPONetworks, normalize: Callable, data: Dict[str
                    "entropy_loss": stats[3], "sim2real_loss": sim2real_loss, "rsr_distribution_distance": distance}
 
 
+# ---------------------------------------------------------------------- evaluation
+class Evaluator:
+    """brax.training.acting.Evaluator + envs.training.EvalWrapper (RSR/train.py:441-447, :452, :482): every eval env
+    runs one episode; reward and every env metric are summed while the episode is active (up to and including the step
+    that ends it), `episode_steps` is the wrapper's step counter at that step."""
+
+    def __init__(self, eval_env, make_policy: Callable, num_eval_envs: int, episode_length: int, action_repeat: int = 1,
+                 seed: int = 0):
+        if eval_env.num_envs != num_eval_envs:
+            raise ValueError(f"eval env has {eval_env.num_envs} envs, num_eval_envs={num_eval_envs}")
+        self.env, self.make_policy = eval_env, make_policy
+        self.num_eval_envs, self.steps = num_eval_envs, episode_length // action_repeat
+        self._steps_per_unroll = episode_length * num_eval_envs
+        self._eval_walltime = 0.0
+        self._seed, self._calls = seed, 0
+        self._gen = torch.Generator(device=eval_env.device).manual_seed(seed * 104729 + 17)
+
+    @torch.no_grad()
+    def run_evaluation(self, training_metrics: Dict[str, float], aggregate_episodes: bool = True) -> Dict[str, Any]:
+        from . import prng
+        env, N = self.env, self.num_eval_envs
+        t0 = time.time()
+        key = prng.split(prng.PRNGKey(self._seed + 7919), self._calls + 2)[-1]  # a fresh unroll key per call
+        self._calls += 1
+        state = env.reset(prng.split(key, N))
+        policy = self.make_policy()
+        active = torch.ones(N, device=env.device)
+        ep = {"reward": torch.zeros(N, device=env.device)}
+        ep.update({k: torch.zeros(N, device=env.device) for k in state.metrics})
+        ep_steps = torch.zeros(N, device=env.device)
+        for _ in range(self.steps):
+            env.step(state, policy(state.obs, self._gen))
+            ep["reward"] += state.reward * active
+            for k, v in state.metrics.items():
+                ep[k] += v * active
+            ep_steps = torch.where(active > 0, state.info["steps"].float(), ep_steps)
+            active = active * (1 - state.done)
+        torch.cuda.synchronize(env.device)
+        dt = time.time() - t0
+        self._eval_walltime += dt
+        metrics: Dict[str, Any] = {}
+        for suffix, fn in (("", torch.mean), ("_std", lambda v: torch.std(v, unbiased=False))):
+            for k, v in ep.items():
+                metrics[f"eval/episode_{k}{suffix}"] = float(fn(v)) if aggregate_episodes else v.cpu().numpy()
+        metrics["eval/avg_episode_length"] = float(ep_steps.mean())
+        metrics["eval/epoch_eval_time"] = dt
+        metrics["eval/sps"] = self._steps_per_unroll / dt
+        return {"eval/walltime": self._eval_walltime, **training_metrics, **metrics}
+
+
 # ----------------------------------------------------------------------- training
 def _flat_allreduce_mean(params):
     """gradient pmean: one all-reduce of a flat buffer"""
@@ -357,9 +407,17 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           policy_hidden=(32,) * 4, value_hidden=(256,) * 5,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None,
           use_cuda_graph: bool = True, fused_head: bool = True, allow_tf32: bool = True,
-          max_training_steps: Optional[int] = None, **unused):
+          max_training_steps: Optional[int] = None, num_resets_per_eval: int = 0, deterministic_eval: bool = False,
+          eval_env=None, policy_params_fn: Callable[..., None] = lambda *a: None, run_evals: bool = True,
+          training_step_fn: Optional[Callable[[int, Dict[str, float]], None]] = None, **unused):
     """PPO training (RSR/train.py:76).  `environment` is an `AirbotPlayBase` with `num_envs` envs on this rank
     (under torch.distributed every rank passes its shard; `num_envs` is the per-rank count here).
+
+    Epoch structure of the reference (RSR/train.py:185-196, :449-492): `max(num_evals - 1, 1)` epochs of
+    `num_training_steps_per_epoch` training steps; rank 0 evaluates `num_eval_envs` single episodes before the first
+    epoch (if num_evals > 1) and after every epoch and calls `progress_fn(env_steps, {eval/..., training/...})` and
+    `policy_params_fn(env_steps, make_policy, params)`.  `run_evals=False` skips the evaluator (benchmarks),
+    `training_step_fn(step, training_metrics)` is called after every training step.
     Returns (make_policy, (normalizer, networks), metrics)."""
     env = environment
     # the two MLPs run their matmuls on the tensor cores in TF32, the precision jax gives float32 `dot` on NVIDIA GPUs
@@ -374,7 +432,10 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     env_step_per_training_step = batch_size * unroll_length * num_minibatches * action_repeat * world
-    num_training_steps = int(math.ceil(num_timesteps / env_step_per_training_step))
+    num_evals_after_init = max(num_evals - 1, 1)
+    steps_per_epoch = int(math.ceil(num_timesteps / (num_evals_after_init * env_step_per_training_step
+                                                      * max(num_resets_per_eval, 1)))) * max(num_resets_per_eval, 1)
+    num_training_steps = steps_per_epoch * num_evals_after_init
     if max_training_steps is not None:
         num_training_steps = min(num_training_steps, max_training_steps)
 
@@ -475,7 +536,28 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             _flat_allreduce_mean(params)
             opt.step()
 
+    def make_policy(deterministic: bool = False):
+        @torch.no_grad()
+        def policy(obs, generator=None):
+            logits = net.policy(normalize(obs))
+            return NormalTanh.mode(logits) if deterministic else torch.tanh(NormalTanh.sample_raw(logits, generator))
+        return policy
+
+    evaluator = None
+    if run_evals and rank == 0:
+        if eval_env is None:
+            from . import prng
+            rfn = getattr(env, "_randomization_fn", None)
+            eval_env = env.clone(num_eval_envs, randomization_fn=rfn,
+                                 randomization_rng=prng.split(prng.PRNGKey(seed + 2), num_eval_envs) if rfn else None)
+        evaluator = Evaluator(eval_env, lambda: make_policy(deterministic_eval), num_eval_envs, episode_length,
+                              action_repeat, seed)
+
     metrics_out: Dict[str, float] = {}
+    final_metrics: Dict[str, Any] = {}
+    if evaluator is not None and num_evals > 1:
+        final_metrics = evaluator.run_evaluation({})
+        progress_fn(0, final_metrics)
     t_start = time.time()
     env_steps = 0
     for it in range(num_training_steps):
@@ -500,14 +582,14 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         metrics_out["training/collect_s"] = ev[0].elapsed_time(ev[1]) * 1e-3  # device time of the unrolls
         metrics_out["training/update_s"] = ev[1].elapsed_time(ev[2]) * 1e-3   # ... of the SGD epochs
         metrics_out["training/reward_mean"] = float(data["reward"].mean())
-        if num_evals > 0 and (it + 1) % max(num_training_steps // max(num_evals, 1), 1) == 0:
-            progress_fn(env_steps, metrics_out)
+        if training_step_fn is not None:
+            training_step_fn(it, metrics_out)
+        if num_resets_per_eval > 0 and (it + 1) % max(steps_per_epoch // num_resets_per_eval, 1) == 0:
+            state = env.reset(sharding.shard_keys(seed + 1 + it, num_envs, rank, world))  # RSR/train.py:473-478
+        if (it + 1) % steps_per_epoch == 0 or it + 1 == num_training_steps:
+            final_metrics = evaluator.run_evaluation(metrics_out) if evaluator is not None else dict(metrics_out)
+            if rank == 0:
+                progress_fn(env_steps, final_metrics)
+                policy_params_fn(env_steps, make_policy, (norm, net))
 
-    def make_policy(deterministic: bool = False):
-        @torch.no_grad()
-        def policy(obs, generator=None):
-            logits = net.policy(normalize(obs))
-            return NormalTanh.mode(logits) if deterministic else torch.tanh(NormalTanh.sample_raw(logits, generator))
-        return policy
-
-    return make_policy, (norm, net), metrics_out
+    return make_policy, (norm, net), final_metrics or metrics_out

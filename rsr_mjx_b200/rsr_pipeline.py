@@ -189,7 +189,7 @@ def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, p
         from . import sac
         opts = {k: v for k, v in sac_and_extra_options.items()
                 if k in ("tau", "min_replay_size", "max_replay_size", "grad_updates_per_step", "hidden_layer_sizes",
-                         "use_cuda_graph", "allow_tf32", "max_training_steps")}
+                         "use_cuda_graph", "allow_tf32", "max_training_steps", "eval_env", "run_evals")}
         make_inference_fn, params, _ = sac.train(
             environment=env, past_data=past_data, num_timesteps=num_timesteps, num_evals=num_evals,
             num_eval_envs=num_eval_envs, reward_scaling=reward_scaling, episode_length=episode_length,
@@ -203,5 +203,8 @@ def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, p
         action_repeat=action_repeat, unroll_length=unroll_length, num_minibatches=num_minibatches,
         num_updates_per_batch=num_updates_per_batch, discounting=discounting, learning_rate=learning_rate,
         entropy_cost=entropy_cost, num_envs=num_envs, batch_size=batch_size, progress_fn=progress_fn or (lambda *a: None),
-        rsr_loss_scale=rsr_loss_scale, seed=seed, **{k: v for k, v in sac_and_extra_options.items() if k in ("use_cuda_graph", "fused_head", "allow_tf32", "max_training_steps")})
+        rsr_loss_scale=rsr_loss_scale, seed=seed, num_resets_per_eval=num_resets_per_eval,
+        deterministic_eval=deterministic_eval, policy_params_fn=policy_params_fn or (lambda *a: None),
+        **{k: v for k, v in sac_and_extra_options.items()
+           if k in ("use_cuda_graph", "fused_head", "allow_tf32", "max_training_steps", "eval_env", "run_evals")})
     return make_inference_fn, params

@@ -29,7 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import rsr_loss as rsr
-from .ppo import MLP, NormalTanh, RunningStatistics, _flat_allreduce_mean
+from .ppo import MLP, Evaluator, NormalTanh, RunningStatistics, _flat_allreduce_mean
 
 
 class _ReluMLP(MLP):
@@ -139,7 +139,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           max_replay_size: Optional[int] = None, grad_updates_per_step: int = 1, deterministic_eval: bool = False,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None, rsr_loss_scale: float = 1.0,
           hidden_layer_sizes=(256, 256), use_cuda_graph: bool = True, allow_tf32: bool = True,
-          max_training_steps: Optional[int] = None, **unused):
+          max_training_steps: Optional[int] = None, eval_env=None, run_evals: bool = True, **unused):
     """SAC training (RSR/sac_train.py:28).  `environment`: an `AirbotPlayBase` with `num_envs` envs on this rank.
     Returns (make_policy, (normalizer, networks), metrics)."""
     if rsr_loss_scale < 0:
@@ -294,9 +294,30 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             opt_alpha.step(); opt_q.step(); opt_pi.step()
             finish()
 
+    def make_policy(deterministic: bool = deterministic_eval):
+        @torch.no_grad()
+        def policy(obs, generator=None):
+            logits = net.policy(normalize(obs[..., :obs_size]))
+            return NormalTanh.mode(logits) if deterministic else torch.tanh(NormalTanh.sample_raw(logits, generator))
+        return policy
+
+    # brax sac.train: evaluation before training (num_evals > 1) and after every epoch, on rank 0
+    evaluator = None
+    if run_evals and rank == 0:
+        if eval_env is None:
+            from . import prng
+            rfn = getattr(env, "_randomization_fn", None)
+            eval_env = env.clone(num_eval_envs, randomization_fn=rfn,
+                                 randomization_rng=prng.split(prng.PRNGKey(seed + 2), num_eval_envs) if rfn else None)
+        evaluator = Evaluator(eval_env, lambda: make_policy(deterministic_eval), num_eval_envs, episode_length,
+                              action_repeat, seed)
+    metrics_out: Dict[str, Any] = {}
+    if evaluator is not None and num_evals > 1:
+        metrics_out = evaluator.run_evaluation({})
+        progress_fn(0, metrics_out)
+
     for _ in range(num_prefill_actor_steps):
         actor_step()
-    metrics_out: Dict[str, float] = {}
     env_steps = num_prefill_env_steps
     t_start = time.time()
     eval_every = max(steps_per_epoch, 1)
@@ -310,19 +331,14 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         if (it + 1) % eval_every == 0 or it + 1 == total_steps:
             torch.cuda.synchronize(dev)
             dt = time.time() - t0
-            metrics_out = {f"training/{k}": float(v.detach()) for k, v in metrics.items()}
-            metrics_out["training/sps"] = steps_since * env_steps_per_actor_step / dt
-            metrics_out["training/walltime"] = time.time() - t_start
-            metrics_out["training/reward_mean"] = float(state.reward.mean())
-            metrics_out["training/replay_size"] = float(buffer.size)
-            progress_fn(env_steps, metrics_out)
+            tm = {f"training/{k}": float(v.detach()) for k, v in metrics.items()}
+            tm["training/sps"] = steps_since * env_steps_per_actor_step / dt
+            tm["training/walltime"] = time.time() - t_start
+            tm["training/reward_mean"] = float(state.reward.mean())
+            tm["training/replay_size"] = float(buffer.size)
+            metrics_out = evaluator.run_evaluation(tm) if evaluator is not None else tm
+            if rank == 0:
+                progress_fn(env_steps, metrics_out)
             t0, steps_since = time.time(), 0
-
-    def make_policy(deterministic: bool = deterministic_eval):
-        @torch.no_grad()
-        def policy(obs, generator=None):
-            logits = net.policy(normalize(obs[..., :obs_size]))
-            return NormalTanh.mode(logits) if deterministic else torch.tanh(NormalTanh.sample_raw(logits, generator))
-        return policy
 
     return make_policy, (norm, net), metrics_out

@@ -179,3 +179,42 @@ def test_linear_act_fused_backward_matches_torch(act, rows, cin, cout):
             assert torch.equal(a_, b_), name  # deterministic
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def test_evaluator_matches_eval_wrapper_semantics():
+    """acting.Evaluator / EvalWrapper (RSR/train.py:441-447): reward and metrics summed while the episode is active,
+    one episode per eval env, `eval/*` keys the reference's progress_fn reads (test/rsr_policy_training.py:247-248)"""
+    env = AirbotPlayBase("sf", num_envs=32, episode_length=50)
+    zero_policy = lambda: (lambda obs, generator=None: torch.zeros(obs.shape[0], 5, device="cuda"))
+    ev = ppo.Evaluator(env, zero_policy, 32, 50, 1, seed=0)
+    m = ev.run_evaluation({"training/x": 1.0})
+    for k in ("eval/episode_reward", "eval/episode_reward_std", "eval/avg_episode_length", "eval/epoch_eval_time", "eval/sps",
+              "eval/walltime", "training/x"):
+        assert k in m, k
+    assert m["eval/avg_episode_length"] == 50.0  # nothing terminates early under the zero action: truncation at 50
+    # the same episode by hand
+    from rsr_mjx_b200 import prng
+    key = prng.split(prng.PRNGKey(7919), 2)[-1]
+    st = env.reset(prng.split(key, 32))
+    total = torch.zeros(32, device="cuda")
+    for _ in range(50):
+        env.step(st, torch.zeros(32, 5, device="cuda"))
+        total += st.reward
+    assert m["eval/episode_reward"] == pytest.approx(float(total.mean()), rel=1e-6)
+    per_env = ev.run_evaluation({}, aggregate_episodes=False)
+    assert per_env["eval/episode_reward"].shape == (32,)
+    with pytest.raises(ValueError):
+        ppo.Evaluator(env, zero_policy, 16, 50)
+
+
+def test_train_epochs_and_callbacks_follow_the_reference():
+    """num_evals=3 -> eval before training + after each of the 2 epochs; policy_params_fn after every epoch"""
+    env = AirbotPlayBase("sf", num_envs=64, episode_length=40)
+    seen, saved = [], []
+    per_step = 8 * 5 * 8  # batch_size * unroll_length * num_minibatches
+    ppo.train(env, num_timesteps=4 * per_step, episode_length=40, num_envs=64, unroll_length=5, batch_size=8, num_minibatches=8,
+              num_updates_per_batch=1, num_evals=3, num_eval_envs=16, progress_fn=lambda n, m: seen.append((n, m)),
+              policy_params_fn=lambda n, mk, params: saved.append(n))
+    assert [n for n, _ in seen] == [0, 2 * per_step, 4 * per_step] and saved == [2 * per_step, 4 * per_step]
+    assert "training/sps" not in seen[0][1] and "eval/episode_reward" in seen[0][1]
+    assert "training/sps" in seen[-1][1] and "eval/episode_reward_std" in seen[-1][1]

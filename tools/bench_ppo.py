@@ -23,7 +23,8 @@ sps, split = [], []
 ppo.train(env, num_timesteps=10**9, episode_length=1200, num_envs=N, learning_rate=1e-4, entropy_cost=2e-2, discounting=0.96,
           unroll_length=10, batch_size=256 // world, num_minibatches=32, num_updates_per_batch=8, num_evals=steps,
           normalize_observations=True, reward_scaling=0.1, use_cuda_graph=graph, max_training_steps=steps,
-          progress_fn=lambda n, m: (sps.append(m["training/sps"]), split.append((m["training/collect_s"], m["training/update_s"]))))
+          run_evals=False,
+          training_step_fn=lambda n, m: (sps.append(m["training/sps"]), split.append((m["training/collect_s"], m["training/update_s"]))))
 if rank == 0:
     print(json.dumps({"metric": "ppo_train_env_steps_per_sec", "n_gpus": world, "training_steps": steps, "cuda_graph": graph,
                       "sps_per_training_step": sps, "sps_steady": sum(sps[1:]) / max(len(sps) - 1, 1), "collect_s_update_s": split,

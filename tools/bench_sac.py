@@ -12,7 +12,7 @@ graph = (sys.argv[2] != "eager") if len(sys.argv) > 2 else True
 env = AirbotPlayBase("sf", num_envs=512, episode_length=1200)
 seen = []
 sac.train(env, num_timesteps=10**9, episode_length=1200, num_envs=512, batch_size=128, min_replay_size=10_000,
-          max_replay_size=200_000, num_evals=5, max_training_steps=steps, use_cuda_graph=graph,
+          max_replay_size=200_000, num_evals=5, max_training_steps=steps, use_cuda_graph=graph, run_evals=False,
           progress_fn=lambda n, m: seen.append(m["training/sps"]))
 # max_training_steps cuts the run short of an epoch: one progress call at the end
 print(json.dumps({"metric": "sac_train_env_steps_per_sec", "n_gpus": 1, "training_steps": steps, "cuda_graph": graph,
