@@ -154,3 +154,25 @@ def write_rsr_datasets(data_dir, real_obs, real_action, past_sim_obs, current_si
     tables = dict(zip(REQUIRED_DATA_FILES, (real_obs, real_action, past_sim_obs, current_sim_obs, obs, actions)))
     for name, table in tables.items():
         write_numeric_table(Path(data_dir) / name, table)
+
+
+def load_dataset_from_path(path):
+    """`(states, actions, next_states)` from an `.npz` with those three arrays (RSR/dataset_processor.py:10-14)."""
+    with np.load(Path(path), allow_pickle=True) as data:
+        missing = [k for k in ("states", "actions", "next_states") if k not in data]
+        if missing:
+            raise KeyError(f"{path}: missing arrays {missing}")
+        return np.array(data["states"]), np.array(data["actions"]), np.array(data["next_states"])
+
+
+def concatenate_states(states):
+    """Stacks the observations of a list of env `State`s row-wise (RSR/dataset_processor.py:45-53); accepts our batched
+    `State` (obs [N, obs_size]) as well as plain arrays."""
+    rows = []
+    for s in states:
+        obs = getattr(s, "obs", s)
+        obs = obs.detach().cpu().numpy() if hasattr(obs, "detach") else np.asarray(obs)
+        rows.append(obs.reshape(-1, obs.shape[-1]))
+    if not rows:
+        raise ValueError("no states to concatenate")
+    return np.vstack(rows)

@@ -87,3 +87,21 @@ def test_tuning_samples(tmp_path):
     assert len(o) == len(a) == len(n) == 5
     with pytest.raises(ValueError, match="no aligned transitions"):
         D.load_tuning_samples(tmp_path / "real_obs.txt", tmp_path / "real_action.txt", n=15, index=41)
+
+
+def test_npz_and_state_helpers(tmp_path):
+    g = np.random.default_rng(0)
+    S, A, S1 = g.normal(size=(7, 23)), g.normal(size=(7, 5)), g.normal(size=(7, 23))
+    np.savez(tmp_path / "d.npz", states=S, actions=A, next_states=S1)
+    s, a, s1 = D.load_dataset_from_path(tmp_path / "d.npz")
+    np.testing.assert_array_equal(s, S); np.testing.assert_array_equal(a, A); np.testing.assert_array_equal(s1, S1)
+    np.savez(tmp_path / "bad.npz", states=S)
+    with pytest.raises(KeyError, match="actions"):
+        D.load_dataset_from_path(tmp_path / "bad.npz")
+
+    class St:
+        def __init__(self, o): self.obs = o
+    out = D.concatenate_states([St(S[:3]), St(S[3]), S[4:]])
+    np.testing.assert_array_equal(out, S)
+    with pytest.raises(ValueError):
+        D.concatenate_states([])
