@@ -384,18 +384,15 @@ class Evaluator:
 
 # ----------------------------------------------------------------------- training
 def _flat_allreduce_mean(params):
-    """gradient pmean: one all-reduce of a flat buffer"""
+    """gradient pmean (RSR/train.py:261-262): one all-reduce of a flat buffer; flatten, scale and scatter-back are one
+    kernel each (multi-tensor copy), not one per parameter"""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    flat = torch._utils._flatten_dense_tensors(grads)
     dist.all_reduce(flat)
-    flat /= dist.get_world_size()
-    o = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[o:o + n].view_as(g))
-        o += n
+    flat.div_(dist.get_world_size())
+    torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
 
 
 def train(environment, num_timesteps: int, episode_length: int, past_data: Any = None, action_repeat: int = 1,

@@ -21,7 +21,19 @@ def _worker(rank, world, port, q):
         qpos, qvel, ctrl = A.sample_reset(m, "sf", keys)
         tmax = sharding.reduce_max([1.0 + rank, 5.0 - rank])
         gathered = sharding.gather_concat(torch.arange(3, dtype=torch.float32) + 10 * rank)
-        q.put((rank, keys, qpos, tmax, gathered.numpy(), list(sharding.env_range(n, rank))))
+        # PPO / SAC gradient pmean (RSR/train.py:261-262) and the normaliser's cross-rank statistics (:333-336)
+        from rsr_mjx_b200 import ppo
+        torch.manual_seed(0)
+        net = ppo.MLP([3, 4, 2])
+        extra = torch.nn.Parameter(torch.zeros(()))
+        params = list(net.parameters()) + [extra]
+        for i, p in enumerate(params):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        ppo._flat_allreduce_mean(params)
+        norm = ppo.RunningStatistics(2, "cpu")
+        norm.update(torch.tensor([[1.0, 2.0], [3.0, 6.0]]) + 10.0 * rank)
+        q.put((rank, keys, qpos, tmax, gathered.numpy(), list(sharding.env_range(n, rank)),
+               [float(p.grad.flatten()[0]) for p in params], norm.mean.numpy(), float(norm.count), norm.std.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -47,6 +59,12 @@ def test_env_sharding_world2():
     for r in res:
         assert r[3] == [2.0, 5.0]  # MAX over ranks, identical everywhere
         np.testing.assert_array_equal(r[4], [0, 1, 2, 10, 11, 12])
+        assert r[6] == [1.5 * (i + 1) for i in range(5)]  # mean over ranks of (rank + 1) * (i + 1), every parameter
+        # statistics of the union of both ranks' batches
+        allx = np.array([[1.0, 2.0], [3.0, 6.0], [11.0, 12.0], [13.0, 16.0]])
+        np.testing.assert_allclose(r[7], allx.mean(0), rtol=1e-6)
+        assert r[8] == 4.0
+        np.testing.assert_allclose(r[9], allx.std(0), rtol=1e-5)
 
 
 def test_single_process_degenerates():
