@@ -277,9 +277,9 @@ def main():
             "status_flagged_envs": status_bad,
         }
         if not args.no_cpu_baseline and world == 1:
-            rate, dt, thr = cpu_oracle_rate(args.kind, args.cpu_envs, 100, dense=False)
+            rate, dt, thr = cpu_oracle_rate(args.kind, args.cpu_envs, 1000, dense=False)  # ~10 s on 16 host threads
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": thr, "kind": "port",
-                                    "sample": f"{args.cpu_envs} envs x 100 steps, oracle port (C float32, OpenMP), active-set rows; {dt:.1f} s"}
+                                    "sample": f"{args.cpu_envs} envs x 1000 steps, oracle port (C float32, OpenMP), active-set rows; {dt:.1f} s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
