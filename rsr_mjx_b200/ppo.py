@@ -403,7 +403,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           gae_lambda: float = 0.95, rsr_loss_scale: float = 1.0, normalize_advantage: bool = True,
           policy_hidden=(32,) * 4, value_hidden=(256,) * 5,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None,
-          use_cuda_graph: bool = True, fused_head: bool = True, allow_tf32: bool = True,
+          use_cuda_graph: bool = True, fused_head: bool = True, allow_tf32: bool = True, graph_collect: bool = True,
           max_training_steps: Optional[int] = None, num_resets_per_eval: int = 0, deterministic_eval: bool = False,
           eval_env=None, policy_params_fn: Callable[..., None] = lambda *a: None, run_evals: bool = True,
           training_step_fn: Optional[Callable[[int, Dict[str, float]], None]] = None, **unused):
@@ -417,6 +417,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     `training_step_fn(step, training_metrics)` is called after every training step.
     Returns (make_policy, (normalizer, networks), metrics)."""
     env = environment
+    graph_collect_enabled = bool(graph_collect and use_cuda_graph)
     # the two MLPs run their matmuls on the tensor cores in TF32, the precision jax gives float32 `dot` on NVIDIA GPUs
     # by default (the reference never raises `jax_default_matmul_precision`); everything else stays fp32
     torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
@@ -453,14 +454,17 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
            dict(observation=(obs_size,), next_observation=(obs_size,), raw_action=(act_size,), log_prob=(), reward=(),
                 discount=(), truncation=()).items()}
 
+    act_noise = torch.empty(n_unrolls, T, num_envs, act_size, device=dev)  # N(0,1) of the behaviour policy, per unroll step
+
     @torch.no_grad()
-    def collect():
+    def collect_body():
         for u in range(n_unrolls):
             for t in range(T):
                 obs = state.obs
                 buf["observation"][u, t].copy_(obs)
                 logits = net.policy(normalize(obs))
-                raw = NormalTanh.sample_raw(logits, gen)
+                loc, scale = NormalTanh.params(logits)
+                raw = loc + scale * act_noise[u, t]
                 buf["raw_action"][u, t].copy_(raw)
                 buf["log_prob"][u, t].copy_(NormalTanh.log_prob(logits, raw))
                 env.step(state, torch.tanh(raw))
@@ -468,6 +472,18 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                 buf["reward"][u, t].copy_(state.reward)
                 buf["discount"][u, t].copy_(1 - state.done)
                 buf["truncation"][u, t].copy_(state.info["truncation"])
+
+    collect_graph = None
+
+    @torch.no_grad()
+    def collect():
+        """n_unrolls x T actor steps into `buf` (one CUDA-graph replay when captured: the ~45 small launches around
+        every env.step then run back to back)"""
+        act_noise.normal_(generator=gen)
+        if collect_graph is not None:
+            collect_graph.replay()
+        else:
+            collect_body()
         # [n_unrolls, T, N, ...] -> [B = n_unrolls * N, T, ...]
         return {k: v.permute(0, 2, 1, *range(3, v.dim())).reshape(B, T, *v.shape[3:]) for k, v in buf.items()}
 
@@ -518,6 +534,11 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph_opt):
             opt.step()
+        if graph_collect_enabled:
+            # capture only records: the env state is not advanced here; env.step is a plain launch on the capture stream
+            collect_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(collect_graph):
+                collect_body()
 
     def minibatch_step(batch, idx):
         nonlocal last_metrics
@@ -582,7 +603,9 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         if training_step_fn is not None:
             training_step_fn(it, metrics_out)
         if num_resets_per_eval > 0 and (it + 1) % max(steps_per_epoch // num_resets_per_eval, 1) == 0:
-            state = env.reset(sharding.shard_keys(seed + 1 + it, num_envs, rank, world))  # RSR/train.py:473-478
+            fresh = env.reset(sharding.shard_keys(seed + 1 + it, num_envs, rank, world))  # RSR/train.py:473-478
+            for k_, v_ in state._buf.items():  # in place: a captured collect graph keeps reading these buffers
+                v_.copy_(fresh._buf[k_])
         if (it + 1) % steps_per_epoch == 0 or it + 1 == num_training_steps:
             final_metrics = evaluator.run_evaluation(metrics_out) if evaluator is not None else dict(metrics_out)
             if rank == 0:
