@@ -16,8 +16,12 @@ using namespace rsrx;
 struct rsrx_model {
   DModel host;
   DModel* dev;
-  int smem_bytes;
+  int smem_bytes;   // dynamic shared memory of a full CTA (WPB envs)
   int num_sms;
+  // overflow of the shared-memory Jacobian-row pool: [spill_envs][ar::SPILL_STRIDE] floats, grown on demand (the only
+  // allocation reset/step ever make: the first call for a larger N, never inside a stream capture)
+  float* spill = nullptr;
+  int spill_envs = 0;
 };
 
 // Launch shape for N envs: one CTA per SM per round, the rounds as evenly filled as possible.  8192 envs on 148 SMs:
@@ -30,8 +34,7 @@ static LaunchCfg launch_cfg(const rsrx_model* m, int N) {
   static const int forced = getenv("RSRX_FORCE_WPB") ? atoi(getenv("RSRX_FORCE_WPB")) : 0;  // experiments only
   if (forced > 0) w = forced;
   w = w < 1 ? 1 : (w > WPB ? WPB : w);
-  const size_t pad = (size_t)(m->smem_bytes - WPB * ar::TOTAL * (int)sizeof(float));
-  return {(N + w - 1) / w, 32 * w, (size_t)w * ar::TOTAL * sizeof(float) + pad};
+  return {(N + w - 1) / w, 32 * w, (size_t)w * m->host.arena_stride * sizeof(float)};
 }
 
 static thread_local std::string g_err;
@@ -253,7 +256,7 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
     for (int e = 0; e < d.ntri; e++) {
       int i = d.tri_i[e], j = d.tri_j[e], pi = d.pos_of_dof[i], pj = d.pos_of_dof[j];
       d.tri_src[e] = (unsigned short)(i * LD + j);
-      d.tri_dst[e] = (unsigned short)((pi > pj ? pi : pj) * LD + (pi > pj ? pj : pi));
+      d.tri_dst[e] = (unsigned short)(tri(pi > pj ? pi : pj) + (pi > pj ? pj : pi));
     }
     for (int q = 0; q < b.nv; q++) {  // per-tree sub-blocks inside the permuted order
       int t = d.body_treeid[b.dof_bodyid[d.dof_of_pos[q]]], lo = q, hi = q;
@@ -329,13 +332,23 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
   if (blob_bytes != sizeof(rsrx_model_blob)) return fail("rsrx_model_create: blob size mismatch (host/lib out of sync)");
   rsrx_model* m = new rsrx_model();
   if (build_dmodel(*reinterpret_cast<const rsrx_model_blob*>(blob_host), *cfg_host, m->host)) { delete m; return 1; }
-  m->smem_bytes = WPB * ar::TOTAL * (int)sizeof(float);
   {
-    int dev = 0;
+    // the arena fills the SM's shared memory at WPB envs per CTA: whatever is left after the fixed part is the
+    // Jacobian-row pool (B200: 232448 B / 19 envs = 3058 floats per env, 2176 fixed, 882 pool)
+    int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || m->num_sms <= 0)
       m->num_sms = 148;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || max_smem <= 0)
+      max_smem = 227 * 1024;
+    int stride = max_smem / (int)sizeof(float) / WPB;
+    int pool = stride - ar::FIXED;
+    if (const char* f = getenv("RSRX_POOL_FLOATS")) pool = atoi(f);  // tests: a small pool forces the spill path
+    if (pool > MAXC * 4 * NCOL) pool = MAXC * 4 * NCOL;
+    if (pool < ar::MIN_POOL) { delete m; return fail("rsrx_model_create: not enough shared memory per block for the arena"); }
+    m->host.pool_floats = pool;
+    m->host.arena_stride = ar::FIXED + pool;
+    m->smem_bytes = WPB * m->host.arena_stride * (int)sizeof(float);
   }
-  if (const char* pad = getenv("RSRX_SMEM_PAD")) m->smem_bytes += atoi(pad);  // occupancy experiments only
   cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
@@ -354,6 +367,7 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
 extern "C" void rsrx_model_destroy(rsrx_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
+  if (m->spill) cudaFree(m->spill);
   delete m;
 }
 
@@ -363,10 +377,25 @@ extern "C" int rsrx_model_layout(const rsrx_model* m, rsrx_layout* out) {
   return 0;
 }
 
-static PerEnv to_pe(const rsrx_per_env* p) {
-  PerEnv pe = {nullptr, nullptr, nullptr, nullptr};
+static PerEnv to_pe(const rsrx_model* m, const rsrx_per_env* p) {
+  PerEnv pe = {nullptr, nullptr, nullptr, nullptr, m->spill};
   if (p) { pe.geom_friction = p->geom_friction; pe.body_mass = p->body_mass; pe.dof_damping = p->dof_damping; pe.dof_frictionloss = p->dof_frictionloss; }
   return pe;
+}
+// make sure the spill buffer covers N envs
+static int ensure_spill(const rsrx_model* cm, int N) {
+  rsrx_model* m = const_cast<rsrx_model*>(cm);
+  if (N <= m->spill_envs) return 0;
+  float* fresh = nullptr;
+  cudaError_t e = cudaMalloc(&fresh, sizeof(float) * (size_t)N * ar::SPILL_STRIDE);
+  if (e != cudaSuccess) {
+    return fail(std::string("rsrx: cannot allocate the Jacobian spill buffer (call reset/step once for this batch size "
+                            "before capturing a CUDA graph): ") + cudaGetErrorString(e));
+  }
+  if (m->spill) { cudaDeviceSynchronize(); cudaFree(m->spill); }
+  m->spill = fresh;
+  m->spill_envs = N;
+  return 0;
 }
 static StatePtrs to_sp(const rsrx_state& s) {
   StatePtrs p;
@@ -385,8 +414,9 @@ extern "C" int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, con
   if (!m || !qpos || !qvel || !ctrl) return fail("rsrx_env_reset: null argument");
   if (N <= 0) return fail("rsrx_env_reset: N must be positive");
   if (check_state(st)) return 1;
+  if (ensure_spill(m, N)) return 1;
   const LaunchCfg lc = launch_cfg(m, N);
-  reset_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(per_env), to_sp(st));
+  reset_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -396,8 +426,9 @@ extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const fl
   if (!m || !action) return fail("rsrx_env_step: null argument");
   if (N <= 0) return fail("rsrx_env_step: N must be positive");
   if (check_state(st)) return 1;
+  if (ensure_spill(m, N)) return 1;
   const LaunchCfg lc = launch_cfg(m, N);
-  step_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(per_env), to_sp(st));
+  step_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -411,8 +442,9 @@ extern "C" int rsrx_env_step_host(const rsrx_model* m, int N, rsrx_state st, con
   cudaStream_t s = (cudaStream_t)stream;
   const rsrx_layout& L = m->host.lay;
   CUDA_OK(cudaMemcpyAsync(action_staging, host_action, sizeof(float) * (size_t)N * m->host.nu, cudaMemcpyHostToDevice, s));
+  if (ensure_spill(m, N)) return 1;
   const LaunchCfg lc = launch_cfg(m, N);
-  step_kernel<<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(per_env), to_sp(st));
+  step_kernel<<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   if (host_obs) CUDA_OK(cudaMemcpyAsync(host_obs, st.obs, sizeof(float) * (size_t)N * L.obs_stride, cudaMemcpyDeviceToHost, s));
   if (host_reward) CUDA_OK(cudaMemcpyAsync(host_reward, st.reward, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
@@ -424,8 +456,9 @@ extern "C" int rsrx_physics_step(const rsrx_model* m, int N, float* data, int ns
                                  int32_t* status, void* stream) {
   if (!m || !data) return fail("rsrx_physics_step: null argument");
   if (N <= 0 || nsteps < 0) return fail("rsrx_physics_step: bad N / nsteps");
+  if (ensure_spill(m, N)) return 1;
   const LaunchCfg lc = launch_cfg(m, N);
-  physics_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(per_env), status, nullptr);
+  physics_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(m, per_env), status, nullptr);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -434,8 +467,9 @@ extern "C" int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, 
                                        void* stream) {
   if (!m || !data || !dump) return fail("rsrx_physics_step_debug: null argument");
   if (N <= 0) return fail("rsrx_physics_step_debug: bad N");
+  if (ensure_spill(m, N)) return 1;
   const LaunchCfg lc = launch_cfg(m, N);
-  physics_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, data, 1, to_pe(per_env), nullptr, dump);
+  physics_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, data, 1, to_pe(m, per_env), nullptr, dump);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -21,6 +21,7 @@ constexpr int MAXSR = 20;         // sparse rows: equality + dof friction + join
 constexpr int MAXROW = MAXSR + 6 * MAXC;
 constexpr int LD = NV + 1;        // padded leading dimension of the dense nv x nv matrices
 constexpr int NTRI = NV * (NV + 1) / 2;
+__host__ __device__ constexpr int tri(int p) { return (p * (p + 1)) >> 1; }  // start of row p in a packed lower triangle
 constexpr int MAXMENT = 96;       // (i, ancestor j) entries of the mass matrix
 constexpr int MAXTREE_ = 4;
 constexpr int OBS_STRIDE = 24;
@@ -84,6 +85,8 @@ struct DModel {
   float action_scale[NU], push_reward_weight, siet_to_box_reward_weight, healthy_reward, endpoint_min_z_pos;
   // layout
   rsrx_layout lay;
+  // shared-memory arena: floats per env (ar::FIXED + pool_floats) and the size of the Jacobian-row pool at its end
+  int arena_stride, pool_floats;
 };
 
 // ---- per-warp shared-memory arena (float words) --------------------------------
@@ -93,9 +96,14 @@ struct DModel {
 // collision / make_constraint (same results).
 constexpr int MAXTREE = MAXTREE_;   // kinematic trees (top-level bodies)
 constexpr int NCOL = 14;     // widest contact Jacobian: dofs of the two trees a collision pair joins
+// envs (= warps) per CTA at most: the arena is sized so that this many fill one SM's shared memory
+#ifndef RSRX_WPB
+#define RSRX_WPB 19
+#endif
 namespace ar {
-constexpr int PTRS = 0;  // 4 device pointers (per-env geom_friction, body_mass, dof_frictionloss, spare)
-constexpr int QPOS = PTRS + 8;
+constexpr int PTRS = 0;  // 4 device pointers (per-env geom_friction, body_mass, dof_frictionloss, Jacobian-row spill) + 2 int flags
+constexpr int FLAGS = 8; // int index into PTRS: [8] = "a contact couples two kinematic trees"
+constexpr int QPOS = PTRS + 12;
 constexpr int QVEL = QPOS + NQ;
 constexpr int CTRL = QVEL + NV;
 constexpr int WARM = CTRL + NU;
@@ -106,26 +114,25 @@ constexpr int SXPOS = XQUAT + NB * 4;
 constexpr int SCOM = SXPOS + NS * 3;       // subtree com of each kinematic tree root
 constexpr int CDOF = SCOM + MAXTREE * 3;
 constexpr int MM = CDOF + NV * 6;          // lower triangle, packed: M[i][j] at i (i + 1) / 2 + j
-constexpr int HH = MM + NTRI;              // dense, leading dim LD, block-permuted order; also scratch
+constexpr int HH = MM + NTRI;              // lower triangle, packed by rows (row p at tri(p)), block-permuted order; also scratch
 // nv-vectors
-constexpr int V_SMOOTH = HH + NV * LD;
+constexpr int V_SMOOTH = HH + NTRI;
 constexpr int V_QACCS = V_SMOOTH + NV;
 constexpr int V_QACC = V_QACCS + NV;
 constexpr int V_QFRCC = V_QACC + NV;
 constexpr int V_MA = V_QFRCC + NV;
 constexpr int V_GRAD = V_MA + NV;
 constexpr int V_MGRAD = V_GRAD + NV;
-constexpr int V_SEARCH = V_MGRAD + NV;
-constexpr int V_MV = V_SEARCH + NV;
+constexpr int V_SEARCH = V_MGRAD;     // search = -Mgrad, negated in place
+constexpr int V_MV = V_MGRAD + NV;
 constexpr int V_TMP = V_MV + NV;
 constexpr int V_RDIAG = V_TMP + NV;  // 1 / L_kk of the factor in HH
 constexpr int V_ACT = V_TMP;          // qfrc_actuator (debug dump only) shares V_TMP (integration scratch)
-// contacts
-constexpr int CSTRIDE = 21;
+// contacts: the part of the record that lives through the solver (cf::)
+constexpr int CSTRIDE = 10;
 constexpr int CON = V_RDIAG + NV;
-constexpr int BROW = CON + MAXC * CSTRIDE;  // [c][4][NCOL]
 // efc rows
-constexpr int E_AREF = BROW + MAXC * 4 * NCOL;
+constexpr int E_AREF = CON + MAXC * CSTRIDE;
 constexpr int E_DS = E_AREF + MAXROW;     // D of the sparse rows (contact rows: D in the contact record)
 // sparse-row meta
 constexpr int SR_DOFA = E_DS + MAXSR;     // int
@@ -146,27 +153,43 @@ constexpr int CRB = CINERT + NB * 10;     // crb while building M, then cacc
 constexpr int CDOFDOT = CRB + NB * 10;    // crb_cdof while building M, then cdof_dot
 constexpr int CVEL = CDOFDOT + NV * 6;
 constexpr int P_END = CVEL + NB * 6;
-// ---- ... region C (collision only; P is dead by then, S not yet alive): world poses of all geoms + surviving pairs
-constexpr int GPOSE = U;                   // [g][12]: pos(3), mat(9)
-constexpr int PLIST = GPOSE + NG * 12;     // int [MAXPAIR]
-constexpr int CSCRATCH = PLIST + RSRX_MAXPAIR;  // 8 clipped polygon vertices per half warp
-constexpr int C_END = CSCRATCH + 2 * 24;
 // ---- ... and region S (alive from make_constraint's contact pass to the end of the solver)
 constexpr int E_JAREF = U;
 constexpr int E_JV = E_JAREF + MAXROW;
-constexpr int E_ACT = E_JV + MAXROW;
-constexpr int UB = E_ACT + MAXROW;         // [c][4] base-row scratch ...
+constexpr int E_ACT = E_JV + MAXROW;       // one bit per row
+constexpr int UB = E_ACT + (MAXROW + 31) / 32;  // [c][4] base-row scratch ...
 constexpr int CW = UB;                     // ... / [c][8] per-contact Hessian weights (never live together)
 constexpr int S_END = CW + MAXC * 8;
-constexpr int TOTAL = (P_END > S_END ? P_END : S_END);
-static_assert(C_END <= TOTAL, "collision scratch must fit the union region");
+// the transient part of the contact record (ct::: position + frame) is only read while the Jacobian rows are built, i.e.
+// before the solver first writes E_JAREF / E_JV
+constexpr int CTMP = E_JAREF;              // [c][CTSTRIDE]
+constexpr int CTSTRIDE = 12;
+static_assert(MAXC * CTSTRIDE <= 2 * MAXROW, "transient contact data must fit E_JAREF + E_JV");
+constexpr int U_END = (P_END > S_END ? P_END : S_END);
+// ---- Jacobian base rows: a POOL at the end of the arena, DModel::pool_floats long (chosen at model creation so that
+// the arena fills the SM's shared memory at WPB envs per CTA).  Contact c owns 4 rows of width na + nb at cf::BOFF; what
+// does not fit goes to the env's global-memory spill row (cf::BOFF < 0).  The arena stride is FIXED + pool_floats.
+constexpr int BROW = U_END;
+constexpr int FIXED = BROW;
+// ---- region C (collision only: the pool is empty then): world poses of all geoms + surviving pairs + clip scratch
+constexpr int GPOSE = BROW;                // [g][12]: pos(3), mat(9)
+constexpr int PLIST = GPOSE + NG * 12;     // int [MAXPAIR]
+constexpr int CSCRATCH = PLIST + RSRX_MAXPAIR;  // 8 clipped polygon vertices per half warp
+constexpr int C_END = CSCRATCH + 2 * 24;
+constexpr int MIN_POOL = C_END - BROW;     // the pool must at least hold region C
+constexpr int SPILL_STRIDE = MAXC * 4 * NCOL;  // floats per env in the global spill buffer (contact c at c * 4 * NCOL)
 }  // namespace ar
 
 // contact record fields
 namespace cf {
-constexpr int POS = 0, FRAME = 3, DIST = 12, MU = 13, KIMPD = 16, B = 17, D = 18, BODIES = 19, COLS = 20;  // MU: mu, mu, torsion
+constexpr int DIST = 0, MU = 1, KIMPD = 4, B = 5, D = 6, BODIES = 7, COLS = 8, BOFF = 9;  // MU: mu, mu, torsion
 // COLS packs the dof ranges of the two kinematic trees the contact joins: a0 | na << 8 | b0 << 16 | nb << 24;
-// Jacobian column c is dof a0 + c (c < na) or b0 + c - na.
+// Jacobian column c is dof a0 + c (c < na) or b0 + c - na.  BOFF: int offset of the contact's 4 x (na + nb) base rows
+// in the pool, or -(spill offset + 1).
+}
+// transient contact fields (ar::CTMP)
+namespace ct {
+constexpr int POS = 0, FRAME = 3;
 }
 
 // ---- debug dump layout (floats per env) -----------------------------------------

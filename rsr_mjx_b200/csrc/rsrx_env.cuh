@@ -12,6 +12,7 @@ struct PerEnv {
   const float* body_mass;
   const float* dof_damping;
   const float* dof_frictionloss;
+  float* spill;  // [N][ar::SPILL_STRIDE] library-owned overflow of the Jacobian-row pool
 };
 
 // load the dynamic state of env `e` into the arena; per-env model arrays stay in global memory and
@@ -34,7 +35,8 @@ __device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, 
     ptrs[0] = pe.geom_friction ? pe.geom_friction + (size_t)e * dm->ngeom * 3 : nullptr;
     ptrs[1] = pe.body_mass ? pe.body_mass + (size_t)e * dm->nbody : nullptr;
     ptrs[2] = pe.dof_frictionloss ? pe.dof_frictionloss + (size_t)e * dm->nv : nullptr;
-    reinterpret_cast<int*>(sm + ar::PTRS)[6] = 1;
+    ptrs[3] = pe.spill + (size_t)e * ar::SPILL_STRIDE;
+    reinterpret_cast<int*>(sm + ar::PTRS)[ar::FLAGS] = 1;
   }
   RSRX_SYNC();
 }
@@ -86,11 +88,8 @@ __device__ void get_obs(const DModel* __restrict__ dm, float* sm, const float* i
 // Warps per CTA: one env per warp, warps are independent (only __syncwarp).  Single-warp CTAs all land on
 // the same SM sub-partition (warp id within the CTA selects the scheduler), leaving 3 of the 4 schedulers
 // idle — so a CTA carries WPB envs; with the per-substep phase barrier (rsrx_physics.cuh) ONE CTA of
-// WPB = 14 warps per SM (the 16.3 KB arena allows 14) keeps every resident warp in the same code region
+// WPB = 19 warps per SM (what the 12 KB arena allows) keeps every resident warp in the same code region
 // (measured at 8192 envs: 1 x 14 warps 4.9 ms, 2 x 7 warps 5.6 ms, 8 warps 6.3 ms, no barrier 9.5 ms).
-#ifndef RSRX_WPB
-#define RSRX_WPB 14
-#endif
 constexpr int WPB = RSRX_WPB;
 
 struct StatePtrs {
@@ -106,7 +105,7 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
                                                   PerEnv pe, StatePtrs st) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
-  float* sm = smem + wib * ar::TOTAL;
+  float* sm = smem + wib * dm->arena_stride;
   if (e >= N) return;
   const rsrx_layout& L = dm->lay;
   float* row = st.data + (size_t)e * L.data_stride;
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(32 * WPB) step_kernel(const DModel* __restrict
                                                  PerEnv pe, StatePtrs st) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
-  float* sm = smem + wib * ar::TOTAL;
+  float* sm = smem + wib * dm->arena_stride;
   if (e >= N) {
     for (int f = 0; f < dm->n_frames * kPhaseBarriers; ++f) phase_barrier<true>(__builtin_ctz(RSRX_SYNC_MASK));  // shadow the phase barriers
     return;
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
                                                     float* __restrict__ dump) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
-  float* sm = smem + wib * ar::TOTAL;
+  float* sm = smem + wib * dm->arena_stride;
   if (e >= N) return;
   const rsrx_layout& L = dm->lay;
   float* row = data + (size_t)e * L.data_stride;
@@ -358,11 +357,17 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
         dp[dbg::QFRC_ACT + i] = sm[ar::V_ACT + i];
       }
       if (lane == 0) { dp[dbg::NCON] = (float)sd.ncon; dp[dbg::NEFC] = (float)sd.nrow; dp[dbg::NITER] = (float)(niter & 0xff); dp[dbg::LS_TOTAL] = (float)(niter >> 8); }
+      // the contact positions lived in storage the solver has reused: qpos is unchanged, so collision() rebuilds them
+      {
+        int scratch_status = 0;
+        collision(dm, sm, lane, &scratch_status);
+      }
       for (int c = lane; c < MAXC; c += 32) {
         const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+        const float* ctm = sm + ar::CTMP + c * ar::CTSTRIDE;
         const bool v = c < sd.ncon;
         dp[dbg::CDIST + c] = v ? cr[cf::DIST] : 0.f;
-        for (int i = 0; i < 3; i++) dp[dbg::CPOS + c * 3 + i] = v ? cr[cf::POS + i] : 0.f;
+        for (int i = 0; i < 3; i++) dp[dbg::CPOS + c * 3 + i] = v ? ctm[ct::POS + i] : 0.f;
         const int bodies = __float_as_int(cr[cf::BODIES]);
         dp[dbg::CGEOM + c] = v ? (float)(((bodies >> 16) & 0xff) * 64 + ((bodies >> 24) & 0xff)) : -1.f;
       }

@@ -196,10 +196,10 @@ __device__ __noinline__ void com_pos(const DModel* __restrict__ dm, float* sm, i
 // BLOCK-PERMUTED dof order (DModel::pos_of_dof: dofs that can ever be coupled —
 // same kinematic tree or a collision pair between their trees — are contiguous;
 // everything outside the diagonal blocks is structurally zero and never touched).
-// A's lower triangle (leading dim LD) is overwritten by its factor; 1/L_kk goes to
+// A's lower triangle (packed by rows) is overwritten by its factor; 1/L_kk goes to
 // ar::V_RDIAG.  COMPACT code on purpose (the kernel is instruction-fetch bound, see
 // profiles/): rolled right-looking factorisation; lane p owns row p, which lives in
-// shared memory (stride LD = 21 words: conflict-free) and is touched by that lane
+// shared memory (row starts 0, 1, 3, 6, ...: distinct banks for nv <= 20) and is touched by that lane
 // only; whatever crosses lanes (pivot, column k) travels by shuffle, so there are
 // no barriers in the dependency chain; the pivot column is scaled by one rsqrt
 // (no IEEE sqrt / division subroutines).
@@ -209,7 +209,7 @@ __device__ __noinline__ void warp_chol_factor(const DModel* __restrict__ dm, flo
   const int n = dm->nv;
   const bool own = lane < n;
   const int p = own ? lane : n - 1;  // surplus lanes shadow the last row (reads only)
-  float* row = A + p * LD;
+  float* row = A + tri(p);
   // tree_blocks: no contact couples two kinematic trees right now (always true for M itself), so the blocks are
   // the trees (8 | 6 | 6 instead of 14 | 6 for the cube model).  The diagonal blocks are independent, so they are
   // factored SIDE BY SIDE: in round kk every block eliminates its own kk-th column (pivot lane pstart + kk), and the
@@ -253,7 +253,7 @@ __device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, floa
   const int rounds = tree_blocks ? dm->tblk_max : dm->blk_max;
   const int dof = dm->dof_of_pos[p];
   const float rdiag = sm[ar::V_RDIAG + p];
-  const float* row = A + p * LD;
+  const float* row = A + tri(p);
   float xi = x[dof];
 #pragma unroll 1
   for (int kk = 0; kk < rounds; ++kk) {  // forward: L y = b (row-oriented, own row)
@@ -269,7 +269,7 @@ __device__ __noinline__ void warp_chol_solve(const DModel* __restrict__ dm, floa
     const bool act = own && k <= pend;
     const float xk = __shfl_sync(FULL, xi * rdiag, act ? k : p);
     if (act && lane == k) xi = xk;
-    else if (act && lane < k) xi -= A[k * LD + p] * xk;
+    else if (act && lane < k) xi -= A[tri(k) + p] * xk;
   }
   if (own) x[dof] = xi;
   RSRX_SYNC();
@@ -666,7 +666,7 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
 #ifdef RSRX_PRINT_NSURV
   if (lane == 0) { printf("NSURV %d :", nsurv); for (int q = 0; q < nsurv; q++) printf(" %d-%d", dm->pair_g1[plist[q]], dm->pair_g2[plist[q]]); printf("\n"); }
 #endif
-  int ncon = 0;
+  int ncon = 0, boff = 0;  // contacts so far / cursor into the Jacobian-row pool
   Half hw;
   hw.shift = lane & 16; hw.l = lane & 15; hw.mask = 0xffffu << hw.shift;
 #pragma unroll 1
@@ -695,25 +695,33 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
     if (am == 0u) continue;
     const int slot = ncon + __popc(am & ((1u << lane) - 1u));
     if (ncon + __popc(am) > MAXC) *status |= RSRX_STATUS_CONTACT_OVERFLOW;
+    // dof ranges of the two trees this pair joins (a static body contributes no columns) = width of its Jacobian rows
+    const int b1 = dm->geom_bodyid[g1], b2 = dm->geom_bodyid[g2];
+    const int t1 = dm->body_treeid[b1], t2 = dm->body_treeid[b2];
+    const int na = dm->body_dofmask[b1] ? dm->tree_dofnum[t1] : 0, nb = dm->body_dofmask[b2] ? dm->tree_dofnum[t2] : 0;
+    // row-pool allocation in contact order: half 0's contacts, then half 1's (a contact that does not fit is spilled
+    // but still advances the cursor, so everything after it spills too: rare)
+    const int sz = 4 * (na + nb);
+    const int sz0 = __shfl_sync(0xffffffffu, sz, 0), sz1 = __shfl_sync(0xffffffffu, sz, 16);
+    const int cnt0 = __popc(am & 0xffffu), cnt1 = __popc(am >> 16);
+    const int rank = __popc(am & hw.mask & ((1u << lane) - 1u));
+    const int off = boff + (hw.shift ? cnt0 * sz0 : 0) + rank * sz;
     if (active && slot < MAXC) {
       float frame[9];
       make_frame(frame, mf.nrm);
-      const int b1 = dm->geom_bodyid[g1], b2 = dm->geom_bodyid[g2];
       float mu[3];
       const float* gfric_e = reinterpret_cast<const float* const*>(sm + ar::PTRS)[0];
       for (int i = 0; i < 3; i++)
         mu[i] = gfric_e ? fmaxf(gfric_e[g1 * 3 + i], gfric_e[g2 * 3 + i]) : fmaxf(dm->geom_friction[g1][i], dm->geom_friction[g2][i]);
-      // dof ranges of the two trees this pair joins (a static body contributes no columns)
-      const int t1 = dm->body_treeid[b1], t2 = dm->body_treeid[b2];
-      const int na = dm->body_dofmask[b1] ? dm->tree_dofnum[t1] : 0, nb = dm->body_dofmask[b2] ? dm->tree_dofnum[t2] : 0;
       const int cols = (na ? dm->tree_dofadr[t1] : 0) | (na << 8) | ((nb ? dm->tree_dofadr[t2] : 0) << 16) | (nb << 24);
       float solref[2] = {dm->pair_solref[p][0], dm->pair_solref[p][1]}, solimp[5];
       for (int i = 0; i < 5; i++) solimp[i] = dm->pair_solimp[p][i];
       const float tran = dm->pair_tran[p];
       const float invw = (tran + mu[0] * mu[0] * tran) * 2.f * mu[0] * mu[0] / dm->impratio;
       float* cr = sm + ar::CON + slot * ar::CSTRIDE;
-      for (int i = 0; i < 3; i++) cr[cf::POS + i] = mf.pos[i];
-      for (int i = 0; i < 9; i++) cr[cf::FRAME + i] = frame[i];
+      float* ctm = sm + ar::CTMP + slot * ar::CTSTRIDE;
+      for (int i = 0; i < 3; i++) ctm[ct::POS + i] = mf.pos[i];
+      for (int i = 0; i < 9; i++) ctm[ct::FRAME + i] = frame[i];
       const float ps = mf.dist - margin;
       float k, bb, imp;
       kbi(dm, solref, solimp, ps, &k, &bb, &imp);
@@ -726,7 +734,9 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
       cr[cf::D] = 1.f / rr;
       cr[cf::BODIES] = __int_as_float(b1 | (b2 << 8) | (g1 << 16) | (g2 << 24));
       cr[cf::COLS] = __int_as_float(cols);
+      cr[cf::BOFF] = __int_as_float(off + sz <= dm->pool_floats ? off : -(slot * 4 * NCOL + 1));
     }
+    boff += cnt0 * sz0 + cnt1 * sz1;
     ncon += __popc(am);
   }
   RSRX_SYNC();
@@ -734,14 +744,21 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
   return ncon;
 }
 
+// the 4 x (na + nb) Jacobian base rows of a contact: in the shared-memory pool, or (overflow) in the env's spill row
+__device__ __forceinline__ float* brow(float* sm, const float* cr) {
+  const int off = __float_as_int(cr[cf::BOFF]);
+  return off >= 0 ? sm + ar::BROW + off : reinterpret_cast<float* const*>(sm + ar::PTRS)[3] + (-off - 1);
+}
+
 // UB[c][p] = B[c][p][:] . x over the contact's dof columns (x: nv-vector in shared memory)
 __device__ __noinline__ void mul_B(float* sm, int lane, int ncon, const float* x) {
 #pragma unroll 1
   for (int t = lane; t < ncon * 4; t += 32) {
     const int c = t >> 2;
-    const int cols = __float_as_int(sm[ar::CON + c * ar::CSTRIDE + cf::COLS]);
+    const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    const int cols = __float_as_int(cr[cf::COLS]);
     const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
-    const float* Bp = sm + ar::BROW + t * NCOL;
+    const float* Bp = brow(sm, cr) + (t & 3) * (na + nb);
     float s = 0.f;
 #pragma unroll 1
     for (int i = 0; i < na; i++) s += Bp[i] * x[a0 + i];
@@ -858,10 +875,12 @@ __device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float
   for (int t = lane; t < ncon * NCOL; t += 32) {
     const int c = t / NCOL, col = t - c * NCOL;
     const float* cr = sm + ar::CON + c * ar::CSTRIDE;
+    const float* ctm = sm + ar::CTMP + c * ar::CTSTRIDE;
     const int cols = __float_as_int(cr[cf::COLS]);
     const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
-    float* B = sm + ar::BROW + c * 4 * NCOL;
-    if (col >= na + nb) { B[col] = B[NCOL + col] = B[2 * NCOL + col] = B[3 * NCOL + col] = 0.f; continue; }
+    const int w = na + nb;  // row width of this contact
+    if (col >= w) continue;
+    float* B = brow(sm, cr);
     const int d = col < na ? a0 + col : b0 + col - na;
     const int bodies = __float_as_int(cr[cf::BODIES]);
     const int b1 = bodies & 0xff, b2 = (bodies >> 8) & 0xff;
@@ -870,20 +889,20 @@ __device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float
     const float* cd = sm + ar::CDOF + d * 6;
     if (in2) {
       const float* sc = sm + ar::SCOM + dm->body_treeid[b2] * 3;
-      float off[3] = {cr[0] - sc[0], cr[1] - sc[1], cr[2] - sc[2]}, x[3];
+      float off[3] = {ctm[ct::POS] - sc[0], ctm[ct::POS + 1] - sc[1], ctm[ct::POS + 2] - sc[2]}, x[3];
       cross3(x, cd, off);
       for (int i = 0; i < 3; i++) { dp[i] = cd[3 + i] + x[i]; dr[i] = cd[i]; }
     }
     if (in1) {
       const float* sc = sm + ar::SCOM + dm->body_treeid[b1] * 3;
-      float off[3] = {cr[0] - sc[0], cr[1] - sc[1], cr[2] - sc[2]}, x[3];
+      float off[3] = {ctm[ct::POS] - sc[0], ctm[ct::POS + 1] - sc[1], ctm[ct::POS + 2] - sc[2]}, x[3];
       cross3(x, cd, off);
       for (int i = 0; i < 3; i++) { dp[i] -= cd[3 + i] + x[i]; dr[i] -= cd[i]; }
     }
-    B[col] = dot3(cr + cf::FRAME, dp);
-    B[NCOL + col] = dot3(cr + cf::FRAME + 3, dp);
-    B[2 * NCOL + col] = dot3(cr + cf::FRAME + 6, dp);
-    B[3 * NCOL + col] = dot3(cr + cf::FRAME, dr);
+    B[col] = dot3(ctm + ct::FRAME, dp);
+    B[w + col] = dot3(ctm + ct::FRAME + 3, dp);
+    B[2 * w + col] = dot3(ctm + ct::FRAME + 6, dp);
+    B[3 * w + col] = dot3(ctm + ct::FRAME, dr);
   }
   RSRX_SYNC();
   {  // does any contact couple two kinematic trees?  (selects the Cholesky block structure of H)
@@ -893,7 +912,7 @@ __device__ __noinline__ int make_constraint(const DModel* __restrict__ dm, float
       cpl |= ((cols >> 8) & 0xff) != 0 && ((cols >> 24) & 0xff) != 0;
     }
     const bool any = __any_sync(0xffffffffu, cpl);
-    if (lane == 0) reinterpret_cast<int*>(sm + ar::PTRS)[6] = any ? 1 : 0;
+    if (lane == 0) reinterpret_cast<int*>(sm + ar::PTRS)[ar::FLAGS] = any ? 1 : 0;
   }
   // --- contact rows: aref (D lives in the contact record)
   mul_B(sm, lane, ncon, sm + ar::QVEL);  // base velocities u_p = B_p . qvel -> UB
@@ -1069,20 +1088,26 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
   const int nv = dm->nv, nrow = nsr + 6 * ncon;
   float cost = 0.f;
   bool changed = false;
+  unsigned* actw = reinterpret_cast<unsigned*>(sm + ar::E_ACT);  // active flags, one bit per row
 #pragma unroll 1
-  for (int r = lane; r < nrow; r += 32) {
-    const float ja = sm[ar::E_JAREF + r], D = row_D(sm, r, nsr);
-    const RowShape s = row_shape(sm, r, nsr);
-    const bool quad = ja > s.lo && ja < s.hi;
-    const bool below = ja <= s.lo;
-    const float f = quad ? -D * ja : (below ? s.fl : -s.fl);
-    cost += quad ? 0.5f * D * ja * ja : s.fl * (-0.5f * s.rf + (below ? -ja : ja));
-    const float actf = quad ? 1.f : 0.f;
-    changed |= sm[ar::E_ACT + r] != actf;
-    sm[ar::E_ACT + r] = actf;
-    sm[ar::E_JV + r] = f;  // E_JV doubles as the force array between line searches
+  for (int base = 0; base < nrow; base += 32) {
+    const int r = base + lane;
+    bool quad = false;
+    if (r < nrow) {
+      const float ja = sm[ar::E_JAREF + r], D = row_D(sm, r, nsr);
+      const RowShape s = row_shape(sm, r, nsr);
+      quad = ja > s.lo && ja < s.hi;
+      const bool below = ja <= s.lo;
+      const float f = quad ? -D * ja : (below ? s.fl : -s.fl);
+      cost += quad ? 0.5f * D * ja * ja : s.fl * (-0.5f * s.rf + (below ? -ja : ja));
+      sm[ar::E_JV + r] = f;  // E_JV doubles as the force array between line searches
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, quad);
+    changed |= actw[base >> 5] != word;
+    RSRX_SYNC();
+    if (lane == 0) actw[base >> 5] = word;
   }
-  *changed_out = __any_sync(0xffffffffu, changed);
+  *changed_out = changed;
   RSRX_SYNC();
   // contact forces in base-row space: g0 = sum f, g_{1+k} = mu_k (f_{2k} - f_{2k+1})
 #pragma unroll 1
@@ -1114,9 +1139,10 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
       const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
       const int col = (d >= a0 && d < a0 + na) ? d - a0 : ((d >= b0 && d < b0 + nb) ? na + d - b0 : -1);
       if (col < 0) continue;
-      const float* B = sm + ar::BROW + c * 4 * NCOL + col;
+      const float* B = brow(sm, sm + ar::CON + c * ar::CSTRIDE) + col;
       const float* g = sm + ar::UB + c * 4;
-      s += B[0] * g[0] + B[NCOL] * g[1] + B[2 * NCOL] * g[2] + B[3 * NCOL] * g[3];
+      const int w = na + nb;
+      s += B[0] * g[0] + B[w] * g[1] + B[2 * w] * g[2] + B[3 * w] * g[3];
     }
     sm[ar::V_QFRCC + d] = s;
     gpart = (sm[ar::V_MA + d] - sm[ar::V_SMOOTH + d]) * (sm[ar::V_QACC + d] - sm[ar::V_QACCS + d]);
@@ -1132,7 +1158,7 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
 // the block-permuted dof order), Cholesky, Mgrad = H^-1 grad
 __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, float* sm, int lane, int nsr, int ncon,
                                              bool reuse_factor) {
-  const bool tree_blocks = reinterpret_cast<const int*>(sm + ar::PTRS)[6] == 0;  // set by make_constraint
+  const bool tree_blocks = reinterpret_cast<const int*>(sm + ar::PTRS)[ar::FLAGS] == 0;  // set by make_constraint
   // (grad itself is formed by the caller, which tests convergence on it before asking for the Newton direction)
   if (reuse_factor) {  // same active set as the previous iteration: H, hence its factor in ar::HH, is unchanged
     RSRX_SYNC();
@@ -1145,12 +1171,15 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
 #pragma unroll 1
   for (int c = lane; c < ncon; c += 32) {
     const float* cr = sm + ar::CON + c * ar::CSTRIDE;
-    const float* act = sm + ar::E_ACT + nsr + c * 6;
+    const unsigned* actw = reinterpret_cast<const unsigned*>(sm + ar::E_ACT);
+    const int r0 = nsr + c * 6;
     const float D = cr[cf::D];
     float w00 = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const float wp = act[2 * k] * D, wm = act[2 * k + 1] * D, mu = cr[cf::MU + k];
+      const int rp = r0 + 2 * k, rm = rp + 1;
+      const float wp = ((actw[rp >> 5] >> (rp & 31)) & 1u) ? D : 0.f, wm = ((actw[rm >> 5] >> (rm & 31)) & 1u) ? D : 0.f;
+      const float mu = cr[cf::MU + k];
       w00 += wp + wm;
       sm[ar::CW + c * 8 + 1 + k] = (wp - wm) * mu;
       sm[ar::CW + c * 8 + 4 + k] = (wp + wm) * mu * mu;
@@ -1158,15 +1187,15 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
     sm[ar::CW + c * 8] = w00;
   }
   RSRX_SYNC();
-  if (lane < nsr && sm[ar::E_ACT + lane] != 0.f) {  // sparse rows touch one diagonal entry (equality: a 2x2 block)
+  if (lane < nsr && ((reinterpret_cast<const unsigned*>(sm + ar::E_ACT)[0] >> lane) & 1u)) {  // sparse rows touch one diagonal entry (equality: a 2x2 block)
     const int a = reinterpret_cast<const int*>(sm + ar::SR_DOFA)[lane], b = reinterpret_cast<const int*>(sm + ar::SR_DOFB)[lane];
     const float ca = sm[ar::SR_CA + lane], cb = sm[ar::SR_CB + lane], D = sm[ar::E_DS + lane];
     const int pa = dm->pos_of_dof[a];
-    atomicAdd(sm + ar::HH + pa * LD + pa, ca * D * ca);
+    atomicAdd(sm + ar::HH + tri(pa) + pa, ca * D * ca);
     if (b >= 0) {
       const int pb = dm->pos_of_dof[b];
-      atomicAdd(sm + ar::HH + pb * LD + pb, cb * D * cb);
-      atomicAdd(sm + ar::HH + max(pa, pb) * LD + min(pa, pb), ca * D * cb);
+      atomicAdd(sm + ar::HH + tri(pb) + pb, cb * D * cb);
+      atomicAdd(sm + ar::HH + tri(max(pa, pb)) + min(pa, pb), ca * D * cb);
     }
   }
   RSRX_SYNC();
@@ -1181,19 +1210,20 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
       const int ci = (i >= a0 && i < a0 + na) ? i - a0 : ((i >= b0 && i < b0 + nb) ? na + i - b0 : -1);
       const int cj = (j >= a0 && j < a0 + na) ? j - a0 : ((j >= b0 && j < b0 + nb) ? na + j - b0 : -1);
       if (ci < 0 || cj < 0) continue;
-      const float* B = sm + ar::BROW + c * 4 * NCOL;
+      const float* B = brow(sm, sm + ar::CON + c * ar::CSTRIDE);
       const float* W = sm + ar::CW + c * 8;
+      const int w = na + nb;
       const float b0i = B[ci], b0j = B[cj];
       float acc = W[0] * b0i * b0j;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const float bki = B[(1 + k) * NCOL + ci], bkj = B[(1 + k) * NCOL + cj];
+        const float bki = B[(1 + k) * w + ci], bkj = B[(1 + k) * w + cj];
         acc += W[1 + k] * (b0i * bkj + bki * b0j) + W[4 + k] * bki * bkj;
       }
       h += acc;
     }
     const int pi = dm->pos_of_dof[i], pj = dm->pos_of_dof[j];
-    sm[ar::HH + max(pi, pj) * LD + min(pi, pj)] += h;
+    sm[ar::HH + tri(max(pi, pj)) + min(pi, pj)] += h;
   }
   RSRX_SYNC();
   warp_chol_factor(dm, sm, lane, tree_blocks);
@@ -1438,9 +1468,6 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
 #endif
 #ifndef RSRX_BAR_GROUPS
 #define RSRX_BAR_GROUPS 1
-#endif
-#ifndef RSRX_WPB
-#define RSRX_WPB 14
 #endif
 constexpr int kPhaseBarriers = __builtin_popcount(RSRX_SYNC_MASK & 0x3f);
 template <bool SYNC>
