@@ -26,6 +26,7 @@ struct rsrx_model {
 
 // Launch shape for N envs: one CTA per SM per round, the rounds as evenly filled as possible.  8192 envs on 148 SMs:
 // 4 rounds of 14 envs per CTA; 1024 envs: one round of 147 CTAs x 7 envs instead of 74 CTAs x 14 on half the SMs.
+constexpr int kSmallW = WPB < 14 ? WPB : 14;  // CTAs of up to 14 warps use the 128-register instantiation of step_kernel
 struct LaunchCfg { int grid, block; size_t smem; };
 static LaunchCfg launch_cfg(const rsrx_model* m, int N) {
   const int per_round = m->num_sms * WPB;
@@ -342,16 +343,18 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
       max_smem = 227 * 1024;
     int stride = max_smem / (int)sizeof(float) / WPB;
     int pool = stride - ar::FIXED;
-    if (const char* f = getenv("RSRX_POOL_FLOATS")) pool = atoi(f);  // tests: a small pool forces the spill path
     if (pool > MAXC * 4 * NCOL) pool = MAXC * 4 * NCOL;
     if (pool < ar::MIN_POOL) { delete m; return fail("rsrx_model_create: not enough shared memory per block for the arena"); }
-    m->host.pool_floats = pool;
     m->host.arena_stride = ar::FIXED + pool;
+    // tests: RSRX_POOL_LIMIT caps what contacts may allocate in the pool (0 = every contact's rows go to the spill row)
+    if (const char* f = getenv("RSRX_POOL_LIMIT")) pool = std::min(pool, std::max(0, atoi(f)));
+    m->host.pool_floats = pool;
     m->smem_bytes = WPB * m->host.arena_stride * (int)sizeof(float);
   }
   cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(step_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(step_kernel<kSmallW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallW * m->host.arena_stride * (int)sizeof(float));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
   if (e != cudaSuccess) {
@@ -428,7 +431,8 @@ extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const fl
   if (check_state(st)) return 1;
   if (ensure_spill(m, N)) return 1;
   const LaunchCfg lc = launch_cfg(m, N);
-  step_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
+  if (lc.block <= 32 * kSmallW) step_kernel<kSmallW><<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
+  else step_kernel<WPB><<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -444,7 +448,8 @@ extern "C" int rsrx_env_step_host(const rsrx_model* m, int N, rsrx_state st, con
   CUDA_OK(cudaMemcpyAsync(action_staging, host_action, sizeof(float) * (size_t)N * m->host.nu, cudaMemcpyHostToDevice, s));
   if (ensure_spill(m, N)) return 1;
   const LaunchCfg lc = launch_cfg(m, N);
-  step_kernel<<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
+  if (lc.block <= 32 * kSmallW) step_kernel<kSmallW><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
+  else step_kernel<WPB><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
   if (host_obs) CUDA_OK(cudaMemcpyAsync(host_obs, st.obs, sizeof(float) * (size_t)N * L.obs_stride, cudaMemcpyDeviceToHost, s));
   if (host_reward) CUDA_OK(cudaMemcpyAsync(host_reward, st.reward, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));

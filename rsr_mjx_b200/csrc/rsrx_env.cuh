@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
 }
 
 // ----------------------------------------------------------------- step kernel
-__global__ void __launch_bounds__(32 * WPB) step_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ action,
+// MAXW: the most warps a CTA of this instantiation is launched with.  Up to 14 the register file allows 128 registers
+// per thread; the 19-warp shape (3 rounds at 8192 envs) has to live with 96.
+template <int MAXW>
+__global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ action,
                                                  PerEnv pe, StatePtrs st) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;

@@ -321,3 +321,27 @@ def test_step_host_equals_step():
         env2.step_host(s2, torch.zeros(255, 5))
     with pytest.raises(ValueError):
         env2.step_host(s2, torch.zeros(256, 5), host_obs=torch.zeros(256, 3))
+
+
+@pytest.mark.parametrize("limit", ["0", "120"])
+def test_jacobian_row_spill_path_is_bitwise_identical(limit, monkeypatch):
+    """The Jacobian base rows of a contact live in a shared-memory pool sized for the common case; what does not fit
+    goes to a global-memory spill row.  RSRX_POOL_LIMIT forces every (0) or most (120 floats) of the
+    rows through the spill path: same arithmetic, so the trajectories must be bit-identical."""
+    N = 512
+    env, keys, ic = _mk("sf", N, seed=21)
+    monkeypatch.setenv("RSRX_POOL_LIMIT", limit)
+    env_spill = AirbotPlayBase("sf", num_envs=N, episode_length=1200)
+    monkeypatch.delenv("RSRX_POOL_LIMIT")
+    s1, s2 = env.reset_from(*ic), env_spill.reset_from(*ic)
+    acts = torch.rand(25, N, 5, device="cuda", generator=torch.Generator("cuda").manual_seed(3)) * 2 - 1
+    for t in range(acts.shape[0]):
+        env.step(s1, acts[t])
+        env_spill.step(s2, acts[t])
+    torch.cuda.synchronize()
+    for k in ("data", "obs", "reward", "done", "info", "status"):
+        assert torch.equal(s1._buf[k], s2._buf[k]), k
+    d1 = env.physics_step_debug(s1._buf["data"].clone())
+    d2 = env_spill.physics_step_debug(s2._buf["data"].clone())
+    assert torch.equal(d1, d2)
+    assert float(d1[:, 480].max()) >= 8  # contacts are present (arm / cube / target on the table)
