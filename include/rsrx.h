@@ -17,8 +17,10 @@
  *    unless the name ends in `_host`.
  *  - functions return 0 on success, non-zero on error; rsrx_last_error() gives
  *    the thread-local message.  Nothing throws across the ABI.  Launches are
- *    asynchronous on `stream`; no allocation or host sync happens in
- *    rsrx_env_reset / rsrx_env_step.
+ *    asynchronous on `stream`; no host sync happens in rsrx_env_reset /
+ *    rsrx_env_step, and the only allocation is the model's scratch buffer
+ *    (5.4 KB per env), grown the first time a call sees a larger N: call reset
+ *    once for a batch size before capturing steps in a CUDA graph.
  *  - batched natively: one call advances N environments; it *is* the
  *    AutoReset(Episode(Vmap|DomainRandomizationVmap(env))) stack.
  */
