@@ -1499,7 +1499,8 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
 // phase boundaries lets one fetch serve all of them.  RSRX_SYNC_MASK selects the boundaries (bit 0: substep
 // start, 1: collision, 2: make_constraint, 3: velocity/forces, 4: solve, 5: integrate).
 #ifndef RSRX_SYNC_MASK
-#define RSRX_SYNC_MASK 1  // measured: the substep-start barrier alone is best (6.30 ms vs 6.46-6.49 with more)
+#define RSRX_SYNC_MASK 33  // substep start + after the solver (where the warps are spread the most, so that the integration
+                          // phase streams aligned too): 2.37 ms vs 2.51 with the substep-start barrier alone at 19 warps per CTA
 #endif
 #ifndef RSRX_BAR_GROUPS
 #define RSRX_BAR_GROUPS 1
