@@ -341,7 +341,7 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
       m->num_sms = 148;
     if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || max_smem <= 0)
       max_smem = 227 * 1024;
-    int stride = max_smem / (int)sizeof(float) / WPB;
+    int stride = (max_smem / (int)sizeof(float) / WPB) & ~3;  // 16-byte multiples: the arena starts with 8-byte pointers
     int pool = stride - ar::FIXED;
     if (pool > MAXC * 4 * NCOL) pool = MAXC * 4 * NCOL;
     if (pool < ar::MIN_POOL) { delete m; return fail("rsrx_model_create: not enough shared memory per block for the arena"); }
