@@ -345,3 +345,23 @@ def test_jacobian_row_spill_path_is_bitwise_identical(limit, monkeypatch):
     d2 = env_spill.physics_step_debug(s2._buf["data"].clone())
     assert torch.equal(d1, d2)
     assert float(d1[:, 480].max()) >= 8  # contacts are present (arm / cube / target on the table)
+
+
+@pytest.mark.parametrize("N", [1, 19, 20, 1030, 2812, 2813])
+def test_odd_batch_sizes_and_launch_shapes(N):
+    """launch_cfg picks the envs per CTA from N (1 .. 19, one or several rounds, partially filled last CTA with shadow
+    warps at the phase barriers): env i must come out the same whatever batch it runs in"""
+    env, keys, ic = _mk("sf", N, seed=13)
+    ref_env = AirbotPlayBase("sf", num_envs=1, episode_length=1200)
+    acts = torch.rand(6, N, 5, device="cuda", generator=torch.Generator("cuda").manual_seed(N)) * 2 - 1
+    s = env.reset_from(*ic)
+    for t in range(acts.shape[0]):
+        env.step(s, acts[t])
+    torch.cuda.synchronize()
+    assert torch.isfinite(s._buf["data"]).all() and int((s._buf["status"] & 3).max()) == 0
+    for i in sorted({0, N // 2, N - 1}):
+        r = ref_env.reset_from(*[x[i:i + 1] for x in ic])
+        for t in range(acts.shape[0]):
+            ref_env.step(r, acts[t, i:i + 1].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(r._buf["data"][0], s._buf["data"][i]) and torch.equal(r._buf["obs"][0], s._buf["obs"][i]), i
