@@ -16,7 +16,10 @@ constexpr int NU = RSRX_MAXU;     // 8
 constexpr int NG = RSRX_MAXGEOM;  // 32
 constexpr int NS = RSRX_MAXSITE;  // 4
 constexpr int NP = RSRX_MAXPAIR;  // 64
-constexpr int MAXC = 24;          // active-contact cap per env (overflow -> status bit)
+#ifndef RSRX_MAXC
+#define RSRX_MAXC 24
+#endif
+constexpr int MAXC = RSRX_MAXC;          // active-contact cap per env (overflow -> status bit)
 constexpr int MAXSR = 20;         // sparse rows: equality + dof friction + joint limits
 constexpr int MAXROW = MAXSR + 6 * MAXC;
 constexpr int LD = NV + 1;        // padded leading dimension of the dense nv x nv matrices
