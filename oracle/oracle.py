@@ -1,7 +1,7 @@
 """ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE — see rsr_oracle.c).
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
-reference legs import this module.  PARITY UNPINNED (no runnable MJX here).
+Only tests/ (and the parity / golden-vector scripts under tools/ that serve them), __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs import this module.  PARITY UNPINNED (no runnable MJX here).
 """
 from __future__ import annotations
 

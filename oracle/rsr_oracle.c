@@ -1,7 +1,8 @@
 /* rsr_oracle.c — CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
- * reference legs may load this.  The product path (rsr_mjx_b200/ + librsrx.so)
+ * Only tests/ (and the parity / golden-vector scripts under tools/ that serve them:
+ * make_golden, dev_gpu_check, solver_stats), __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this.  The product path (rsr_mjx_b200/ + librsrx.so)
  * never calls into it.
  *
  * PARITY UNPINNED: the arithmetic of the reference's hot path lives in
