@@ -1180,31 +1180,33 @@ __device__ __noinline__ float update_constraint(const DModel* __restrict__ dm, f
   return cost;
 }
 
-// entry (i, j) of sum_c J_c^T diag(D active) J_c in the 4 x 4 base-row Gram form (weights in CW)
+// H += sum_c J_c^T diag(D active) J_c, contact by contact: the lanes take the w (w + 1) / 2 column pairs of the
+// contact's w = na + nb Jacobian columns (packed lower-triangle order, DModel::tri_i / tri_j) and add the 4 x 4
+// base-row Gram form of the pair to its H entry.  Every pair is a structural non-zero; no (entry, contact) misses.
 template <bool SPILL>
-__device__ __forceinline__ float contact_hessian(float* sm, int i, int j, int ncon) {
-  float h = 0.f;
+__device__ __forceinline__ void contact_hessian_scatter(const DModel* __restrict__ dm, float* sm, int lane, int ncon) {
 #pragma unroll 1
   for (int c = 0; c < ncon; c++) {
     const float* cr = sm + ar::CON + c * ar::CSTRIDE;
     const int cols = __float_as_int(cr[cf::COLS]);
     const int a0 = cols & 0xff, na = (cols >> 8) & 0xff, b0 = (cols >> 16) & 0xff, nb = (cols >> 24) & 0xff;
-    const int ci = (i >= a0 && i < a0 + na) ? i - a0 : ((i >= b0 && i < b0 + nb) ? na + i - b0 : -1);
-    const int cj = (j >= a0 && j < a0 + na) ? j - a0 : ((j >= b0 && j < b0 + nb) ? na + j - b0 : -1);
-    if (ci < 0 || cj < 0) continue;
+    const int w = na + nb, npair = (w * (w + 1)) >> 1;
     const float* B = brow<SPILL>(sm, cr);
     const float* W = sm + ar::CW + c * 8;
-    const int w = na + nb;
-    const float b0i = B[ci], b0j = B[cj];
-    float acc = W[0] * b0i * b0j;
+#pragma unroll 1
+    for (int idx = lane; idx < npair; idx += 32) {
+      const int ci = dm->tri_i[idx], cj = dm->tri_j[idx];
+      const float b0i = B[ci], b0j = B[cj];
+      float acc = W[0] * b0i * b0j;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const float bki = B[(1 + k) * w + ci], bkj = B[(1 + k) * w + cj];
-      acc += W[1 + k] * (b0i * bkj + bki * b0j) + W[4 + k] * bki * bkj;
+      for (int k = 0; k < 3; k++) {
+        const float bki = B[(1 + k) * w + ci], bkj = B[(1 + k) * w + cj];
+        acc += W[1 + k] * (b0i * bkj + bki * b0j) + W[4 + k] * bki * bkj;
+      }
+      const int pi = dm->pos_of_dof[ci < na ? a0 + ci : b0 + ci - na], pj = dm->pos_of_dof[cj < na ? a0 + cj : b0 + cj - na];
+      atomicAdd(sm + ar::HH + tri(max(pi, pj)) + min(pi, pj), acc);
     }
-    h += acc;
   }
-  return h;
 }
 
 // solver.py::_update_gradient (Newton): grad, H = M + J^T diag(D*active) J (in
@@ -1253,13 +1255,8 @@ __device__ __noinline__ void update_gradient(const DModel* __restrict__ dm, floa
     }
   }
   RSRX_SYNC();
-#pragma unroll 1
-  for (int e = lane; e < dm->nhent; e += 32) {  // structurally non-zero entries only
-    const int i = dm->hent_i[e], j = dm->hent_j[e];  // dofs, i >= j
-    const float h = spilled ? contact_hessian<true>(sm, i, j, ncon) : contact_hessian<false>(sm, i, j, ncon);
-    const int pi = dm->pos_of_dof[i], pj = dm->pos_of_dof[j];
-    sm[ar::HH + tri(max(pi, pj)) + min(pi, pj)] += h;
-  }
+  if (spilled) contact_hessian_scatter<true>(dm, sm, lane, ncon);
+  else contact_hessian_scatter<false>(dm, sm, lane, ncon);
   RSRX_SYNC();
   warp_chol_factor(dm, sm, lane, tree_blocks);
   warp_chol_solve(dm, sm, sm + ar::V_MGRAD, lane, tree_blocks);
