@@ -148,6 +148,7 @@ static int build_dmodel(const rsrx_model_blob& b, const rsrx_env_cfg& c, DModel&
     if (hi >= 0) {
       d.tree_dofadr[t] = lo; d.tree_dofnum[t] = hi - lo + 1;
       for (int v = lo; v <= hi; v++) if (d.body_treeid[b.dof_bodyid[v]] != t) return fail("dofs of a kinematic tree must be contiguous");
+      for (int v = lo; v <= hi; v++) { d.dof_tree_lo[v] = lo; d.dof_tree_hi[v] = hi; }
     }
   }
   for (int j = 0; j < b.njnt; j++) {

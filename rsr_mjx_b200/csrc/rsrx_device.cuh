@@ -47,6 +47,7 @@ struct DModel {
       body_depth[NB], body_static[NB], body_subtree_end[NB];
   uint32_t body_dofmask[NB];  // dofs on the path from the body to the world
   int body_treeid[NB], ntree, tree_dofadr[MAXTREE_], tree_dofnum[MAXTREE_];
+  int dof_tree_lo[NV], dof_tree_hi[NV];  // dof range of the kinematic tree a dof belongs to (M is block diagonal over trees)
   float body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_iquat[NB][4], body_mass[NB], body_inertia[NB][3],
       body_invweight0[NB];
   float static_xpos[NB][3], static_xquat[NB][4];

@@ -1073,8 +1073,10 @@ __device__ __noinline__ void mul_M(const DModel* __restrict__ dm, const float* s
   const int nv = dm->nv;
   if (lane < nv) {
     float s = 0.f;
+    // M couples only dofs of the same kinematic tree: the other entries are exact zeros and are skipped
+    const int j1 = dm->dof_tree_hi[lane];
 #pragma unroll 4
-    for (int j = 0; j < nv; j++) {
+    for (int j = dm->dof_tree_lo[lane]; j <= j1; j++) {
       const int hi = lane > j ? lane : j, lo = lane > j ? j : lane;
       s += sm[ar::MM + ((hi * (hi + 1)) >> 1) + lo] * x[j];
     }
