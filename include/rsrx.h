@@ -165,6 +165,12 @@ int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, floa
  * pos(4x3) normal(3), a slot with dist >= 0 holds no contact.  Device pointers. */
 int rsrx_debug_narrowphase(const float* pairs, int n, int plane, float* out, void* stream);
 
+/* Minibatch gather for the trainers: dst[k][r][:] = src[k][idx[r]][:] for nfields (<= 8) row-major float tensors with
+ * row_floats[k] floats per row, one launch.  src / dst / row_floats are HOST arrays (of device pointers / sizes), idx is a
+ * device array of nrows int64 row indices. */
+int rsrx_gather_rows(const float* const* src, float* const* dst, const int32_t* row_floats, int nfields,
+                     const int64_t* idx, int nrows, void* stream);
+
 /* MLP backward helper for the trainers' networks: grad_z = grad_y * act'(z) (activation 0 none, 1 silu, 2 relu;
  * grad_z may be NULL when activation is 0) and grad_bias[c] = sum over rows of grad_z[r][c], one deterministic launch.
  * Row-major [rows][cols] device arrays; workspace: rsrx_act_bias_backward_workspace(rows, cols) floats whose FIRST

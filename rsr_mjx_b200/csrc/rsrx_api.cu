@@ -498,6 +498,21 @@ extern "C" int rsrx_debug_narrowphase(const float* pairs, int n, int plane, floa
   return 0;
 }
 
+extern "C" int rsrx_gather_rows(const float* const* src, float* const* dst, const int32_t* row_floats, int nfields,
+                                const int64_t* idx, int nrows, void* stream) {
+  if (!src || !dst || !row_floats || !idx) return fail("rsrx_gather_rows: null argument");
+  if (nfields <= 0 || nfields > gather::MAXF || nrows <= 0) return fail("rsrx_gather_rows: 1..8 fields, nrows > 0");
+  gather::Fields f;
+  f.n = nfields;
+  for (int k = 0; k < nfields; k++) {
+    if (!src[k] || !dst[k] || row_floats[k] <= 0) return fail("rsrx_gather_rows: bad field");
+    f.src[k] = src[k]; f.dst[k] = dst[k]; f.width[k] = row_floats[k];
+  }
+  return gather::launch(f, reinterpret_cast<const long long*>(idx), nrows, (cudaStream_t)stream)
+             ? fail(std::string("rsrx_gather_rows: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+
 extern "C" size_t rsrx_act_bias_backward_workspace(int rows, int cols) { return mlp::workspace_floats(rows, cols); }
 
 extern "C" int rsrx_act_bias_backward(const float* grad_y, const float* z, int rows, int cols, int activation, float* grad_z,

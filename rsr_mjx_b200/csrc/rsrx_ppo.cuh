@@ -218,3 +218,34 @@ inline int launch(const float* grad_y, const float* z, int rows, int cols, int a
 
 }  // namespace mlp
 }  // namespace rsrx
+
+// ---- minibatch gather: dst_f[r][:] = src_f[idx[r]][:] for up to 8 row-major float tensors in one launch ---------------
+namespace rsrx {
+namespace gather {
+
+constexpr int MAXF = 8;
+struct Fields {
+  const float* src[MAXF];
+  float* dst[MAXF];
+  int width[MAXF];  // floats per row
+  int n;
+};
+
+__global__ void __launch_bounds__(256) gather_kernel(Fields f, const long long* __restrict__ idx, int nrows) {
+  const int r = blockIdx.x;
+  if (r >= nrows) return;
+  const long long s = idx[r];
+  for (int k = 0; k < f.n; k++) {
+    const float* src = f.src[k] + (size_t)s * f.width[k];
+    float* dst = f.dst[k] + (size_t)r * f.width[k];
+    for (int i = threadIdx.x; i < f.width[k]; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+inline int launch(const Fields& f, const long long* idx, int nrows, cudaStream_t stream) {
+  gather_kernel<<<nrows, 256, 0, stream>>>(f, idx, nrows);
+  return cudaGetLastError() != cudaSuccess;
+}
+
+}  // namespace gather
+}  // namespace rsrx

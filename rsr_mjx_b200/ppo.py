@@ -540,10 +540,20 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             with torch.cuda.graph(collect_graph):
                 collect_body()
 
+    import ctypes as C
+    from . import _lib
+    _keys = list(static)
+    _nf = len(_keys)
+    _dst = (C.c_void_p * _nf)(*[static[k].data_ptr() for k in _keys])
+    _widths = (C.c_int32 * _nf)(*[static[k][0].numel() for k in _keys])
+
     def minibatch_step(batch, idx):
         nonlocal last_metrics
-        for k in static:
-            static[k].copy_(batch[k][idx])
+        # all seven fields of the minibatch in one gather launch (rows = sequences of T transitions)
+        src = (C.c_void_p * _nf)(*[batch[k].data_ptr() for k in _keys])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rsrx_gather_rows(src, _dst, _widths, _nf, idx.data_ptr(), mb,
+                                                   torch.cuda.current_stream(dev).cuda_stream), "rsrx_gather_rows")
         static_noise.normal_(generator=gen)
         if graph_bwd is not None:
             graph_bwd.replay()

@@ -218,3 +218,22 @@ def test_train_epochs_and_callbacks_follow_the_reference():
     assert [n for n, _ in seen] == [0, 2 * per_step, 4 * per_step] and saved == [2 * per_step, 4 * per_step]
     assert "training/sps" not in seen[0][1] and "eval/episode_reward" in seen[0][1]
     assert "training/sps" in seen[-1][1] and "eval/episode_reward_std" in seen[-1][1]
+
+
+def test_gather_rows_matches_torch_indexing():
+    import ctypes as C
+    g = torch.Generator("cuda").manual_seed(0)
+    srcs = [torch.randn(100, 10, 23, device="cuda", generator=g), torch.randn(100, 10, device="cuda", generator=g),
+            torch.randn(100, 10, 5, device="cuda", generator=g)]
+    idx = torch.randperm(100, device="cuda", generator=g)[10:47]
+    dsts = [torch.zeros(37, *s.shape[1:], device="cuda") for s in srcs]
+    n = len(srcs)
+    _lib.check(_lib.lib().rsrx_gather_rows((C.c_void_p * n)(*[s.data_ptr() for s in srcs]),
+                                           (C.c_void_p * n)(*[d.data_ptr() for d in dsts]),
+                                           (C.c_int32 * n)(*[s[0].numel() for s in srcs]), n, idx.data_ptr(), 37,
+                                           torch.cuda.current_stream().cuda_stream), "rsrx_gather_rows")
+    torch.cuda.synchronize()
+    for s, d in zip(srcs, dsts):
+        assert torch.equal(d, s[idx])
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.lib().rsrx_gather_rows(None, None, None, 1, idx.data_ptr(), 1, None), "rsrx_gather_rows")
