@@ -165,6 +165,12 @@ int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, floa
  * pos(4x3) normal(3), a slot with dist >= 0 holds no contact.  Device pointers. */
 int rsrx_debug_narrowphase(const float* pairs, int n, int plane, float* out, void* stream);
 
+/* Behaviour-policy head of the actor step (brax NormalTanhDistribution, min_std 0.001): logits [N][2A] (loc |
+ * pre-softplus scale) and noise [N][A] ~ N(0,1) give raw_action = loc + scale * noise, action = tanh(raw_action) and
+ * log_prob [N] of raw_action under the tanh-normal (NULL to skip).  Device float32 arrays, one launch. */
+int rsrx_tanh_normal_act(const float* logits, const float* noise, int N, int A, float* raw_action, float* action,
+                         float* log_prob, void* stream);
+
 /* Minibatch gather for the trainers: dst[k][r][:] = src[k][idx[r]][:] for nfields (<= 8) row-major float tensors with
  * row_floats[k] floats per row, one launch.  src / dst / row_floats are HOST arrays (of device pointers / sizes), idx is a
  * device array of nrows int64 row indices. */

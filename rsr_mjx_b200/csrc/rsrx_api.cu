@@ -498,6 +498,15 @@ extern "C" int rsrx_debug_narrowphase(const float* pairs, int n, int plane, floa
   return 0;
 }
 
+extern "C" int rsrx_tanh_normal_act(const float* logits, const float* noise, int N, int A, float* raw_action, float* action,
+                                    float* log_prob, void* stream) {
+  if (!logits || !noise || !raw_action || !action) return fail("rsrx_tanh_normal_act: null argument");
+  if (N <= 0 || A <= 0) return fail("rsrx_tanh_normal_act: bad sizes");
+  return ppo::launch_act(logits, noise, N, A, raw_action, action, log_prob, (cudaStream_t)stream)
+             ? fail(std::string("rsrx_tanh_normal_act: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+
 extern "C" int rsrx_gather_rows(const float* const* src, float* const* dst, const int32_t* row_floats, int nfields,
                                 const int64_t* idx, int nrows, void* stream) {
   if (!src || !dst || !row_floats || !idx) return fail("rsrx_gather_rows: null argument");

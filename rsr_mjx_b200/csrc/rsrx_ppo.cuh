@@ -249,3 +249,35 @@ inline int launch(const Fields& f, const long long* idx, int nrows, cudaStream_t
 
 }  // namespace gather
 }  // namespace rsrx
+
+// ---- behaviour policy head: raw = loc + scale * noise, action = tanh(raw), log-prob of raw, one launch ------------------
+// (brax NormalTanhDistribution.sample_no_postprocessing / log_prob / postprocess; RSR/train.py:313 actor_step)
+namespace rsrx {
+namespace ppo {
+
+__global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ logits, const float* __restrict__ noise, int N, int A,
+                                                  float* __restrict__ raw, float* __restrict__ action,
+                                                  float* __restrict__ log_prob) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* lg = logits + (size_t)n * 2 * A;
+  float lp = 0.f;
+  for (int k = 0; k < A; k++) {
+    const float loc = lg[k], sc = softplus(lg[A + k]) + MIN_STD;
+    const float x = loc + sc * noise[(size_t)n * A + k];
+    const float z = (x - loc) / sc;
+    lp += -0.5f * z * z - 0.5f * LOG_2PI - logf(sc) - log_det_jac(x);
+    raw[(size_t)n * A + k] = x;
+    action[(size_t)n * A + k] = tanhf(x);
+  }
+  if (log_prob) log_prob[n] = lp;
+}
+
+inline int launch_act(const float* logits, const float* noise, int N, int A, float* raw, float* action, float* log_prob,
+                      cudaStream_t stream) {
+  act_kernel<<<(N + 255) / 256, 256, 0, stream>>>(logits, noise, N, A, raw, action, log_prob);
+  return cudaGetLastError() != cudaSuccess;
+}
+
+}  // namespace ppo
+}  // namespace rsrx

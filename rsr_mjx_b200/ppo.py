@@ -143,6 +143,25 @@ class NormalTanh:
     def mode(cls, logits):
         return torch.tanh(cls.params(logits)[0])
 
+    @staticmethod
+    def act(logits, noise, raw_out=None, action_out=None, log_prob_out=None):
+        """sample_no_postprocessing + postprocess + log_prob for the actor step in one CUDA launch
+        (`rsrx_tanh_normal_act`): returns (raw, action, log_prob); the `_out` tensors are written in place."""
+        from . import _lib
+        N, A2 = logits.shape
+        A = A2 // 2
+        raw = raw_out if raw_out is not None else torch.empty(N, A, device=logits.device)
+        action = action_out if action_out is not None else torch.empty(N, A, device=logits.device)
+        lp = log_prob_out if log_prob_out is not None else torch.empty(N, device=logits.device)
+        for t in (logits, noise, raw, action, lp):
+            if t.device.type != "cuda" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("NormalTanh.act needs contiguous float32 CUDA tensors")
+        with torch.cuda.device(logits.device):
+            _lib.check(_lib.lib().rsrx_tanh_normal_act(logits.data_ptr(), noise.data_ptr(), N, A, raw.data_ptr(), action.data_ptr(),
+                                                       lp.data_ptr(), torch.cuda.current_stream(logits.device).cuda_stream),
+                       "rsrx_tanh_normal_act")
+        return raw, action, lp
+
 
 # ---------------------------------------------------------------------- normaliser
 class RunningStatistics:
@@ -455,6 +474,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                 discount=(), truncation=()).items()}
 
     act_noise = torch.empty(n_unrolls, T, num_envs, act_size, device=dev)  # N(0,1) of the behaviour policy, per unroll step
+    action_buf = torch.empty(num_envs, act_size, device=dev)
 
     @torch.no_grad()
     def collect_body():
@@ -463,11 +483,9 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                 obs = state.obs
                 buf["observation"][u, t].copy_(obs)
                 logits = net.policy(normalize(obs))
-                loc, scale = NormalTanh.params(logits)
-                raw = loc + scale * act_noise[u, t]
-                buf["raw_action"][u, t].copy_(raw)
-                buf["log_prob"][u, t].copy_(NormalTanh.log_prob(logits, raw))
-                env.step(state, torch.tanh(raw))
+                # raw action, its log-prob (straight into the rollout buffers) and the tanh action: one launch
+                NormalTanh.act(logits, act_noise[u, t], buf["raw_action"][u, t], action_buf, buf["log_prob"][u, t])
+                env.step(state, action_buf)
                 buf["next_observation"][u, t].copy_(state.obs)
                 buf["reward"][u, t].copy_(state.reward)
                 buf["discount"][u, t].copy_(1 - state.done)

@@ -237,3 +237,17 @@ def test_gather_rows_matches_torch_indexing():
         assert torch.equal(d, s[idx])
     with pytest.raises(RuntimeError):
         _lib.check(_lib.lib().rsrx_gather_rows(None, None, None, 1, idx.data_ptr(), 1, None), "rsrx_gather_rows")
+
+
+def test_tanh_normal_act_matches_torch():
+    g = torch.Generator("cuda").manual_seed(5)
+    logits = torch.randn(1000, 10, device="cuda", generator=g) * 2
+    noise = torch.randn(1000, 5, device="cuda", generator=g)
+    raw, action, lp = ppo.NormalTanh.act(logits, noise)
+    loc, scale = ppo.NormalTanh.params(logits)
+    raw_ref = loc + scale * noise
+    torch.testing.assert_close(raw, raw_ref, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(action, torch.tanh(raw_ref), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(lp, ppo.NormalTanh.log_prob(logits, raw_ref), rtol=1e-5, atol=2e-5)
+    with pytest.raises(ValueError):
+        ppo.NormalTanh.act(logits.cpu(), noise.cpu())
