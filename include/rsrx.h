@@ -69,8 +69,12 @@ typedef struct rsrx_layout {
 
 /* per-env status bits written by the kernels (no host sync needed to keep going) */
 #define RSRX_STATUS_NONFINITE 1      /* a non-finite value reached qpos/qvel */
-#define RSRX_STATUS_CONTACT_OVERFLOW 2 /* more active contacts than the kernel's cap */
+#define RSRX_STATUS_CONTACT_OVERFLOW 2 /* contacts were dropped.  Cannot happen in reset / step / physics_step: an env
+                                        * whose substep has more active contacts than the fast kernel's arena holds
+                                        * (rsrx_max_contacts()) is re-run by the large-capacity kernel, which keeps every
+                                        * slot of every geom pair (4 x npair) like MJX.  Only the debug dump can set it. */
 #define RSRX_STATUS_SOLVER_CAP 4     /* Newton hit opt.iterations */
+#define RSRX_STATUS_CONTACT_REDO 8   /* informational: at least one step of this env went through the large-capacity kernel */
 
 /* State of N wrapped envs; every pointer is a caller-owned device buffer. */
 typedef struct rsrx_state {
@@ -141,7 +145,7 @@ int rsrx_physics_step(const rsrx_model* m, int N, float* data, int nsteps, const
  * qfrc_constraint[nv], ncon, nefc, niter, contact dist[cap], contact pos[cap*3].
  * `dump` is [N][rsrx_debug_stride()] floats. */
 int rsrx_debug_stride(void);
-int rsrx_max_contacts(void); /* active-contact cap per env (RSRX_STATUS_CONTACT_OVERFLOW beyond it) */
+int rsrx_max_contacts(void); /* active contacts per env the fast kernel holds (beyond it: RSRX_STATUS_CONTACT_REDO) */
 int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, const rsrx_per_env* per_env, float* dump,
                             void* stream);
 

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,c
 INFO_STRIDE = 20
 INFO = dict(TARGET=0, TARGET2=3, NEWPOS=6, SITE=8, OBJ=11, LAST_ACTION=14, XITA=15, TARGET_W=16, STEPS=17,
             TRUNCATION=18)
-STATUS_NONFINITE, STATUS_CONTACT_OVERFLOW, STATUS_SOLVER_CAP = 1, 2, 4
+STATUS_NONFINITE, STATUS_CONTACT_OVERFLOW, STATUS_SOLVER_CAP, STATUS_CONTACT_REDO = 1, 2, 4, 8
 OBS_STRIDE = 24
 METRICS_STRIDE = 8
 
@@ -40,11 +40,11 @@ class PerEnvC(C.Structure):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc-compile csrc/rsrx_api.cu -> librsrx.so (sm_100a, in-tree)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     srcs += [os.path.join(_HERE, "..", "include", f) for f in ("rsrx.h", "rsrx_model.h")]
     if (not force) and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "rsrx_api.cu")]
+    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "rsrx_api.cu"), os.path.join(CSRC, "rsrx_redo.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

@@ -10,6 +10,7 @@
 #include "rsrx_env.cuh"
 #include "rsrx_loss.cuh"
 #include "rsrx_ppo.cuh"
+#include "rsrx_redo.h"
 
 using namespace rsrx;
 
@@ -22,6 +23,12 @@ struct rsrx_model {
   // allocation reset/step ever make: the first call for a larger N, never inside a stream capture)
   float* spill = nullptr;
   int spill_envs = 0;
+  // envs whose substep exceeds the fast arena's contact capacity are re-run by the large-capacity instantiation
+  // (rsrx_redo.cu): its device model, launch shape, and the device list the fast kernels append to ([0] count,
+  // [1] ticket, [2..] env ids; spill_envs entries)
+  void* big_dev = nullptr;
+  int big_smem = 0, big_grid = 0;
+  int* redo = nullptr;
 };
 
 // Launch shape for N envs: one CTA per SM per round, the rounds as evenly filled as possible.  8192 envs on 148 SMs:
@@ -351,6 +358,18 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
     if (const char* f = getenv("RSRX_POOL_LIMIT")) pool = std::min(pool, std::max(0, atoi(f)));
     m->host.pool_floats = pool;
     m->smem_bytes = WPB * m->host.arena_stride * (int)sizeof(float);
+    // tests: RSRX_CONTACT_CAP lowers the number of active contacts the fast kernel accepts before it hands the env to
+    // the large-capacity kernel (0 = every env-step with a contact goes there)
+    m->host.contact_cap = MAXC;
+    if (const char* f = getenv("RSRX_CONTACT_CAP")) m->host.contact_cap = std::min(MAXC, std::max(0, atoi(f)));
+    const char* err = nullptr;
+    int big_maxc = 0;
+    if (rsrx_big_prepare(&m->host, sizeof(DModel), max_smem, &m->big_dev, &m->big_smem, &big_maxc, &err)) {
+      std::string msg = err ? err : "rsrx_big_prepare failed";
+      delete m;
+      return fail(msg);
+    }
+    m->big_grid = m->num_sms;
   }
   cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
@@ -371,7 +390,9 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
 extern "C" void rsrx_model_destroy(rsrx_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
+  if (m->big_dev) cudaFree(m->big_dev);
   if (m->spill) cudaFree(m->spill);
+  if (m->redo) cudaFree(m->redo);
   delete m;
 }
 
@@ -382,24 +403,48 @@ extern "C" int rsrx_model_layout(const rsrx_model* m, rsrx_layout* out) {
 }
 
 static PerEnv to_pe(const rsrx_model* m, const rsrx_per_env* p) {
-  PerEnv pe = {nullptr, nullptr, nullptr, nullptr, m->spill};
+  PerEnv pe = {nullptr, nullptr, nullptr, nullptr, m->spill, m->redo};
   if (p) { pe.geom_friction = p->geom_friction; pe.body_mass = p->body_mass; pe.dof_damping = p->dof_damping; pe.dof_frictionloss = p->dof_frictionloss; }
   return pe;
 }
-// make sure the spill buffer covers N envs
+// make sure the spill buffer and the redo list cover N envs (the only allocation the library makes after model
+// creation: the first call that sees a larger N, never inside a stream capture)
 static int ensure_spill(const rsrx_model* cm, int N) {
   rsrx_model* m = const_cast<rsrx_model*>(cm);
   if (N <= m->spill_envs) return 0;
   float* fresh = nullptr;
+  int* redo = nullptr;
   cudaError_t e = cudaMalloc(&fresh, sizeof(float) * (size_t)N * ar::SPILL_STRIDE);
+  if (e == cudaSuccess) e = cudaMalloc(&redo, sizeof(int) * ((size_t)N + 2));
+  if (e == cudaSuccess) e = cudaMemset(redo, 0, sizeof(int) * ((size_t)N + 2));
   if (e != cudaSuccess) {
+    if (fresh) cudaFree(fresh);
+    if (redo) cudaFree(redo);
     return fail(std::string("rsrx: cannot allocate the Jacobian spill buffer (call reset/step once for this batch size "
                             "before capturing a CUDA graph): ") + cudaGetErrorString(e));
   }
-  if (m->spill) { cudaDeviceSynchronize(); cudaFree(m->spill); }
+  if (m->spill) { cudaDeviceSynchronize(); cudaFree(m->spill); cudaFree(m->redo); }
   m->spill = fresh;
+  m->redo = redo;
   m->spill_envs = N;
   return 0;
+}
+// the large-capacity pass over whatever the fast kernel left on the redo list (normally nothing: ~3 us)
+static cudaError_t launch_redo(const rsrx_model* m, rsrx_redo_launch a, const rsrx_per_env* p, const rsrx_state* st, cudaStream_t s) {
+  a.geom_friction = p ? p->geom_friction : nullptr; a.body_mass = p ? p->body_mass : nullptr;
+  a.dof_damping = p ? p->dof_damping : nullptr; a.dof_frictionloss = p ? p->dof_frictionloss : nullptr;
+  a.redo = m->redo;
+  if (st) {
+    a.data = st->data; a.first_data = st->first_data; a.obs = st->obs; a.first_obs = st->first_obs; a.reward = st->reward;
+    a.done = st->done; a.info = st->info; a.metrics = st->metrics; a.status = st->status;
+  }
+  return rsrx_big_launch(m->big_dev, a, m->big_grid, m->big_smem, s);
+}
+static rsrx_redo_launch redo_args(int mode) {
+  rsrx_redo_launch a;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode;
+  return a;
 }
 static StatePtrs to_sp(const rsrx_state& s) {
   StatePtrs p;
@@ -422,6 +467,9 @@ extern "C" int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, con
   const LaunchCfg lc = launch_cfg(m, N);
   reset_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, qpos, qvel, ctrl, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
+  rsrx_redo_launch ra = redo_args(0);
+  ra.qpos = qpos; ra.qvel = qvel; ra.ctrl = ctrl;
+  CUDA_OK(launch_redo(m, ra, per_env, &st, (cudaStream_t)stream));
   return 0;
 }
 
@@ -435,6 +483,9 @@ extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const fl
   if (lc.block <= 32 * kSmallW) step_kernel<kSmallW><<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
   else step_kernel<WPB><<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
+  rsrx_redo_launch ra = redo_args(1);
+  ra.action = action;
+  CUDA_OK(launch_redo(m, ra, per_env, &st, (cudaStream_t)stream));
   return 0;
 }
 
@@ -452,6 +503,9 @@ extern "C" int rsrx_env_step_host(const rsrx_model* m, int N, rsrx_state st, con
   if (lc.block <= 32 * kSmallW) step_kernel<kSmallW><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
   else step_kernel<WPB><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
   CUDA_OK(cudaGetLastError());
+  rsrx_redo_launch ra = redo_args(1);
+  ra.action = action_staging;
+  CUDA_OK(launch_redo(m, ra, per_env, &st, s));
   if (host_obs) CUDA_OK(cudaMemcpyAsync(host_obs, st.obs, sizeof(float) * (size_t)N * L.obs_stride, cudaMemcpyDeviceToHost, s));
   if (host_reward) CUDA_OK(cudaMemcpyAsync(host_reward, st.reward, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
   if (host_done) CUDA_OK(cudaMemcpyAsync(host_done, st.done, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
@@ -466,6 +520,9 @@ extern "C" int rsrx_physics_step(const rsrx_model* m, int N, float* data, int ns
   const LaunchCfg lc = launch_cfg(m, N);
   physics_kernel<<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, data, nsteps, to_pe(m, per_env), status, nullptr);
   CUDA_OK(cudaGetLastError());
+  rsrx_redo_launch ra = redo_args(2);
+  ra.phys_data = data; ra.nsteps = nsteps; ra.phys_status = status;
+  CUDA_OK(launch_redo(m, ra, per_env, nullptr, (cudaStream_t)stream));
   return 0;
 }
 

@@ -6,7 +6,14 @@
 
 #include "../../include/rsrx.h"
 
-namespace rsrx {
+// The whole stepper is compiled twice into librsrx.so: as `rsrx` (RSRX_MAXC = 24 active contacts per env, the arena
+// that fits 19 envs into one SM's shared memory) and as `rsrx_big` (rsrx_redo.cu: RSRX_MAXC = 4 * RSRX_MAXPAIR, i.e. every
+// slot of every geom pair — it cannot overflow), which re-runs the rare env-steps the first one had to give up on.
+#ifndef RSRX_NS
+#define RSRX_NS rsrx
+#endif
+
+namespace RSRX_NS {
 
 constexpr int NB = RSRX_MAXBODY;  // 16
 constexpr int NJ = RSRX_MAXJNT;   // 12
@@ -91,6 +98,9 @@ struct DModel {
   rsrx_layout lay;
   // shared-memory arena: floats per env (ar::FIXED + pool_floats) and the size of the Jacobian-row pool at its end
   int arena_stride, pool_floats;
+  // an env-step that sees more than contact_cap (<= MAXC) active contacts is not committed but handed to the
+  // large-capacity kernel (RSRX_STATUS_CONTACT_REDO); MAXC unless a test lowers it (RSRX_CONTACT_CAP)
+  int contact_cap;
 };
 
 // ---- per-warp shared-memory arena (float words) --------------------------------
@@ -320,4 +330,4 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-}  // namespace rsrx
+}  // namespace RSRX_NS

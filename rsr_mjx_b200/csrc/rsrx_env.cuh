@@ -5,20 +5,23 @@
 #pragma once
 #include "rsrx_physics.cuh"
 
-namespace rsrx {
+namespace RSRX_NS {
 
 struct PerEnv {
   const float* geom_friction;
   const float* body_mass;
   const float* dof_damping;
   const float* dof_frictionloss;
-  float* spill;  // [N][ar::SPILL_STRIDE] library-owned overflow of the Jacobian-row pool
+  float* spill;  // [slots][ar::SPILL_STRIDE] library-owned overflow of the Jacobian-row pool
+  // redo list (library-owned): [0] = number of envs this launch could not finish within contact_cap, [1] = CTA ticket
+  // of the redo kernel, [2 + i] = env ids.  nullptr: no redo, the env only gets RSRX_STATUS_CONTACT_OVERFLOW.
+  int* redo;
 };
 
 // load the dynamic state of env `e` into the arena; per-env model arrays stay in global memory and
 // are reached through pointers (pre-offset to this env) kept at ar::PTRS
-__device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, int lane, int e, const float* __restrict__ row,
-                                      const PerEnv& pe) {
+__device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, int lane, int e, int spill_slot,
+                                      const float* __restrict__ row, const PerEnv& pe) {
   const rsrx_layout& L = dm->lay;
 #pragma unroll 1
   for (int i = lane; i < dm->nq; i += 32) sm[ar::QPOS + i] = row[L.qpos + i];
@@ -35,7 +38,7 @@ __device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, 
     ptrs[0] = pe.geom_friction ? pe.geom_friction + (size_t)e * dm->ngeom * 3 : nullptr;
     ptrs[1] = pe.body_mass ? pe.body_mass + (size_t)e * dm->nbody : nullptr;
     ptrs[2] = pe.dof_frictionloss ? pe.dof_frictionloss + (size_t)e * dm->nv : nullptr;
-    ptrs[3] = pe.spill + (size_t)e * ar::SPILL_STRIDE;
+    ptrs[3] = pe.spill + (size_t)spill_slot * ar::SPILL_STRIDE;
     reinterpret_cast<int*>(sm + ar::PTRS)[ar::FLAGS] = 1;
   }
   RSRX_SYNC();
@@ -85,6 +88,7 @@ __device__ void get_obs(const DModel* __restrict__ dm, float* sm, const float* i
   for (; n < OBS_STRIDE; n++) obs[n] = 0.f;
 }
 
+
 // Warps per CTA: one env per warp, warps are independent (only __syncwarp).  Single-warp CTAs all land on
 // the same SM sub-partition (warp id within the CTA selects the scheduler), leaving 3 of the 4 schedulers
 // idle — so a CTA carries WPB envs; with the per-substep phase barrier (rsrx_physics.cuh) ONE CTA of
@@ -97,16 +101,22 @@ struct StatePtrs {
   int* status;
 };
 
-// ---------------------------------------------------------------- reset kernel
-// pipeline_init (make_data + mjx.forward with ctrl = 0, warmstart = 0), then
-// data.replace(ctrl), info / metrics / obs, wrappers' reset bookkeeping.
-__global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ qpos,
-                                                  const float* __restrict__ qvel, const float* __restrict__ ctrl,
-                                                  PerEnv pe, StatePtrs st) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
-  float* sm = smem + wib * dm->arena_stride;
-  if (e >= N) return;
+// append env e to the redo list (lane 0 of its warp)
+__device__ __forceinline__ void redo_push(const PerEnv& pe, int e) {
+  if (pe.redo) pe.redo[2 + atomicAdd(pe.redo, 1)] = e;
+}
+
+// ------------------------------------------------------------------ env bodies
+// One env on one warp.  Each body returns false — having committed NOTHING to the env's state — when a substep saw
+// more active contacts than dm->contact_cap: the caller then queues the env for the large-capacity instantiation
+// (rsrx_redo.cu), which runs the same body from the same inputs.  status_init is OR-ed into the env's status word.
+
+// reset: pipeline_init (make_data + mjx.forward with ctrl = 0, warmstart = 0), then data.replace(ctrl), info /
+// metrics / obs, wrappers' reset bookkeeping.
+__device__ __forceinline__ bool env_reset_body(const DModel* __restrict__ dm, float* sm, int lane, int e, int spill_slot,
+                                               const float* __restrict__ qpos, const float* __restrict__ qvel,
+                                               const float* __restrict__ ctrl, const PerEnv& pe, const StatePtrs& st,
+                                               int status_init) {
   const rsrx_layout& L = dm->lay;
   float* row = st.data + (size_t)e * L.data_stride;
   // stage a row: qpos, qvel, ctrl = 0, warm = 0
@@ -115,10 +125,12 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
   for (int i = lane; i < dm->nq; i += 32) row[L.qpos + i] = qpos[(size_t)e * dm->nq + i];
   for (int i = lane; i < dm->nv; i += 32) row[L.qvel + i] = qvel[(size_t)e * dm->nv + i];
   RSRX_SYNC();
-  load_env(dm, sm, lane, e, row, pe);
+  load_env(dm, sm, lane, e, spill_slot, row, pe);
   SolverDims sd;
-  int status = 0;
+  int status = status_init;
   forward<false>(dm, sm, lane, &sd, &status);
+  status = __reduce_or_sync(0xffffffffu, status);
+  if (status & RSRX_STATUS_CONTACT_OVERFLOW) return false;
   for (int i = lane; i < dm->nu; i += 32) sm[ar::CTRL + i] = ctrl[(size_t)e * dm->nu + i];
   RSRX_SYNC();
   store_env(dm, sm, lane, row, 0.f);
@@ -143,9 +155,8 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
     st.reward[e] = 0.f;
     st.done[e] = 0.f;
     for (int i = 0; i < METRICS_STRIDE; i++) st.metrics[(size_t)e * METRICS_STRIDE + i] = 0.f;
+    st.status[e] = status;
   }
-  status = __reduce_or_sync(0xffffffffu, status);
-  if (lane == 0) st.status[e] = status;
   RSRX_SYNC();
   for (int i = lane; i < OBS_STRIDE; i += 32) {
     st.obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
@@ -155,32 +166,26 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
   RSRX_SYNC();
   float* frow = st.first_data + (size_t)e * L.data_stride;
   for (int i = lane; i < L.data_stride; i += 32) frow[i] = row[i];
+  return true;
 }
 
-// ----------------------------------------------------------------- step kernel
-// MAXW: the most warps a CTA of this instantiation is launched with.  Up to 14 the register file allows 128 registers
-// per thread; the 19-warp shape (3 rounds at 8192 envs) has to live with 96.
-template <int MAXW>
-__global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ action,
-                                                 PerEnv pe, StatePtrs st) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
-  float* sm = smem + wib * dm->arena_stride;
-  if (e >= N) {
-    for (int f = 0; f < dm->n_frames * kPhaseBarriers; ++f) phase_barrier<true>(__builtin_ctz(RSRX_SYNC_MASK));  // shadow the phase barriers
-    return;
-  }
+// step: AutoReset pre, action shaping, n_frames x mjx.step, reward / done / info / obs, Episode + AutoReset post
+template <bool SYNC>
+__device__ __forceinline__ bool env_step_body(const DModel* __restrict__ dm, float* sm, int lane, int e, int spill_slot,
+                                              const float* __restrict__ action, const PerEnv& pe, const StatePtrs& st,
+                                              int status_init) {
   const rsrx_layout& L = dm->lay;
   const int kind = dm->env_kind;
   float* row = st.data + (size_t)e * L.data_stride;
   float* info = st.info + (size_t)e * RSRX_INFO_STRIDE;
-  load_env(dm, sm, lane, e, row, pe);
+  load_env(dm, sm, lane, e, spill_slot, row, pe);
   float time = row[L.time];
-  // ---- AutoReset pre + action shaping (lane 0; reads the *lagged* kinematics of the row)
+  // ---- AutoReset pre + action shaping (lane 0; reads the *lagged* kinematics of the row).  The two info words this
+  // part changes (steps, last_action) stay in registers until the step is known to fit the contact capacity.
+  float steps0 = 0.f, last_action = 0.f;
   if (lane == 0) {
-    float steps = info[RSRX_INFO_STEPS];
-    if (dm->episode_length > 0 && st.done[e] != 0.f) steps = 0.f;
-    info[RSRX_INFO_STEPS] = steps;
+    steps0 = info[RSRX_INFO_STEPS];
+    if (dm->episode_length > 0 && st.done[e] != 0.f) steps0 = 0.f;
     float act[NU];
     const int nu = dm->nu;
     for (int i = 0; i < nu; i++) act[i] = sm[ar::CTRL + i] + dm->action_scale[i] * action[(size_t)e * nu + i];
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restric
       if (kind == RSRX_ENV_SF) {
         float df[3] = {info[RSRX_INFO_TARGET] - cube[0], info[RSRX_INFO_TARGET + 1] - cube[1], info[RSRX_INFO_TARGET + 2] - cube[2]};
         if (sqrtf(dot3(df, df)) < 0.03f) a4 = info[RSRX_INFO_LAST_ACTION];
-        info[RSRX_INFO_LAST_ACTION] = a4;
+        last_action = a4;
       }
       act[4] = a4;
     }
@@ -204,13 +209,15 @@ __global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restric
   }
   RSRX_SYNC();
   // ---- pipeline_step: n_frames x mjx.step
-  int status = 0;
+  int status = status_init;
   SolverDims sd;
   for (int f = 0; f < dm->n_frames; ++f) {
-    forward<true>(dm, sm, lane, &sd, &status);
+    forward<SYNC>(dm, sm, lane, &sd, &status);
     implicit_advance(dm, sm, lane);
     time += dm->timestep;
   }
+  status = __reduce_or_sync(0xffffffffu, status);
+  if (status & RSRX_STATUS_CONTACT_OVERFLOW) return false;  // nothing written yet: the env-step is redone from the same inputs
   // ---- post-physics (lane 0)
   float done = 0.f;
   if (lane == 0) {
@@ -296,10 +303,11 @@ __global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restric
       }
     }
     reward = clipf(reward, -1e2f, 1e2f);
+    if (kind == RSRX_ENV_SF) info[RSRX_INFO_LAST_ACTION] = last_action;
     get_obs(dm, sm, info);
     for (int i = 0; i < 3; i++) { info[RSRX_INFO_SITE + i] = site[i]; info[RSRX_INFO_OBJ + i] = sm[ar::XPOS + dm->cube_body * 3 + i]; }
     // EpisodeWrapper
-    float steps = info[RSRX_INFO_STEPS] + (float)dm->action_repeat;
+    float steps = steps0 + (float)dm->action_repeat;
     float trunc = 0.f;
     if (dm->episode_length > 0 && steps >= (float)dm->episode_length) { trunc = 1.f - done; done = 1.f; }
     info[RSRX_INFO_STEPS] = steps;
@@ -312,8 +320,7 @@ __global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restric
   bool bad = false;
   for (int i = lane; i < dm->nq; i += 32) bad |= !isfinite(sm[ar::QPOS + i]);
   for (int i = lane; i < dm->nv; i += 32) bad |= !isfinite(sm[ar::QVEL + i]);
-  if (bad) status |= RSRX_STATUS_NONFINITE;
-  status = __reduce_or_sync(0xffffffffu, status);
+  if (__any_sync(0xffffffffu, bad)) status |= RSRX_STATUS_NONFINITE;
   if (lane == 0 && status) st.status[e] |= status;
   RSRX_SYNC();
   // ---- AutoReset post: pipeline_state and obs only (episode_length <= 0: bare env, no wrappers)
@@ -325,21 +332,18 @@ __global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restric
     store_env(dm, sm, lane, row, time);
     for (int i = lane; i < OBS_STRIDE; i += 32) st.obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
   }
+  return true;
 }
 
-// ------------------------------------------------------------ physics-only kernel
-__global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restrict__ dm, int N, float* __restrict__ data,
-                                                    int nsteps, PerEnv pe, int* __restrict__ status_out,
-                                                    float* __restrict__ dump) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
-  float* sm = smem + wib * dm->arena_stride;
-  if (e >= N) return;
+// raw nsteps x mjx.step on a data row (parity tests, friction sweep set-up); dump: debug internals of the last forward()
+__device__ __forceinline__ bool physics_body(const DModel* __restrict__ dm, float* sm, int lane, int e, int spill_slot,
+                                             float* __restrict__ data, int nsteps, const PerEnv& pe,
+                                             int* __restrict__ status_out, float* __restrict__ dump, int status_init) {
   const rsrx_layout& L = dm->lay;
   float* row = data + (size_t)e * L.data_stride;
-  load_env(dm, sm, lane, e, row, pe);
+  load_env(dm, sm, lane, e, spill_slot, row, pe);
   float time = row[L.time];
-  int status = 0;
+  int status = status_init;
   SolverDims sd;
   sd.nsr = sd.ncon = sd.nrow = 0;
   int niter = 0;
@@ -378,11 +382,97 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
     implicit_advance(dm, sm, lane);
     time += dm->timestep;
   }
-  store_env(dm, sm, lane, row, time);
   status = __reduce_or_sync(0xffffffffu, status);
+  if ((status & RSRX_STATUS_CONTACT_OVERFLOW) && pe.redo && !dump) return false;
+  store_env(dm, sm, lane, row, time);
   if (lane == 0 && status_out) status_out[e] |= status;
+  return true;
 }
 
+#ifndef RSRX_REDO_ONLY
+// ---------------------------------------------------------------- reset kernel
+__global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ qpos,
+                                                  const float* __restrict__ qvel, const float* __restrict__ ctrl,
+                                                  PerEnv pe, StatePtrs st) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
+  float* sm = smem + wib * dm->arena_stride;
+  if (e >= N) return;
+  if (!env_reset_body(dm, sm, lane, e, e, qpos, qvel, ctrl, pe, st, 0) && lane == 0) {
+    if (pe.redo) redo_push(pe, e); else st.status[e] = RSRX_STATUS_CONTACT_OVERFLOW;
+  }
+}
+
+// ----------------------------------------------------------------- step kernel
+// MAXW: the most warps a CTA of this instantiation is launched with.  Up to 14 the register file allows 128 registers
+// per thread; the 19-warp shape (3 rounds at 8192 envs) has to live with 96.
+template <int MAXW>
+__global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ action,
+                                                 PerEnv pe, StatePtrs st) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
+  float* sm = smem + wib * dm->arena_stride;
+  if (e >= N) {
+    for (int f = 0; f < dm->n_frames * kPhaseBarriers; ++f) phase_barrier<true>(__builtin_ctz(RSRX_SYNC_MASK));  // shadow the phase barriers
+    return;
+  }
+  if (!env_step_body<true>(dm, sm, lane, e, e, action, pe, st, 0) && lane == 0) {
+    if (pe.redo) redo_push(pe, e); else st.status[e] |= RSRX_STATUS_CONTACT_OVERFLOW;
+  }
+}
+
+// ------------------------------------------------------------ physics-only kernel
+__global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restrict__ dm, int N, float* __restrict__ data,
+                                                    int nsteps, PerEnv pe, int* __restrict__ status_out,
+                                                    float* __restrict__ dump) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, e = blockIdx.x * (int)(blockDim.x >> 5) + wib;
+  float* sm = smem + wib * dm->arena_stride;
+  if (e >= N) return;
+  if (!physics_body(dm, sm, lane, e, e, data, nsteps, pe, status_out, dump, 0) && lane == 0) redo_push(pe, e);
+}
+#endif  // RSRX_REDO_ONLY
+
+// ------------------------------------------------------------------ redo kernel
+// Runs the env bodies for the envs on the redo list (persistent: warp w of the grid takes entries w, w + W, ...); the
+// last CTA to finish clears the list for the next launch.  Meant for the large-capacity instantiation (rsrx_redo.cu),
+// where contact_cap = 4 slots x every geom pair and a body cannot fail.
+struct RedoArgs {
+  int mode;  // 0 reset, 1 step, 2 physics
+  const float *qpos, *qvel, *ctrl;  // reset
+  const float* action;              // step
+  float* data; int nsteps; int* status_out;  // physics
+};
+template <int W>
+__global__ void __launch_bounds__(32 * W) redo_kernel(const DModel* __restrict__ dm, RedoArgs a, PerEnv pe, StatePtrs st) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, slot = blockIdx.x * W + wib;
+  float* sm = smem + wib * dm->arena_stride;
+  const int n = *reinterpret_cast<volatile int*>(pe.redo);
+  PerEnv pq = pe;
+  pq.redo = nullptr;
+#pragma unroll 1
+  for (int i = slot; i < n; i += gridDim.x * W) {
+    const int e = pe.redo[2 + i];
+    bool ok;
+    if (a.mode == 0) ok = env_reset_body(dm, sm, lane, e, slot, a.qpos, a.qvel, a.ctrl, pq, st, RSRX_STATUS_CONTACT_REDO);
+    else if (a.mode == 1) ok = env_step_body<false>(dm, sm, lane, e, slot, a.action, pq, st, RSRX_STATUS_CONTACT_REDO);
+    else ok = physics_body(dm, sm, lane, e, slot, a.data, a.nsteps, pq, a.status_out, nullptr, RSRX_STATUS_CONTACT_REDO);
+    if (!ok && lane == 0) st.status[e] |= RSRX_STATUS_CONTACT_OVERFLOW;  // unreachable while contact_cap >= 4 * npair
+    RSRX_SYNC();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(pe.redo + 1, 1) == (int)gridDim.x - 1) {
+      pe.redo[0] = 0;
+      pe.redo[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+#ifndef RSRX_REDO_ONLY
 // Debug/parity entry: the cooperative narrow phase on a batch of explicit geom pairs (one half warp per pair, as in
 // collision()).  in: [n][30] = p1(3) m1(9) s1(3) p2(3) m2(9) s2(3); plane != 0: geom 1 is a plane (s1 unused).
 // out: [n][19] = dist(4) pos(4x3) nrm(3).
@@ -411,4 +501,6 @@ __global__ void __launch_bounds__(32) narrowphase_kernel(const float* __restrict
   }
 }
 
-}  // namespace rsrx
+#endif  // RSRX_REDO_ONLY
+
+}  // namespace RSRX_NS

@@ -6,7 +6,7 @@
 #pragma once
 #include "rsrx_device.cuh"
 
-namespace rsrx {
+namespace RSRX_NS {
 
 #define RSRX_SYNC() __syncwarp()
 
@@ -695,7 +695,7 @@ __device__ __noinline__ int collision(const DModel* __restrict__ dm, float* sm, 
     const unsigned am = __ballot_sync(0xffffffffu, active);
     if (am == 0u) continue;
     const int slot = ncon + __popc(am & ((1u << lane) - 1u));
-    if (ncon + __popc(am) > MAXC) *status |= RSRX_STATUS_CONTACT_OVERFLOW;
+    if (ncon + __popc(am) > dm->contact_cap) *status |= RSRX_STATUS_CONTACT_OVERFLOW;  // the caller hands the env-step to the large-capacity kernel
     // dof ranges of the two trees this pair joins (a static body contributes no columns) = width of its Jacobian rows
     const int b1 = dm->geom_bodyid[g1], b2 = dm->geom_bodyid[g2];
     const int t1 = dm->body_treeid[b1], t2 = dm->body_treeid[b2];
@@ -1569,4 +1569,4 @@ __device__ __noinline__ void implicit_advance(const DModel* __restrict__ dm, flo
   RSRX_SYNC();
 }
 
-}  // namespace rsrx
+}  // namespace RSRX_NS
