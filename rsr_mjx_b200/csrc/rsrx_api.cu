@@ -353,7 +353,7 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
     int pool = stride - ar::FIXED;
     if (pool > MAXC * 4 * NCOL) pool = MAXC * 4 * NCOL;
     if (pool < ar::MIN_POOL) { delete m; return fail("rsrx_model_create: not enough shared memory per block for the arena"); }
-    m->host.arena_stride = ar::FIXED + pool;
+    m->host.arena_stride = (ar::FIXED + pool + 3) & ~3;
     // tests: RSRX_POOL_LIMIT caps what contacts may allocate in the pool (0 = every contact's rows go to the spill row)
     if (const char* f = getenv("RSRX_POOL_LIMIT")) pool = std::min(pool, std::max(0, atoi(f)));
     m->host.pool_floats = pool;

@@ -27,7 +27,7 @@ int rsrx_big_prepare(const void* host_dmodel, size_t bytes, int max_smem_optin, 
   if (pool > MAXC * 4 * NCOL) pool = MAXC * 4 * NCOL;
   // the pool holds the Jacobian rows of all MAXC contacts, so this instantiation never spills (and gets no spill buffer)
   if (pool < MAXC * 4 * NCOL) { *err = "rsrx_big_prepare: not enough shared memory per block for the redo arena"; return 1; }
-  d.arena_stride = ar::FIXED + pool;
+  d.arena_stride = (ar::FIXED + pool + 3) & ~3;  // 16-byte multiples: the arena starts with 8-byte pointers
   d.pool_floats = pool;
   d.contact_cap = MAXC;
   const int smem = WPB * d.arena_stride * (int)sizeof(float);

@@ -66,6 +66,7 @@ def host_layout(m):
         o += n
     L.data_stride = (o + 3) // 4 * 4
     L.obs_stride, L.info_stride, L.metrics_stride = _lib.OBS_STRIDE, _lib.INFO_STRIDE, _lib.METRICS_STRIDE
+    L.obs_size = 16 if m.nq == 15 else 23  # T-shape env : cube envs
     L.nq, L.nv, L.nu, L.nbody, L.nsite, L.ngeom = m.nq, m.nv, m.nu, m.nbody, m.nsite, m.ngeom
     return L
 
