@@ -45,47 +45,82 @@ def read_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def read_traffic(kind, n_envs):
-    """dram bytes per launch of step_kernel from the committed ncu summary (captured at 8192 envs), if any"""
-    p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-    if os.path.exists(p) and n_envs == 8192:
-        with open(p) as f:
-            return json.load(f).get(kind)
-    return None
+def kernel_source_hash():
+    """sha256 over the CUDA sources of the stepper: the committed ncu summary is only quoted for the build it measured"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "rsr_mjx_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f in ("rsrx_device.cuh", "rsrx_physics.cuh", "rsrx_env.cuh", "rsrx_api.cu", "rsrx_redo.cu", "rsrx_redo.h"):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
-def read_compute_view(n_envs):
-    """the compute-side view of step_kernel from the committed `ncu --set full` summary
-    (fp32 pipe, issue slots, IPC, resident warps) — the numbers that actually explain an issue/latency-bound kernel"""
-    p = os.path.join(ROOT, "profiles", "r1_step_kernel_ncu_full_summary.csv")
-    if not os.path.exists(p) or n_envs != 8192:
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_step_kernel_ncu_full_summary.csv")
+
+
+def read_ncu_summary(kind, n_envs):
+    """The committed `ncu --set full` summary of one step_kernel launch (tools/ncu_summary.py writes it together with the
+    hash of the kernel sources it was captured from).  Returns None when there is none for this workload, and
+    {'stale': True} when the kernel sources have changed since — stale counters are never quoted."""
+    meta_p = NCU_SUMMARY.replace(".csv", ".meta.json")
+    if not (os.path.exists(NCU_SUMMARY) and os.path.exists(meta_p)):
         return None
+    with open(meta_p) as f:
+        meta = json.load(f)
+    if meta.get("kind") != kind or meta.get("envs") != n_envs:
+        return None
+    if meta.get("source_hash") != kernel_source_hash():
+        return {"stale": True, "captured_from_source_hash": meta.get("source_hash"), "current_source_hash": kernel_source_hash()}
+    raw = {}
+    with open(NCU_SUMMARY) as f:
+        for ln in f:
+            parts = ln.strip().split(",")
+            if len(parts) == 3 and parts[0] != "metric":
+                scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(parts[1], 1.0)  # -> bytes, ms
+                try:
+                    raw[parts[0]] = float(parts[2]) * scale
+                except ValueError:
+                    pass
+    return {"stale": False, "raw": raw, "meta": meta}
+
+
+def compute_view(summary, n_envs, kern_ms, sm_mhz, n_sms=148):
+    """the compute-side view of step_kernel — what actually bounds an issue/latency-bound kernel.
+    Counter values come from the committed ncu capture of THIS build (hash-checked); the issue-slot fraction is
+    re-derived from this run's own kernel time: warp-instructions per launch (a property of the workload, stable to
+    ~1 % between launches of the same distribution) / (launch time x SM clock x SMs x 4 schedulers)."""
+    if summary is None:
+        return None
+    if summary["stale"]:
+        return {"stale": True, "note": "kernel sources changed since the committed ncu capture; re-run tools/ncu_summary.py",
+                **{k: v for k, v in summary.items() if k != "stale"}}
+    raw = summary["raw"]
     want = {"sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "fp32_fma_pipe_pct",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
             "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
             "sm__inst_executed.avg.per_cycle_active": "ipc_per_sm",
             "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
-            "smsp__inst_issued.sum": "warp_instructions_per_launch"}
-    out = {"source": "profiles/r1_step_kernel_ncu_full_summary.csv (ncu --set full, one launch, 8192 envs)"}
-    raw = {}
-    with open(p) as f:
-        for ln in f:
-            parts = ln.strip().split(",")
-            if len(parts) == 3:
-                raw[parts[0]] = parts[2]
-                if parts[0] in want:
-                    out[want[parts[0]]] = float(parts[2])
-    # executed fp32 work: thread-level FADD + FMUL + 2 x FFMA per elapsed cycle, summed over the chip
+            "smsp__inst_issued.sum": "warp_instructions_per_launch",
+            "gpu__time_duration.sum": "ncu_launch_ms"}
+    out = {"stale": False, "source": "profiles/" + os.path.basename(NCU_SUMMARY) + " (ncu --set full, one launch)",
+           "source_hash": summary["meta"]["source_hash"]}
+    for k, name in want.items():
+        if k in raw:
+            out[name] = raw[k]
     try:
-        per_cycle = (float(raw["smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed"])
-                     + float(raw["smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed"])
-                     + 2.0 * float(raw["smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed"]))
-        flop = per_cycle * float(raw["sm__cycles_elapsed.max"])
+        per_cycle = (raw["smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed"]
+                     + raw["smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed"]
+                     + 2.0 * raw["smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed"])
+        flop = per_cycle * raw["sm__cycles_elapsed.max"]
         out["fp32_flop_per_env_step"] = flop / n_envs
-        out["fp32_tflops_achieved"] = flop / (float(raw["gpu__time_duration.sum"]) * 1e-3) / 1e12
-        out["fp32_tflops_peak"] = 148 * 128 * 2 * float(raw["sm__cycles_elapsed.avg.per_second"]) * 1e9 / 1e12
-    except (KeyError, ValueError):
+        out["fp32_tflops_peak_at_run_clock"] = n_sms * 128 * 2 * sm_mhz * 1e6 / 1e12 if sm_mhz else None
+        out["fp32_tflops_achieved_this_run"] = flop / (kern_ms * 1e-3) / 1e12
+    except KeyError:
         pass
+    if "smsp__inst_issued.sum" in raw and sm_mhz:
+        out["issue_slot_frac_this_run"] = raw["smsp__inst_issued.sum"] / (kern_ms * 1e-3 * sm_mhz * 1e6 * n_sms * 4)
     return out
 
 
@@ -167,6 +202,103 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def stagger_episode_phases(env, state, gen):
+    """Put env i at a uniformly random phase of its episode: the step counter of the EpisodeWrapper gets a random
+    offset, so env i is truncated and auto-reset 1200 - offset_i steps from now; after 1200 further steps every env has
+    been reset once and sits offset_i steps into a fresh episode — the stationary distribution of a running job."""
+    import torch
+    from rsr_mjx_b200 import _lib
+    off = torch.randint(0, env.episode_length, (env.num_envs,), device=env.device, generator=gen).float()
+    state._buf["info"][:, _lib.INFO["STEPS"]] = off
+    state._buf["done"].zero_()  # a set done flag makes the next step restart the counter at 0 (AutoReset pre-step)
+
+
+def time_env(env, state, actions_fn, W, K, flush, barrier, episode_profile=True):
+    """Timing protocol of one env (all on the current stream, CUDA events):
+       1. (the caller has run W warm-up steps on a throw-away state; `state` is fresh from reset)
+       2. (episode_profile) a whole episode from reset, 1200 steps, timed as one block and in windows at t = 0 / 300 /
+          600 / 900 -> the from-reset profile and the full-episode mean;
+       3. episode phases staggered, 1200 more steps (timed as one block: the stationary mean, L2 warm);
+       4. the K timed steps of the bench contract on that stationary population, one event pair per step with an L2
+          flush between steps."""
+    import torch
+    EP = env.episode_length
+    out = {}
+    barrier()
+    if episode_profile:
+        marks = sorted({0, 16, 300, 316, 600, 616, 900, 916, EP})
+        ev = {m: torch.cuda.Event(enable_timing=True) for m in marks}
+        for t in range(EP):
+            if t in ev:
+                ev[t].record()
+            env.step(state, actions_fn(t))
+        ev[EP].record()
+        barrier()
+        out["episode_from_reset_mean_ms"] = ev[0].elapsed_time(ev[EP]) / EP
+        out["from_reset_window_ms"] = {f"t{m}": ev[m].elapsed_time(ev[m + 16]) / 16 for m in (0, 300, 600, 900)}
+    gen = torch.Generator(device=env.device).manual_seed(12345)
+    stagger_episode_phases(env, state, gen)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(EP):
+        env.step(state, actions_fn(t + 7))
+    e1.record()
+    barrier()
+    out["stationary_1200_step_mean_ms_l2_warm"] = e0.elapsed_time(e1) / EP
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for t in range(K):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        evs[t][0].record()
+        env.step(state, actions_fn(t + 3))
+        evs[t][1].record()
+    barrier()
+    out["step_ms"] = np.array([a.elapsed_time(b) for a, b in evs])
+    return out
+
+
+def synthetic_rsr_files(obs_size, act_size, n=51, seed=2):
+    """BASELINE config 4: six synthetic tables (real / past-sim / current-sim observations and actions, 51 rows each)
+    -> the five arrays `policy_params_training` takes.  Values are smooth random walks around the reset observation
+    scale; the loss kernel's cost does not depend on them."""
+    rng = np.random.default_rng(seed)
+    base = np.cumsum(rng.normal(0, 0.01, (n, obs_size)), axis=0).astype(np.float32)
+    real = base + rng.normal(0, 1e-3, base.shape).astype(np.float32)
+    past = base + rng.normal(0, 5e-3, base.shape).astype(np.float32)
+    cur = base + rng.normal(0, 2e-3, base.shape).astype(np.float32)
+    act = rng.uniform(-1, 1, (n, act_size)).astype(np.float32)
+    m = min(n - 1, 50)
+    return real[:m], act[:m], real[1:m + 1], past[1:m + 1], cur[1:m + 1]
+
+
+def ppo_sub_record(dev, rank, world, training_steps=5):
+    """BASELINE config 3 + 4: PPO exactly as ppo_train/airbot_training/train.py:45-55 (1024 envs globally, unroll 10,
+    32 x 256 minibatches, 8 updates per batch, lr 1e-4, gamma 0.96, entropy 2e-2, reward scaling 0.1, obs normalisation,
+    domain randomisation) WITH the RSR term (past_data, RSR/losses.py:186-195); `training/sps` of RSR/train.py:378-385 =
+    env-steps consumed / wall time of a training step, first (graph-capturing) step dropped."""
+    from rsr_mjx_b200 import domain_randomize as DR, ppo, prng, rsr_pipeline as RP
+    from rsr_mjx_b200.envs import AirbotPlayBase
+    N = 1024 // world
+    env = AirbotPlayBase("cube", num_envs=N, episode_length=1200, device=dev, randomization_fn=DR.domain_randomize,
+                         randomization_rng=prng.split(prng.PRNGKey(1), N))
+    past = RP.build_policy_rsr_data(*synthetic_rsr_files(env.observation_size, env.action_size), device=dev)
+    sps, split, rsr = [], [], []
+    ppo.train(env, num_timesteps=10**9, episode_length=1200, past_data=past, num_envs=N, learning_rate=1e-4,
+              entropy_cost=2e-2, discounting=0.96, unroll_length=10, batch_size=256 // world, num_minibatches=32,
+              num_updates_per_batch=8, num_evals=training_steps, normalize_observations=True, reward_scaling=0.1,
+              max_training_steps=training_steps, run_evals=False,
+              training_step_fn=lambda n, m: (sps.append(m["training/sps"]), rsr.append(m.get("training/sim2real_loss")),
+                                             split.append((m["training/collect_s"], m["training/update_s"]))))
+    steady = sps[1:] if len(sps) > 1 else sps
+    return {"metric": "ppo_train_env_steps_per_sec", "value": float(np.mean(steady)), "unit": "env-steps/s", "n_gpus": world,
+            "training_steps_timed": len(steady), "env_steps_per_training_step": 256 * 10 * 32,
+            "collect_s": float(np.mean([c for c, _ in split[1:] or split])), "update_s": float(np.mean([u for _, u in split[1:] or split])),
+            "rsr_term": True, "sim2real_loss_last": rsr[-1],
+            "config": {"workload": "PPO on cube_env + domain randomisation with the RSR KDE+Wasserstein term (BASELINE configs 3+4)",
+                       "global_envs": 1024, "unroll_length": 10, "minibatches": "32 x 256 sequences", "updates_per_batch": 8,
+                       "past_data": "synthetic six-table set, 50 transitions, grid 10 x 51, h = 0.1"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +310,7 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the T-shape and PPO sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -197,13 +330,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W, K, N = max(args.warmup, 3), args.steps, args.envs
-
-    env = AirbotPlayBase(args.kind, num_envs=N, episode_length=1200, device=dev)
-    # env i of the global job = rank * N + i: disjoint reset keys per rank, no communication
-    keys = sharding.shard_keys(0, N, rank, world)
-    state = env.reset(keys)
-    gen = torch.Generator(device=dev).manual_seed(1 + rank)
-    actions = torch.rand(W + K, N, env.action_size, device=dev, generator=gen) * 2 - 1
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -211,26 +337,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def make(kind):
+        env = AirbotPlayBase(kind, num_envs=N, episode_length=1200, device=dev)
+        # env i of the global job = rank * N + i: disjoint reset keys per rank, no communication
+        keys = sharding.shard_keys(0, N, rank, world)
+        gen = torch.Generator(device=dev).manual_seed(1 + rank)
+        actions = torch.rand(64, N, env.action_size, device=dev, generator=gen) * 2 - 1  # U(-1,1)^5, cycled
+        warm = env.reset(keys)
+        for t in range(W):
+            env.step(warm, actions[t % 64])
+        return env, env.reset(keys), actions
+
+    env, state, actions = make(args.kind)
     sampler = ClockSampler(local)
-    # ---- device-resident timing
-    for t in range(W):
-        env.step(state, actions[t])
-    barrier()
     sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for t in range(K):
-        if flush is not None:
-            flush.fill_(t & 0xFF)
-        evs[t][0].record()
-        env.step(state, actions[W + t])
-        evs[t][1].record()
-    barrier()
-    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    tm = time_env(env, state, lambda t: actions[t % 64], W, K, flush, barrier)
+    step_ms = tm.pop("step_ms")
     total_ms = float(step_ms.sum())
     # ---- end-to-end timing: host action buffer in, host obs/reward/done out, every step, through the host-buffer entry
-    # of the C-ABI (rsrx_env_step_host: H2D action, launch, D2H obs/reward/done queued by one call)
+    # of the C-ABI (rsrx_env_step_host: H2D action, launch, D2H obs/reward/done queued by one call); same stationary
+    # population of envs
     h_act = torch.empty(K, N, env.action_size, dtype=torch.float32).pin_memory()
-    h_act.copy_(actions[W:].cpu())
+    h_act.copy_(actions[torch.arange(K) % 64].cpu())
     h_obs = torch.empty(N, env.layout.obs_stride, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
     h_done = torch.empty(N, dtype=torch.float32).pin_memory()
@@ -247,7 +375,27 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    status_bad = int((state._buf["status"] != 0).sum().item())
+    from rsr_mjx_b200 import _lib
+    status = state._buf["status"]
+    status_counts = {name: int(((status & bit) != 0).sum().item()) for name, bit in
+                     (("nonfinite", _lib.STATUS_NONFINITE), ("contact_dropped", _lib.STATUS_CONTACT_OVERFLOW),
+                      ("newton_iteration_cap", _lib.STATUS_SOLVER_CAP), ("large_capacity_redo", _lib.STATUS_CONTACT_REDO))}
+
+    # ---- sub-records (same JSON line): BASELINE config 2 (T-shape env, 8192 envs) and configs 3+4 (PPO with the RSR term)
+    sub = {}
+    if not args.no_sub:
+        if args.kind != "T":
+            envT, stateT, actT = make("T")
+            tT = time_env(envT, stateT, lambda t: actT[t % 64], W, K, flush, barrier, episode_profile=False)
+            msT = float(sharding.reduce_max([float(tT["step_ms"].sum())], device=dev)[0])
+            sub["airbot_T_env_steps_per_sec"] = {
+                "value": N * world * K / (msT * 1e-3), "unit": "env-steps/s", "ms_per_step": msT / K, "n_gpus": world,
+                "config": {"workload": "airbot_T env.step (T_shape_env.py + T_shape.xml, box-box contacts), stationary episode phases",
+                           "envs_per_gpu": N}}
+            del envT, stateT, actT
+        barrier()
+        sub["ppo_train_env_steps_per_sec"] = ppo_sub_record(dev, rank, world)
+        barrier()
 
     total_ms, e2e_ms = sharding.reduce_max([total_ms, e2e_ms], device=dev)
     if rank == 0:
@@ -255,6 +403,11 @@ def main():
         value = N * world * K / (total_ms * 1e-3)
         kern_ms = float(np.mean(step_ms))
         achieved = ALGO_BYTES[args.kind] * N / (kern_ms * 1e-3) / 1e9
+        clocks = sampler.summary()
+        summary = read_ncu_summary(args.kind, N)
+        cv = compute_view(summary, N, kern_ms, clocks.get("sm_mhz"))
+        traffic = summary["raw"].get("dram__bytes_read.sum", 0.0) + summary["raw"].get("dram__bytes_write.sum", 0.0) \
+            if summary and not summary["stale"] else None
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -262,19 +415,25 @@ def main():
             "config": {"workload": f"airbot_{args.kind} env.step (test/airbot.py + sf.xml; 4 x mjx.step + reward/obs/done + episode/auto-reset)",
                        "envs_per_gpu": N, "global_envs": N * world, "actions": "U(-1,1)^5 pre-generated on device",
                        "reset": "jax-style keys split(PRNGKey(0)), reference reset law", "domain_randomization": False,
+                       "episode_phase": "stationary: envs staggered uniformly over the 1200-step episode before the timed steps "
+                                        "(a whole episode from reset and 1200 staggering steps run first, outside the timed region)",
                        "parallelism": f"dp{world} (envs sharded, no collective)",
                        "l2": "256 MiB flush between timed steps" if flush is not None else "no flush"},
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "e2e": {"value": N * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": N * env.action_size * 4, "d2h_bytes_per_step": N * (env.layout.obs_stride + 2) * 4},
-            "gpu_launches": K,
+            # two launches of ours per env.step: step_kernel and the large-capacity pass over the (normally empty) redo list
+            "gpu_launches": 2 * K,
+            "episode_profile": {k: (v if isinstance(v, dict) else float(v)) for k, v in tm.items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": read_traffic(args.kind, N), "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES[args.kind],
-                         "compute_view": read_compute_view(N),
-                         "note": "scan-like state-in/state-out step: far below the HBM roof by design (SURVEY.md §8d); "
-                                 "issue/latency-bound, see profiles/"},
-            "status_flagged_envs": status_bad,
+                         "issue_slot_frac": (cv or {}).get("issue_slot_frac_this_run"),
+                         "compute_view": cv,
+                         "note": "scan-like state-in/state-out step: far below the HBM roof by design (SURVEY.md §8d); the "
+                                 "kernel is issue/latency-bound, so the issue-slot fraction next to `frac` is the one to watch"},
+            "status_flagged_envs": status_counts,
+            "sub": sub,
         }
         if not args.no_cpu_baseline and world == 1:
             rate, dt, thr = cpu_oracle_rate(args.kind, args.cpu_envs, 1000, dense=False)  # ~10 s on 16 host threads

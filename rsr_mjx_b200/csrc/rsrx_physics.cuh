@@ -1475,6 +1475,9 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
     bool done = niter >= dm->iterations;
     done |= improvement < dm->tolerance;
     done |= gradient < dm->tolerance;
+    // a non-finite state (an exploded simulation; MJX propagates NaN the same way) cannot satisfy either test and would
+    // spin through iterations x ls_iterations passes for a result that is NaN anyway, stalling its whole CTA
+    done |= !(cost == cost) || !(gradient == gradient);
     if (done) break;
     RSRX_SYNC();
     update_gradient(dm, sm, lane, nsr, ncon, !changed && have_factor);

@@ -158,7 +158,7 @@ def write_rsr_datasets(data_dir, real_obs, real_action, past_sim_obs, current_si
 
 def load_dataset_from_path(path):
     """`(states, actions, next_states)` from an `.npz` with those three arrays (RSR/dataset_processor.py:10-14)."""
-    with np.load(Path(path), allow_pickle=True) as data:
+    with np.load(Path(path), allow_pickle=False) as data:
         missing = [k for k in ("states", "actions", "next_states") if k not in data]
         if missing:
             raise KeyError(f"{path}: missing arrays {missing}")

@@ -210,10 +210,16 @@ class AirbotPlayBase:
         if randomization_fn is not None:
             if randomization_rng is None:
                 raise ValueError("randomization_fn needs randomization_rng (keys [num_envs, 2])")
-            sys_v, _ = randomization_fn(self.sys, randomization_rng)
-            self.set_per_env(**{k: sys_v._ov[k] for k in System._PER_ENV if k in sys_v._ov})
+            self.randomize(randomization_fn, randomization_rng)
         self._lowers = torch.tensor(self.model.act_ctrlrange[:, 0], dtype=torch.float32, device=self.device)
         self._uppers = torch.tensor(self.model.act_ctrlrange[:, 1], dtype=torch.float32, device=self.device)
+
+    def randomize(self, randomization_fn: Callable, rng) -> None:
+        """DomainRandomizationVmapWrapper (wrapper.py:139-165): `randomization_fn(sys, rng[N, 2]) -> (sys_v, in_axes)`
+        installs the batched model leaves of `sys_v` on this env."""
+        sys_v, _ = randomization_fn(self.sys, rng)
+        self.set_per_env(**{k: sys_v._ov[k] for k in System._PER_ENV if k in sys_v._ov})
+        self._randomization_fn = randomization_fn
 
     def clone(self, num_envs: int, randomization_fn: Optional[Callable] = None, randomization_rng=None) -> "AirbotPlayBase":
         """A second env of the same kind / reward parameters / wrapper settings with its own batch size (the eval env

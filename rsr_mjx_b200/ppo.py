@@ -425,7 +425,9 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           use_cuda_graph: bool = True, fused_head: bool = True, allow_tf32: bool = True, graph_collect: bool = True,
           max_training_steps: Optional[int] = None, num_resets_per_eval: int = 0, deterministic_eval: bool = False,
           eval_env=None, policy_params_fn: Callable[..., None] = lambda *a: None, run_evals: bool = True,
-          training_step_fn: Optional[Callable[[int, Dict[str, float]], None]] = None, **unused):
+          training_step_fn: Optional[Callable[[int, Dict[str, float]], None]] = None,
+          network_factory: Any = None, randomization_fn: Optional[Callable] = None,
+          restore_checkpoint_path: Optional[str] = None, **brax_plumbing):
     """PPO training (RSR/train.py:76).  `environment` is an `AirbotPlayBase` with `num_envs` envs on this rank
     (under torch.distributed every rank passes its shard; `num_envs` is the per-rank count here).
 
@@ -434,8 +436,21 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     epoch (if num_evals > 1) and after every epoch and calls `progress_fn(env_steps, {eval/..., training/...})` and
     `policy_params_fn(env_steps, make_policy, params)`.  `run_evals=False` skips the evaluator (benchmarks),
     `training_step_fn(step, training_metrics)` is called after every training step.
+    Reference arguments that configure the run are honoured or raise, never dropped (train_args.py):
+    `network_factory` (a functools.partial over make_ppo_networks: its *_hidden_layer_sizes are used),
+    `randomization_fn` (installed on the env with the keys RSR/train.py:212-217 derives from `seed`),
+    `restore_checkpoint_path` (own torch file or a brax `model.save_params` pickle; like the reference, a path that does
+    not exist is skipped; an Orbax directory raises with the conversion recipe — checkpoints.py).
     Returns (make_policy, (normalizer, networks), metrics)."""
+    import os
+    from . import checkpoints, train_args
     env = environment
+    train_args.reject_unknown(brax_plumbing, "ppo.train")
+    _sizes = train_args.hidden_sizes(network_factory, dict(policy_hidden_layer_sizes=policy_hidden,
+                                                           value_hidden_layer_sizes=value_hidden))
+    policy_hidden, value_hidden = _sizes["policy_hidden_layer_sizes"], _sizes["value_hidden_layer_sizes"]
+    train_args.apply_randomization(env, randomization_fn, seed)
+    past_data = rsr.prepare_rsr_data(past_data, env.device)
     graph_collect_enabled = bool(graph_collect and use_cuda_graph)
     # the two MLPs run their matmuls on the tensor cores in TF32, the precision jax gives float32 `dot` on NVIDIA GPUs
     # by default (the reference never raises `jax_default_matmul_precision`); everything else stays fp32
@@ -461,6 +476,11 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     params = list(net.parameters())
     opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8, capturable=bool(use_cuda_graph), fused=True)
     norm = RunningStatistics(env.observation_size, dev)
+    if restore_checkpoint_path is not None and os.path.exists(str(restore_checkpoint_path)):  # RSR/train.py:410-422
+        r_norm, r_net = checkpoints.restore(str(restore_checkpoint_path), "ppo", dev)
+        net.load_state_dict(r_net.state_dict())
+        for k in ("count", "mean", "summed_variance", "std"):
+            getattr(norm, k).copy_(getattr(r_norm, k))
     normalize = norm.normalize if normalize_observations else (lambda x: x)
     gen = torch.Generator(device=dev).manual_seed(seed * 7919 + rank + 1)
 

@@ -62,6 +62,14 @@ def split(key, num: int = 2) -> np.ndarray:
     return bits.reshape(bits.shape[:-1] + (num, 2))
 
 
+def fold_in(key, data: int) -> np.ndarray:
+    """jax.random.fold_in: threefry_2x32(key, threefry_seed(data)), threefry_seed(uint32 d) = [0, d] (unverified
+    against jax, like the rest of this module)"""
+    key = np.asarray(key, _U32)
+    y0, y1 = threefry2x32(key[..., 0], key[..., 1], _U32(0), _U32(int(data) & 0xFFFFFFFF))
+    return np.stack([y0, y1], axis=-1).astype(_U32)
+
+
 def random_bits(key, n: int) -> np.ndarray:
     return _threefry_2x32_counts(key, n)
 

@@ -111,6 +111,21 @@ def _as_rsr_data(past_data: Any) -> RSRData:
                    grid=grid, bandwidth=0.1)
 
 
+def prepare_rsr_data(past_data: Any, device) -> Any:
+    """Normalises `past_data` ONCE (the trainers call this before warm-up and CUDA-graph capture): `divergence` becomes a
+    host-side 0-d tensor and `bandwidth` a float, grid / reference arrays contiguous float32 on `device`.  A
+    reference-style RSRData or legacy tuple whose KLD lives on the device would otherwise force a device sync on every
+    loss call (and fail outright inside a stream capture)."""
+    if past_data is None:
+        return None
+    r = _as_rsr_data(past_data)
+    div = r.divergence
+    div = div.detach().cpu().float().reshape(()) if torch.is_tensor(div) else torch.tensor(float(np.asarray(div)))
+    bw = float(r.bandwidth.item() if torch.is_tensor(r.bandwidth) else np.asarray(r.bandwidth))
+    return RSRData(divergence=div, reference_density=_f32c(r.reference_density, device),
+                   reference_data=_f32c(r.reference_data, device), grid=_f32c(r.grid, device), bandwidth=bw)
+
+
 class _RSRLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, batch, grid, reference_data, reference_density, bandwidth, divergence, loss_scale):

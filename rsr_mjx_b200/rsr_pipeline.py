@@ -167,9 +167,12 @@ def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, p
                            **sac_and_extra_options):
     """Trains an RSR policy (reference signature and defaults, rsr_pipeline.py:274-319).
 
-    `env` is a batched `AirbotPlayBase` whose `num_envs` / `episode_length` match the arguments.  Orbax checkpoints
-    are out of scope, so `restore_checkpoint_path` must be None.  ``algorithm='sac'`` takes tau / min_replay_size / max_replay_size /
-    grad_updates_per_step through the keyword options, like the reference (rsr_pipeline.py:396-426).
+    `env` is a batched `AirbotPlayBase` whose `num_envs` / `episode_length` match the arguments.
+    `network_factory` and `restore_checkpoint_path` go to the trainer (ppo.train / sac.train docstrings: hidden sizes
+    from the partial's keywords; own torch file or brax pickle, an Orbax directory raises with the conversion recipe;
+    SAC refuses to resume, like the reference).  ``algorithm='sac'`` takes tau / min_replay_size / max_replay_size /
+    grad_updates_per_step through the keyword options, like the reference (rsr_pipeline.py:396-426); with
+    ``algorithm='ppo'`` those four are accepted and unused, as in the reference.  Any other unknown keyword raises.
     Returns ``(make_inference_fn, (normalizer, networks))``."""
     from . import ppo
     if rsr_loss_scale < 0:
@@ -180,22 +183,35 @@ def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, p
     algorithm = algorithm.strip().lower()
     if algorithm not in ("ppo", "sac"):
         raise ValueError(f'unsupported algorithm {algorithm!r}; expected "ppo" or "sac"')
+    _sac_only = ("tau", "min_replay_size", "max_replay_size", "grad_updates_per_step", "hidden_layer_sizes")
+    _common = ("use_cuda_graph", "allow_tf32", "max_training_steps", "eval_env", "run_evals", "randomization_fn",
+               "checkpoint_logdir", "wrap_env_fn", "wrap_env")
+    _ppo_only = ("fused_head", "policy_hidden", "value_hidden", "clipping_epsilon", "gae_lambda", "normalize_advantage",
+                 "graph_collect", "training_step_fn")
+    for k in sac_and_extra_options:
+        if k not in _sac_only + _common + _ppo_only:
+            raise TypeError(f"policy_params_training() got an unexpected keyword argument {k!r}")
     if restore_checkpoint_path:
-        raise NotImplementedError("Orbax checkpoint restore is out of scope (SURVEY.md §5)")
+        import os
+        if algorithm == "sac":  # rsr_pipeline.py:399-403
+            raise ValueError('Brax 0.12.1 SAC cannot resume complete training state; use checkpoint_logdir to save '
+                             'inference checkpoints instead')
+        if os.path.isdir(str(restore_checkpoint_path)):
+            from . import checkpoints
+            checkpoints.load_brax_params(str(restore_checkpoint_path))  # raises: Orbax directories cannot be read here
     past_data = build_policy_rsr_data(past_states, past_actions, past_next_states_real, past_next_states_sim,
                                       current_next_states_sim, num_samples=num_samples, min_val=min_val, max_val=max_val,
                                       bandwidth=bandwidth, seed=seed, device=env.device)
     if algorithm == "sac":
         from . import sac
-        opts = {k: v for k, v in sac_and_extra_options.items()
-                if k in ("tau", "min_replay_size", "max_replay_size", "grad_updates_per_step", "hidden_layer_sizes",
-                         "use_cuda_graph", "allow_tf32", "max_training_steps", "eval_env", "run_evals")}
+        opts = {k: v for k, v in sac_and_extra_options.items() if k in _sac_only + _common}
         make_inference_fn, params, _ = sac.train(
             environment=env, past_data=past_data, num_timesteps=num_timesteps, num_evals=num_evals,
             num_eval_envs=num_eval_envs, reward_scaling=reward_scaling, episode_length=episode_length,
             normalize_observations=normalize_observations, action_repeat=action_repeat, discounting=discounting,
             learning_rate=learning_rate, num_envs=num_envs, batch_size=batch_size, deterministic_eval=deterministic_eval,
-            progress_fn=progress_fn or (lambda *a: None), rsr_loss_scale=rsr_loss_scale, seed=seed, **opts)
+            progress_fn=progress_fn or (lambda *a: None), rsr_loss_scale=rsr_loss_scale, seed=seed,
+            network_factory=network_factory, restore_checkpoint_path=restore_checkpoint_path, **opts)
         return make_inference_fn, params
     make_inference_fn, params, _ = ppo.train(
         environment=env, past_data=past_data, num_timesteps=num_timesteps, num_evals=num_evals, num_eval_envs=num_eval_envs,
@@ -205,6 +221,6 @@ def policy_params_training(env, restore_checkpoint_path: Optional[str] = None, p
         entropy_cost=entropy_cost, num_envs=num_envs, batch_size=batch_size, progress_fn=progress_fn or (lambda *a: None),
         rsr_loss_scale=rsr_loss_scale, seed=seed, num_resets_per_eval=num_resets_per_eval,
         deterministic_eval=deterministic_eval, policy_params_fn=policy_params_fn or (lambda *a: None),
-        **{k: v for k, v in sac_and_extra_options.items()
-           if k in ("use_cuda_graph", "fused_head", "allow_tf32", "max_training_steps", "eval_env", "run_evals")})
+        network_factory=network_factory, restore_checkpoint_path=restore_checkpoint_path,
+        **{k: v for k, v in sac_and_extra_options.items() if k in _common + _ppo_only})
     return make_inference_fn, params

@@ -139,12 +139,26 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           max_replay_size: Optional[int] = None, grad_updates_per_step: int = 1, deterministic_eval: bool = False,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None, rsr_loss_scale: float = 1.0,
           hidden_layer_sizes=(256, 256), use_cuda_graph: bool = True, allow_tf32: bool = True,
-          max_training_steps: Optional[int] = None, eval_env=None, run_evals: bool = True, **unused):
+          max_training_steps: Optional[int] = None, eval_env=None, run_evals: bool = True,
+          network_factory: Any = None, randomization_fn: Optional[Callable] = None,
+          restore_checkpoint_path: Optional[str] = None, sgd_probe_fn: Optional[Callable[[str, Dict[str, Any]], None]] = None,
+          **brax_plumbing):
     """SAC training (RSR/sac_train.py:28).  `environment`: an `AirbotPlayBase` with `num_envs` envs on this rank.
+    `network_factory` (functools.partial over make_sac_networks: `hidden_layer_sizes` is used), `randomization_fn`
+    (installed on the env) are honoured; `restore_checkpoint_path` raises like the reference ("Brax 0.12.1 SAC cannot
+    resume complete training state", RSR/rsr_pipeline.py:399-403); unknown keywords raise (train_args.py).
     Returns (make_policy, (normalizer, networks), metrics)."""
+    from . import train_args
     if rsr_loss_scale < 0:
         raise ValueError(f"rsr_loss_scale must be non-negative, got {rsr_loss_scale}")
     env = environment
+    train_args.reject_unknown(brax_plumbing, "sac.train")
+    if restore_checkpoint_path:
+        raise ValueError('Brax 0.12.1 SAC cannot resume complete training state; use checkpoint_logdir to save '
+                         'inference checkpoints instead')
+    hidden_layer_sizes = train_args.hidden_sizes(network_factory, dict(hidden_layer_sizes=hidden_layer_sizes))["hidden_layer_sizes"]
+    train_args.apply_randomization(env, randomization_fn, seed)
+    past_data = rsr.prepare_rsr_data(past_data, env.device)
     if env.num_envs != num_envs:
         raise ValueError(f"environment has {env.num_envs} envs, num_envs={num_envs}")
     if env.episode_length != episode_length:
@@ -284,6 +298,9 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         nonlocal metrics
         static.copy_(buffer.sample(batch_size, gen))
         noise.normal_(generator=gen)
+        if sgd_probe_fn is not None:  # tests: everything the three losses of this step are computed from
+            sgd_probe_fn("before", dict(static=static, noise=noise, log_alpha=log_alpha, net=net, target=target, norm=norm,
+                                        fields=fields))
         if graph_a is not None:
             graph_a.replay()
             _flat_allreduce_mean(q_params + pol_params + [log_alpha])
@@ -293,6 +310,8 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             _flat_allreduce_mean(q_params + pol_params + [log_alpha])
             opt_alpha.step(); opt_q.step(); opt_pi.step()
             finish()
+        if sgd_probe_fn is not None:
+            sgd_probe_fn("after", dict(metrics=metrics, log_alpha=log_alpha, net=net, target=target))
 
     def make_policy(deterministic: bool = deterministic_eval):
         @torch.no_grad()

@@ -90,3 +90,82 @@ def test_policy_params_training_sac_end_to_end():
     with pytest.raises(ValueError, match="unsupported algorithm"):
         RP.policy_params_training(env, past_states=S, past_actions=A, past_next_states_real=S2, past_next_states_sim=S2,
                                   current_next_states_sim=S2, algorithm="td3")
+
+
+def test_cuda_graphed_step_matches_numpy_restatement():
+    """The SGD step the trainer actually runs (CUDA-graphed, on the batches it sampled from its replay ring) against a
+    float64 NumPy restatement of RSR/sac_losses.py:38-128 evaluated on the same batch, noise and pre-update parameters:
+    alpha / critic / actor losses within 1e-4 (fp32 matmuls: allow_tf32=False here), and the polyak step of the target
+    critics (tau) exact."""
+    import math
+    snaps, results = [], []
+
+    def mlp_np(mlp, x, act_relu=True):
+        ls = list(mlp.layers)
+        for i, l in enumerate(ls):
+            x = x @ l["weight"].T + l["bias"]
+            if i + 1 < len(ls) and act_relu:
+                x = np.maximum(x, 0)
+        return x
+
+    class NP:  # parameter snapshot of an MLP as float64 numpy
+        def __init__(self, mlp):
+            self.layers = [dict(weight=l.weight.detach().double().cpu().numpy(), bias=l.bias.detach().double().cpu().numpy())
+                           for l in mlp.layers]
+
+    def probe(phase, c):
+        if phase == "before":
+            n = c["norm"]
+            snaps.append(dict(static=c["static"].double().cpu().numpy(), noise=c["noise"].double().cpu().numpy(),
+                              log_alpha=float(c["log_alpha"].detach()), fields=c["fields"],
+                              mean=n.mean.double().cpu().numpy(), std=n.std.double().cpu().numpy(),
+                              pol=NP(c["net"].policy), q1=NP(c["net"].q1), q2=NP(c["net"].q2), t1=NP(c["target"].q1),
+                              t2=NP(c["target"].q2)))
+        else:
+            torch.cuda.synchronize()
+            results.append(dict({k: float(v) for k, v in c["metrics"].items()}, t1=NP(c["target"].q1), q1=NP(c["net"].q1)))
+
+    env = AirbotPlayBase("sf", num_envs=64, episode_length=1200)
+    tau = 0.01
+    sac.train(env, num_timesteps=10**9, episode_length=1200, past_data=None, num_envs=64, learning_rate=1e-3, discounting=0.96,
+              batch_size=64, num_evals=2, normalize_observations=True, reward_scaling=0.1, min_replay_size=256,
+              max_replay_size=4096, grad_updates_per_step=1, hidden_layer_sizes=(64, 64), use_cuda_graph=True,
+              allow_tf32=False, tau=tau, max_training_steps=5, run_evals=False, sgd_probe_fn=probe)
+    assert len(snaps) == len(results) == 5
+    A = 5
+
+    def lp_np(logits, raw):
+        loc, s_ = logits[:, :A], logits[:, A:]
+        scale = np.log1p(np.exp(s_)) + 0.001
+        lp = -0.5 * ((raw - loc) / scale) ** 2 - 0.5 * math.log(2 * math.pi) - np.log(scale)
+        return (lp - 2.0 * (math.log(2.0) - raw - np.log1p(np.exp(-2.0 * raw)))).sum(-1), loc, scale
+
+    for s_, r in zip(snaps, results):
+        f = s_["fields"]
+        tr = {k: s_["static"][:, sl] for k, sl in f.items()}
+        nz = lambda x: (x - s_["mean"]) / s_["std"]
+        alpha = math.exp(s_["log_alpha"])
+        logits = mlp_np(s_["pol"], nz(tr["observation"]))
+        loc, scale = logits[:, :A], np.log1p(np.exp(logits[:, A:])) + 0.001
+        lp0, _, _ = lp_np(logits, loc + scale * s_["noise"][0])
+        alpha_loss = np.mean(alpha * (-lp0 + 0.5 * A))
+        nlogits = mlp_np(s_["pol"], nz(tr["next_observation"]))
+        raw = nlogits[:, :A] + (np.log1p(np.exp(nlogits[:, A:])) + 0.001) * s_["noise"][1]
+        nlp, _, _ = lp_np(nlogits, raw)
+        xq = np.concatenate([nz(tr["next_observation"]), np.tanh(raw)], -1)
+        next_v = np.minimum(mlp_np(s_["t1"], xq)[:, 0], mlp_np(s_["t2"], xq)[:, 0]) - alpha * nlp
+        tq = tr["reward"][:, 0] * 0.1 + tr["discount"][:, 0] * 0.96 * next_v
+        xo = np.concatenate([nz(tr["observation"]), tr["action"]], -1)
+        err = (np.stack([mlp_np(s_["q1"], xo)[:, 0], mlp_np(s_["q2"], xo)[:, 0]], -1) - tq[:, None]) * (1 - tr["truncation"])
+        critic_loss = 0.5 * np.mean(err ** 2)
+        raw2 = loc + scale * s_["noise"][2]
+        alp, _, _ = lp_np(logits, raw2)
+        xa = np.concatenate([nz(tr["observation"]), np.tanh(raw2)], -1)
+        actor_loss = np.mean(alpha * alp - np.minimum(mlp_np(s_["q1"], xa)[:, 0], mlp_np(s_["q2"], xa)[:, 0]))
+        assert r["alpha_loss"] == pytest.approx(alpha_loss, rel=1e-4, abs=1e-5)
+        assert r["critic_loss"] == pytest.approx(critic_loss, rel=1e-4, abs=1e-6)
+        assert r["actor_loss"] == pytest.approx(actor_loss, rel=1e-4, abs=1e-5)
+        assert r["alpha"] == pytest.approx(alpha, rel=1e-6)
+        # polyak: target <- (1 - tau) target + tau * NEW q
+        for lt0, lt1, lq1 in zip(s_["t1"].layers, r["t1"].layers, r["q1"].layers):
+            np.testing.assert_allclose(lt1["weight"], (1 - tau) * lt0["weight"] + tau * lq1["weight"], rtol=1e-5, atol=1e-7)

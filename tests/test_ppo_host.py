@@ -126,9 +126,14 @@ def test_policy_params_training_validation_matches_reference():
     with pytest.raises(ValueError, match="unsupported algorithm 'td3'"):
         RP.policy_params_training(None, past_states=z, past_actions=np.zeros((3, 5)), past_next_states_real=z,
                                   past_next_states_sim=z, current_next_states_sim=z, algorithm="TD3")
-    with pytest.raises(NotImplementedError, match="Orbax"):
-        RP.policy_params_training(None, past_states=z, past_actions=np.zeros((3, 5)), past_next_states_real=z,
-                                  past_next_states_sim=z, current_next_states_sim=z, restore_checkpoint_path="/x")
+    kw = dict(past_states=z, past_actions=np.zeros((3, 5)), past_next_states_real=z, past_next_states_sim=z,
+              current_next_states_sim=z)
+    with pytest.raises(NotImplementedError, match="Orbax"):  # a directory = an Orbax PyTreeCheckpointer checkpoint
+        RP.policy_params_training(None, restore_checkpoint_path=os.path.dirname(os.path.abspath(__file__)), **kw)
+    with pytest.raises(ValueError, match="SAC cannot resume"):  # rsr_pipeline.py:399-403
+        RP.policy_params_training(None, algorithm="sac", restore_checkpoint_path="/x", **kw)
+    with pytest.raises(TypeError, match="unexpected keyword argument 'entropy_costs'"):  # nothing is dropped silently
+        RP.policy_params_training(None, entropy_costs=1.0, **kw)
     with pytest.raises(ValueError, match="RSR datasets must have equal lengths"):
         RP.build_policy_rsr_data(z, np.zeros((4, 5)), z, z, z)
     with pytest.raises(ValueError, match="real next-state width must match state width"):
