@@ -156,7 +156,10 @@ int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, const rsrx_
  * loss = loss_scale * divergence * distance.
  * out_host-free: out[0]=loss, out[1]=distance (device).  grad_batch may be NULL;
  * otherwise it receives d loss / d batch [Nb][D] (callers slice the action
- * columns, the only ones a policy gradient flows through). */
+ * columns, the only ones a policy gradient flows through).  Two launches on
+ * `stream` (KDE + tail, gradient) sharing a library-owned per-device scratch
+ * ((Nref + Nb) * M floats, grown the first time a larger size is seen: call once
+ * before capturing a CUDA graph; calls on one device must be stream-ordered). */
 int rsrx_rsr_loss(const float* grid, int M, int D, const float* reference_data, int Nref, const float* batch, int Nb,
                   const float* reference_density, float bandwidth, float divergence, float loss_scale,
                   float* density_out, float* out, float* grad_batch, void* stream);
