@@ -206,6 +206,34 @@ int rsrx_ppo_head(const float* logits, const float* baseline, const float* boots
                   float clipping_epsilon, float entropy_cost, int normalize_advantage, float* workspace, float* out,
                   float* grad_logits, float* grad_baseline, void* stream);
 
+/* ---- tensor-core linear layers for the trainers' value networks (csrc/rsrx_gemm.cuh: tcgen05.mma kind::tf32, fp32
+ * accumulation in TMEM, fused epilogues).  Replaces torch.addmm + SiLU + SiLU' + bias-gradient launches of the value
+ * MLP of RSR/train.py (brax make_ppo_networks, value_hidden_layer_sizes (256,)*5) / the critics of RSR/sac_train.py.
+ * Row-major device float32 arrays; every pointer 16-byte aligned, every leading dimension a multiple of 4.
+ * activation: 0 none, 1 silu (brax swish), 2 relu.
+ *   forward : z[M][N] = x[M][K] w[N][K]^T + bias (z may be NULL), y = act(z)
+ *   dgrad   : dzprev[M][Nin] = (dz[M][Nout] w[Nout][Nin]) * act'(zprev), and, if colsum_partials != NULL, the column sums
+ *             of dzprev over each block of 128 rows -> colsum_partials[ceil(M/128)][ld] (the previous layer's bias
+ *             gradient, finished by rsrx_reduce_partials)
+ *   wgrad   : partials[s][Nout][ldp] = dz[rows_s][Nout]^T x[rows_s][Nin] for row slices of rows_per_split rows
+ *             (ceil(rows / rows_per_split) slices); summed in slice order by rsrx_reduce_partials: deterministic
+ *   reduce  : out_k[i] = sum_{s < S_k} in_k[s * stride_k + i], i < n_k, for up to 24 segments in one launch; in / out /
+ *             n / S / stride are HOST arrays
+ *   value_head_backward: the scalar output layer v = h . w + b fused with the last hidden layer's activation derivative:
+ *             dz[m][j] = g[m] w[j] act'(z[m][j]) and per-128-row partials of colsum(dz), dw[j] = sum g[m] h[m][j],
+ *             db = sum g[m] (colsum_partials [blocks][ld], dw_partials [blocks][n], db_partials [blocks]) */
+int rsrx_linear_forward(const float* x, int ldx, const float* w, int ldw, const float* bias, int M, int N, int K,
+                        int activation, float* z, float* y, int ldy, void* stream);
+int rsrx_linear_dgrad(const float* dz, int lddz, const float* w, int ldw, const float* zprev, int M, int Nin, int Nout,
+                      int activation, float* dzprev, int ld, float* colsum_partials, void* stream);
+int rsrx_linear_wgrad(const float* dz, int lddz, const float* x, int ldx, int rows, int Nout, int Nin, int rows_per_split,
+                      float* partials, int ldp, void* stream);
+int rsrx_reduce_partials(const float* const* in, float* const* out, const int32_t* n, const int32_t* S,
+                         const int64_t* stride, int nseg, void* stream);
+int rsrx_value_head_backward(const float* g, const float* w, const float* z, const float* h, int M, int n, int ld,
+                             int activation, float* dz, float* colsum_partials, float* dw_partials, float* db_partials,
+                             void* stream);
+
 const char* rsrx_last_error(void);
 const char* rsrx_version(void);
 

@@ -10,6 +10,7 @@
 #include "rsrx_env.cuh"
 #include "rsrx_loss.cuh"
 #include "rsrx_ppo.cuh"
+#include "rsrx_gemm.cuh"
 #include "rsrx_redo.h"
 
 using namespace rsrx;
@@ -617,4 +618,82 @@ extern "C" int rsrx_rsr_loss(const float* grid, int M, int D, const float* refer
                       density_out, out, grad_batch, (cudaStream_t)stream)
              ? fail(std::string("rsrx_rsr_loss: ") + cudaGetErrorString(cudaGetLastError()))
              : 0;
+}
+
+// ---- tensor-core linear layers (csrc/rsrx_gemm.cuh) -----------------------------------------------------------------
+static int gemm_check(const char* what, const void* a, const void* b, int lda, int ldb) {
+  if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || (lda & 3) || (ldb & 3))
+    return fail(std::string(what) + ": operands must be 16-byte aligned with leading dimensions that are multiples of 4");
+  return 0;
+}
+
+extern "C" int rsrx_linear_forward(const float* x, int ldx, const float* w, int ldw, const float* bias, int M, int N, int K,
+                                   int activation, float* z, float* y, int ldy, void* stream) {
+  if (!x || !w || !y) return fail("rsrx_linear_forward: null argument");
+  if (M <= 0 || N <= 0 || K <= 0 || (K & 3) || activation < 0 || activation > 2) return fail("rsrx_linear_forward: bad sizes (K % 4 == 0)");
+  if (gemm_check("rsrx_linear_forward", x, w, ldx, ldw)) return 1;
+  gemm::Params p{};
+  p.A = x; p.a_row = ldx; p.a_col = 1; p.B = w; p.b_row = ldw; p.b_col = 1; p.M = M; p.N = N; p.K = K; p.k_split = K;
+  p.epilogue = gemm::EPI_BIAS_ACT; p.act = activation; p.bias = bias; p.D = y; p.Z = z; p.ldd = ldy;
+  CUDA_OK(gemm::launch(p, 0, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int rsrx_linear_dgrad(const float* dz, int lddz, const float* w, int ldw, const float* zprev, int M, int Nin, int Nout,
+                                 int activation, float* dzprev, int ld, float* colsum_partials, void* stream) {
+  if (!dz || !w || !dzprev) return fail("rsrx_linear_dgrad: null argument");
+  if (M <= 0 || Nin <= 0 || Nout <= 0 || (Nout & 3) || (Nin & 3) || activation < 0 || activation > 2 || (activation && !zprev))
+    return fail("rsrx_linear_dgrad: bad sizes");
+  if (gemm_check("rsrx_linear_dgrad", dz, w, lddz, ldw)) return 1;
+  gemm::Params p{};
+  p.A = dz; p.a_row = lddz; p.a_col = 1;          // [M][Nout], contraction over the layer's outputs
+  p.B = w; p.b_row = 1; p.b_col = ldw;            // B[k'][n'] = w[n'][k']
+  p.M = M; p.N = Nin; p.K = Nout; p.k_split = Nout;
+  p.epilogue = gemm::EPI_DGRAD; p.act = activation; p.zprev = zprev; p.D = dzprev; p.colsum = colsum_partials; p.ldd = ld;
+  CUDA_OK(gemm::launch(p, 1, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int rsrx_linear_wgrad(const float* dz, int lddz, const float* x, int ldx, int rows, int Nout, int Nin,
+                                 int rows_per_split, float* partials, int ldp, void* stream) {
+  if (!dz || !x || !partials) return fail("rsrx_linear_wgrad: null argument");
+  if (rows <= 0 || Nout <= 0 || Nin <= 0 || (Nout & 3) || (Nin & 3) || rows_per_split <= 0 || (rows_per_split % gemm::BK))
+    return fail("rsrx_linear_wgrad: bad sizes (rows_per_split % 32 == 0)");
+  if (gemm_check("rsrx_linear_wgrad", dz, x, lddz, ldx)) return 1;
+  gemm::Params p{};
+  p.A = dz; p.a_row = 1; p.a_col = lddz;          // A[n'][m] = dz[m][n']
+  p.B = x; p.b_row = 1; p.b_col = ldx;            // B[k'][m] = x[m][k']
+  p.M = Nout; p.N = Nin; p.K = rows; p.k_split = rows_per_split;
+  p.epilogue = gemm::EPI_PARTIAL; p.D = partials; p.ldd = ldp;
+  CUDA_OK(gemm::launch(p, 2, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int rsrx_reduce_partials(const float* const* in, float* const* out, const int32_t* n, const int32_t* S,
+                                    const int64_t* stride, int nseg, void* stream) {
+  if (!in || !out || !n || !S || !stride || nseg <= 0 || nseg > gemm::MAXSEG) return fail("rsrx_reduce_partials: 1..24 segments");
+  gemm::ReduceArgs a;
+  a.nseg = nseg;
+  int nmax = 0;
+  for (int k = 0; k < nseg; k++) {
+    if (!in[k] || !out[k] || n[k] <= 0 || S[k] <= 0) return fail("rsrx_reduce_partials: bad segment");
+    a.seg[k] = {in[k], out[k], n[k], S[k], (long long)stride[k]};
+    nmax = std::max(nmax, n[k]);
+  }
+  const dim3 grid(std::min((nmax + 255) / 256, 64), nseg);
+  gemm::reduce_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rsrx_value_head_backward(const float* g, const float* w, const float* z, const float* h, int M, int n, int ld,
+                                        int activation, float* dz, float* colsum_partials, float* dw_partials,
+                                        float* db_partials, void* stream) {
+  if (!g || !w || !h || !dz || !colsum_partials || !dw_partials || !db_partials || (activation && !z))
+    return fail("rsrx_value_head_backward: null argument");
+  if (M <= 0 || n <= 0 || ld < n || activation < 0 || activation > 2) return fail("rsrx_value_head_backward: bad sizes");
+  gemm::head_backward_kernel<<<(M + 127) / 128, 256, 0, (cudaStream_t)stream>>>(g, w, z, h, M, n, ld, activation, dz,
+                                                                                colsum_partials, dw_partials, db_partials);
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }

@@ -423,6 +423,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           policy_hidden=(32,) * 4, value_hidden=(256,) * 5,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None,
           use_cuda_graph: bool = True, fused_head: bool = True, allow_tf32: bool = True, graph_collect: bool = True,
+          epoch_graph: bool = True,
           max_training_steps: Optional[int] = None, num_resets_per_eval: int = 0, deterministic_eval: bool = False,
           eval_env=None, policy_params_fn: Callable[..., None] = lambda *a: None, run_evals: bool = True,
           training_step_fn: Optional[Callable[[int, Dict[str, float]], None]] = None,
@@ -496,6 +497,10 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     act_noise = torch.empty(n_unrolls, T, num_envs, act_size, device=dev)  # N(0,1) of the behaviour policy, per unroll step
     action_buf = torch.empty(num_envs, act_size, device=dev)
 
+    # the unrolls re-laid out as [B = n_unrolls * N sequences, T, ...]: fixed buffers, so that the SGD epoch graph can
+    # bake their addresses in
+    batch_static = {k: torch.empty(B, T, *v.shape[3:], device=dev) for k, v in buf.items()}
+
     @torch.no_grad()
     def collect_body():
         for u in range(n_unrolls):
@@ -510,6 +515,9 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                 buf["reward"][u, t].copy_(state.reward)
                 buf["discount"][u, t].copy_(1 - state.done)
                 buf["truncation"][u, t].copy_(state.info["truncation"])
+        # [n_unrolls, T, N, ...] -> [B = n_unrolls * N, T, ...]
+        for k, v in buf.items():
+            batch_static[k].view(n_unrolls, num_envs, T, *v.shape[3:]).copy_(v.permute(0, 2, 1, *range(3, v.dim())))
 
     collect_graph = None
 
@@ -522,8 +530,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             collect_graph.replay()
         else:
             collect_body()
-        # [n_unrolls, T, N, ...] -> [B = n_unrolls * N, T, ...]
-        return {k: v.permute(0, 2, 1, *range(3, v.dim())).reshape(B, T, *v.shape[3:]) for k, v in buf.items()}
+        return batch_static
 
     mb = B // num_minibatches
     static = {k: torch.empty(mb, T, *v.shape[3:], device=dev) for k, v in buf.items()}
@@ -535,11 +542,20 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                    rsr_loss_scale=rsr_loss_scale)
     last_metrics: Dict[str, torch.Tensor] = {}
 
-    def fwd_bwd():
+    def fwd_bwd(noise=None):
         opt.zero_grad(set_to_none=True)
-        loss, metrics = loss_fn(net, normalize, static, static_noise, **loss_kw)
+        loss, metrics = loss_fn(net, normalize, static, static_noise if noise is None else noise, **loss_kw)
         loss.backward()
         return metrics
+
+    # One graph for the whole SGD phase of a training step: num_updates_per_batch x num_minibatches minibatch steps, each
+    # = gather + forward/backward + gradient all-reduce (NCCL is graph-capturable) + Adam, replayed with fresh
+    # permutations and entropy noise written into fixed buffers beforehand.  One launch from the host instead of
+    # ~1000 (the update was launch-bound: 0.43 ms per minibatch step for ~40 small kernels).
+    n_mb_steps = num_updates_per_batch * num_minibatches
+    epoch_graph_enabled = bool(epoch_graph and use_cuda_graph)
+    perm_all = torch.empty(num_updates_per_batch, B, dtype=torch.int64, device=dev)
+    noise_all = torch.empty(n_mb_steps, *static_noise.shape, device=dev) if epoch_graph_enabled else None
 
     graph_bwd = graph_opt = None
     if use_cuda_graph:
@@ -566,12 +582,13 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             for v in st_.values():
                 if torch.is_tensor(v):
                     v.zero_()
-        graph_bwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph_bwd):
-            last_metrics = fwd_bwd()
-        graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph_opt):
-            opt.step()
+        if not epoch_graph_enabled:
+            graph_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_bwd):
+                last_metrics = fwd_bwd()
+            graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_opt):
+                opt.step()
         if graph_collect_enabled:
             # capture only records: the env state is not advanced here; env.step is a plain launch on the capture stream
             collect_graph = torch.cuda.CUDAGraph()
@@ -585,13 +602,53 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     _dst = (C.c_void_p * _nf)(*[static[k].data_ptr() for k in _keys])
     _widths = (C.c_int32 * _nf)(*[static[k][0].numel() for k in _keys])
 
-    def minibatch_step(batch, idx):
-        nonlocal last_metrics
+    def gather_minibatch(batch, idx):
         # all seven fields of the minibatch in one gather launch (rows = sequences of T transitions)
         src = (C.c_void_p * _nf)(*[batch[k].data_ptr() for k in _keys])
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().rsrx_gather_rows(src, _dst, _widths, _nf, idx.data_ptr(), mb,
                                                    torch.cuda.current_stream(dev).cuda_stream), "rsrx_gather_rows")
+
+    sgd_epoch_graph = None
+    if epoch_graph_enabled:
+        perm_all.copy_(torch.arange(B, device=dev).expand(num_updates_per_batch, B))
+        noise_all.zero_()
+        for v in batch_static.values():
+            v.zero_()
+        batch_static["discount"].fill_(1.0)
+        saved = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        sgd_epoch_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(sgd_epoch_graph):
+            k_ = 0
+            for u_ in range(num_updates_per_batch):
+                for m_ in range(num_minibatches):
+                    gather_minibatch(batch_static, perm_all[u_, m_ * mb:(m_ + 1) * mb])
+                    last_metrics = fwd_bwd(noise_all[k_])
+                    _flat_allreduce_mean(params)
+                    opt.step()
+                    k_ += 1
+        # capture only records; make sure nothing of the set-up leaks into the parameters / optimiser state
+        net.load_state_dict(saved)
+        for st_ in opt.state.values():
+            for v in st_.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+
+    def sgd_epoch(batch):
+        """the SGD phase of one training step (RSR/train.py:279-299): num_updates_per_batch shuffles x num_minibatches"""
+        for u_ in range(num_updates_per_batch):
+            perm_all[u_].copy_(torch.randperm(B, device=dev, generator=gen))
+        if sgd_epoch_graph is not None:
+            noise_all.normal_(generator=gen)
+            sgd_epoch_graph.replay()
+            return
+        for u_ in range(num_updates_per_batch):
+            for m_ in range(num_minibatches):
+                minibatch_step(batch, perm_all[u_, m_ * mb:(m_ + 1) * mb])
+
+    def minibatch_step(batch, idx):
+        nonlocal last_metrics
+        gather_minibatch(batch, idx)
         static_noise.normal_(generator=gen)
         if graph_bwd is not None:
             graph_bwd.replay()
@@ -634,10 +691,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         ev[1].record()
         if normalize_observations:
             norm.update(data["observation"])
-        for _ in range(num_updates_per_batch):
-            perm = torch.randperm(B, device=dev, generator=gen)
-            for m_ in range(num_minibatches):
-                minibatch_step(data, perm[m_ * mb:(m_ + 1) * mb])
+        sgd_epoch(data)
         ev[2].record()
         torch.cuda.synchronize(dev)
         dt = time.time() - t0
