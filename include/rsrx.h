@@ -234,6 +234,30 @@ int rsrx_value_head_backward(const float* g, const float* w, const float* z, con
                              int activation, float* dz, float* colsum_partials, float* dw_partials, float* db_partials,
                              void* stream);
 
+/* ---- the trainers' policy network (brax make_ppo_networks policy_hidden_layer_sizes (32,)*4; csrc/rsrx_mlp.cuh):
+ * an MLP with every width <= 32 and <= 8 layers, hidden activation 1 silu / 2 relu, linear output, one warp per row.
+ * weights[l] is [widths[l+1]][widths[l]] row-major (torch nn.Linear), biases[l] [widths[l+1]]; weights / biases / widths
+ * are HOST arrays (device pointers / ints).
+ *   forward : out[rows][ldo] = MLP(x[rows][ldx]); zs [nlayers-1][rows][32] receives the hidden pre-activations
+ *   backward: from grad_out [rows][ldg] and zs, one partial gradient vector per CTA in parameter order (W_0, b_0, W_1,
+ *             b_1, ...): partials [rsrx_small_mlp_backward_ctas(rows)][total]; finish with rsrx_reduce_partials */
+int rsrx_small_mlp_forward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
+                           int activation, const float* x, int ldx, int rows, float* zs, float* out, int ldo, void* stream);
+int rsrx_small_mlp_backward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
+                            int activation, const float* x, int ldx, int rows, const float* zs, const float* grad_out, int ldg,
+                            float* partials, void* stream);
+int rsrx_small_mlp_backward_ctas(int rows);
+
+/* Adam (torch.optim.Adam / optax.adam semantics: bias-corrected moments, no weight decay) on up to 32 tensors in ONE
+ * launch — the optimiser step of RSR/train.py:244-262 (optax.adam(learning_rate)) for the trainers' small networks.
+ * params / grads / exp_avg / exp_avg_sq / sizes are HOST arrays of device pointers / element counts; the gradient is read
+ * as grads[k][i] * grad_scale (1 / world_size after a sum all-reduce).  step_ticket: one device uint64, zero before the
+ * first step, advanced by the kernel itself (so a captured CUDA graph keeps counting on every replay); the number of
+ * steps taken is *step_ticket / (8 * ntensors): keep ntensors fixed for a given ticket. */
+int rsrx_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const int32_t* sizes, int ntensors, float lr, float beta1, float beta2, float eps, float grad_scale,
+                   uint64_t* step_ticket, void* stream);
+
 const char* rsrx_last_error(void);
 const char* rsrx_version(void);
 

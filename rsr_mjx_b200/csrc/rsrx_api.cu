@@ -11,6 +11,7 @@
 #include "rsrx_loss.cuh"
 #include "rsrx_ppo.cuh"
 #include "rsrx_gemm.cuh"
+#include "rsrx_mlp.cuh"
 #include "rsrx_redo.h"
 
 using namespace rsrx;
@@ -621,6 +622,10 @@ extern "C" int rsrx_rsr_loss(const float* grid, int M, int D, const float* refer
 }
 
 // ---- tensor-core linear layers (csrc/rsrx_gemm.cuh) -----------------------------------------------------------------
+static unsigned long long* gemm_dbg() {  // RSRX_GEMM_STAMPS = device address of 8 uint64 (profiling aid)
+  const char* d = getenv("RSRX_GEMM_STAMPS");
+  return d ? reinterpret_cast<unsigned long long*>(strtoull(d, nullptr, 10)) : nullptr;
+}
 static int gemm_check(const char* what, const void* a, const void* b, int lda, int ldb) {
   if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || (lda & 3) || (ldb & 3))
     return fail(std::string(what) + ": operands must be 16-byte aligned with leading dimensions that are multiples of 4");
@@ -635,6 +640,8 @@ extern "C" int rsrx_linear_forward(const float* x, int ldx, const float* w, int 
   gemm::Params p{};
   p.A = x; p.a_row = ldx; p.a_col = 1; p.B = w; p.b_row = ldw; p.b_col = 1; p.M = M; p.N = N; p.K = K; p.k_split = K;
   p.epilogue = gemm::EPI_BIAS_ACT; p.act = activation; p.bias = bias; p.D = y; p.Z = z; p.ldd = ldy;
+  if (((uintptr_t)y & 15) || ((uintptr_t)z & 15) || (ldy & 3)) return fail("rsrx_linear_forward: outputs must be 16-byte aligned, ldy % 4 == 0");
+  p.dbg_t = gemm_dbg();
   CUDA_OK(gemm::launch(p, 0, (cudaStream_t)stream));
   return 0;
 }
@@ -650,6 +657,8 @@ extern "C" int rsrx_linear_dgrad(const float* dz, int lddz, const float* w, int 
   p.B = w; p.b_row = 1; p.b_col = ldw;            // B[k'][n'] = w[n'][k']
   p.M = M; p.N = Nin; p.K = Nout; p.k_split = Nout;
   p.epilogue = gemm::EPI_DGRAD; p.act = activation; p.zprev = zprev; p.D = dzprev; p.colsum = colsum_partials; p.ldd = ld;
+  if (((uintptr_t)dzprev & 15) || ((uintptr_t)zprev & 15) || (ld & 3)) return fail("rsrx_linear_dgrad: outputs must be 16-byte aligned, ld % 4 == 0");
+  p.dbg_t = gemm_dbg();
   CUDA_OK(gemm::launch(p, 1, (cudaStream_t)stream));
   return 0;
 }
@@ -665,6 +674,8 @@ extern "C" int rsrx_linear_wgrad(const float* dz, int lddz, const float* x, int 
   p.B = x; p.b_row = 1; p.b_col = ldx;            // B[k'][m] = x[m][k']
   p.M = Nout; p.N = Nin; p.K = rows; p.k_split = rows_per_split;
   p.epilogue = gemm::EPI_PARTIAL; p.D = partials; p.ldd = ldp;
+  if (((uintptr_t)partials & 15) || (ldp & 3)) return fail("rsrx_linear_wgrad: partials must be 16-byte aligned, ldp % 4 == 0");
+  p.dbg_t = gemm_dbg();
   CUDA_OK(gemm::launch(p, 2, (cudaStream_t)stream));
   return 0;
 }
@@ -692,8 +703,84 @@ extern "C" int rsrx_value_head_backward(const float* g, const float* w, const fl
   if (!g || !w || !h || !dz || !colsum_partials || !dw_partials || !db_partials || (activation && !z))
     return fail("rsrx_value_head_backward: null argument");
   if (M <= 0 || n <= 0 || ld < n || activation < 0 || activation > 2) return fail("rsrx_value_head_backward: bad sizes");
-  gemm::head_backward_kernel<<<(M + 127) / 128, 256, 0, (cudaStream_t)stream>>>(g, w, z, h, M, n, ld, activation, dz,
+  if ((n & 3) || (ld & 3)) return fail("rsrx_value_head_backward: n and ld must be multiples of 4");
+  gemm::head_backward_kernel<<<dim3((M + 127) / 128, (n + 63) / 64), 256, 0, (cudaStream_t)stream>>>(g, w, z, h, M, n, ld, activation, dz,
                                                                                 colsum_partials, dw_partials, db_partials);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rsrx_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                              const int32_t* sizes, int ntensors, float lr, float beta1, float beta2, float eps,
+                              float grad_scale, uint64_t* step_ticket, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !sizes || !step_ticket) return fail("rsrx_adam_step: null argument");
+  if (ntensors <= 0 || ntensors > gemm::ADAM_MAXSEG) return fail("rsrx_adam_step: 1..32 tensors");
+  gemm::AdamArgs a;
+  a.nseg = ntensors; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
+  a.ticket = reinterpret_cast<unsigned long long*>(step_ticket);
+  for (int k = 0; k < ntensors; k++) {
+    if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || sizes[k] <= 0) return fail("rsrx_adam_step: bad tensor");
+    a.seg[k] = {params[k], grads[k], exp_avg[k], exp_avg_sq[k], sizes[k]};
+  }
+  // a FIXED grid per tensor count: the step count is derived from tickets / blocks (see adam_kernel)
+  const dim3 grid(8, ntensors);
+  gemm::adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- warp-per-row small MLP (csrc/rsrx_mlp.cuh): the trainers' policy network --------------------------------------
+static int small_net(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers, int activation,
+                     smallmlp::Net& net, int* total) {
+  if (!weights || !biases || !widths) return fail("rsrx_small_mlp: null argument");
+  if (nlayers <= 0 || nlayers > smallmlp::MAXL || activation < 0 || activation > 2) return fail("rsrx_small_mlp: 1..8 layers, activation 0..2");
+  int t = 0;
+  for (int l = 0; l <= nlayers; l++)
+    if (widths[l] <= 0 || widths[l] > smallmlp::WD) return fail("rsrx_small_mlp: every width must be 1..32");
+  for (int l = 0; l < nlayers; l++) {
+    if (!weights[l] || !biases[l]) return fail("rsrx_small_mlp: null parameter");
+    net.W[l] = weights[l]; net.b[l] = biases[l];
+    t += widths[l] * widths[l + 1] + widths[l + 1];
+  }
+  for (int l = 0; l <= nlayers; l++) net.width[l] = widths[l];
+  net.nl = nlayers; net.act = activation;
+  if (total) *total = t;
+  return 0;
+}
+static int small_grid(int rows) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return std::max(1, std::min(sms, (rows + smallmlp::WARPS - 1) / smallmlp::WARPS));
+}
+extern "C" int rsrx_small_mlp_backward_ctas(int rows) { return small_grid(rows); }
+
+extern "C" int rsrx_small_mlp_forward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
+                                      int activation, const float* x, int ldx, int rows, float* zs, float* out, int ldo,
+                                      void* stream) {
+  smallmlp::Net net;
+  if (small_net(weights, biases, widths, nlayers, activation, net, nullptr)) return 1;
+  if (!x || !out || (nlayers > 1 && !zs) || rows <= 0) return fail("rsrx_small_mlp_forward: bad arguments");
+  const size_t smem = smallmlp::fwd_smem(nlayers);
+  static bool set = false;
+  if (!set) { CUDA_OK(cudaFuncSetAttribute(smallmlp::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smallmlp::fwd_smem(smallmlp::MAXL))); set = true; }
+  smallmlp::forward_kernel<<<small_grid(rows), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, out, ldo);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rsrx_small_mlp_backward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
+                                       int activation, const float* x, int ldx, int rows, const float* zs, const float* grad_out,
+                                       int ldg, float* partials, void* stream) {
+  smallmlp::Net net;
+  int total = 0;
+  if (small_net(weights, biases, widths, nlayers, activation, net, &total)) return 1;
+  if (!x || !grad_out || !partials || (nlayers > 1 && !zs) || rows <= 0) return fail("rsrx_small_mlp_backward: bad arguments");
+  const size_t smem = smallmlp::bwd_smem(nlayers);
+  if (smem > 227 * 1024) return fail("rsrx_small_mlp_backward: too many layers for the shared-memory accumulators");
+  static bool set = false;
+  if (!set) { CUDA_OK(cudaFuncSetAttribute(smallmlp::backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+  smallmlp::backward_kernel<<<small_grid(rows), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, grad_out, ldg,
+                                                                                                 partials, total);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -13,23 +13,28 @@
 //             deterministic, no atomics)
 //
 // Structure (deliberately plain: these GEMMs are 0.4 GFLOP, 44-88 CTAs, latency-bound):
-//   CTA = 128 threads, tile 128 x BN x 32, accumulators in TMEM (BN columns), 2 shared-memory stages.
-//   All threads stage the operand tiles global -> registers -> shared memory in the canonical no-swizzle UMMA layout
+//   CTA = 128 threads, tile 128 x BN, accumulators in TMEM (BN columns).  The whole contraction slice (<= 256) of both
+//   operands is staged at once (192 KB of shared memory), so all global loads of a CTA are in flight together.
+//   All threads stage the operand tiles (cp.async, or loads + transposing stores) in the canonical no-swizzle UMMA layout
 //   (8 x 16-byte core matrices, K-major: ((8,n),2):((16B,SBO),LBO); operands whose global layout is contiguous along
 //   M/N instead of K are transposed in flight),
-//   fence.proxy.async, one elected thread issues 4 x tcgen05.mma.kind::tf32 (K = 8 each) and tcgen05.commit's them to the
-//   stage's mbarrier; the next fill of that stage waits on it.  Epilogue: tcgen05.ld 32x32b (thread = accumulator row),
-//   fused bias / activation / activation-derivative / column sums, row-major stores.
+//   fence.proxy.async, one elected thread issues up to 32 x tcgen05.mma.kind::tf32 (K = 8 each) and tcgen05.commit's them
+//   to an mbarrier.  Epilogue: tcgen05.ld 32x32b (thread = accumulator row) -> padded shared memory -> fused bias /
+//   activation / activation-derivative / column sums with row-contiguous 16-byte global accesses.
 //   No TMA: the operands are small, L2-resident activations whose rows are not all 16-byte multiples apart; plain
 //   coalesced 16-byte loads keep the kernel free of tensor-map plumbing.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 namespace rsrx {
 namespace gemm {
 
-constexpr int BM = 128, BK = 32, THREADS = 128, STAGES = 2;
+// 16 warps per CTA: the tensor-core part needs one thread, but staging the operands and the fused epilogue are SIMT work
+// whose latency shrinks with the number of warps an SM has to interleave (4 warps: 15 us per launch, 16 warps: see profiles/)
+constexpr int BM = 128, BK = 32, THREADS = 512;
 constexpr int UMMA_K = 8;  // tf32
 
 enum Epilogue { EPI_BIAS_ACT = 0, EPI_DGRAD = 1, EPI_PARTIAL = 2 };
@@ -47,7 +52,16 @@ struct Params {
   float* Z;                           // [M][ldd]       (EPI_BIAS_ACT: pre-activation, may be null)
   float* colsum;                      // [gridDim.x][ldd] (EPI_DGRAD: per-CTA column sums of dZprev, may be null)
   int ldd;
+  int kcap;                           // contraction length staged at once (multiple of 32, <= KMAX): sizes the shared memory
+  unsigned long long* dbg_t;          // profiling aid: 8 globaltimer stamps of CTA 0 (nullptr = off)
 };
+__device__ __forceinline__ void stamp(const Params& p, int i) {
+  if (p.dbg_t && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg_t[i] = t;
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -85,179 +99,227 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
 
-// Stage one operand tile (ROWS x BK, row index = the operand's M/N index, column = contraction index) into shared memory.
-// The shared-memory image is always K-major: core matrix = 8 rows x 16 B; element (r, k) at byte
-//       (r % 8) * 16 + (r / 8) * SBO + (k / 4) * 128 + (k % 4) * 4,  SBO = BK / 4 * 128, LBO = 128.
-//   MN_MAJOR = false: global memory contiguous along the contraction: 16-byte loads land as they are;
-//   MN_MAJOR = true: global memory contiguous along the row index: transposed in flight (see below).
-// Rows >= rows_valid and contraction indices >= k_valid are zero-filled.  16-byte global loads: the contiguous stride
-// is 1 and every row / k start is 16-byte aligned (host-checked).
+// Stage one operand tile (ROWS x KB, row index = the operand's M/N index, column = contraction index) into shared memory.
+// The shared-memory image is always K-major, no swizzle: core matrix = 8 rows x 16 B; element (r, k) at byte
+//       (r % 8) * 16 + (r / 8) * SBO + (k / 4) * 128 + (k % 4) * 4,  SBO = KB / 4 * 128, LBO = 128.
+//   MN_MAJOR = false: global memory contiguous along the contraction: 16-byte cp.async straight into place.  Lane bits
+//       [0:2] row & 7, [3:4] chunk & 3: a quarter warp fills the 8 rows of one core matrix (distinct banks), a warp reads
+//       8 rows x 64 contiguous bytes (whole sectors);
+//   MN_MAJOR = true: global memory contiguous along the row index: 16-byte loads of 4 rows at one contraction index,
+//       transposed on the way in (4 scalar stores, issued in an order rotated by (k >> 2) & 3 so that the 32 lanes of one
+//       store instruction hit 32 distinct banks).  Lane bits [0:1] k & 3, [2] chunk parity, [3:4] (k >> 2) & 3.
+// Rows >= rows_valid and contraction indices >= k_valid are zero-filled.  The contiguous stride is 1 and every row / k
+// start is 16-byte aligned (host-checked).  kb: contraction length of this block (multiple of 32, <= KMAX).
 template <int ROWS, bool MN_MAJOR>
 __device__ __forceinline__ void stage_tile(float* smem, const float* __restrict__ g, int row_stride, int col_stride, int row0,
-                                           int k0, int rows_valid, int k_valid) {
+                                           int k0, int rows_valid, int k_valid, int kb) {
   const int tid = threadIdx.x;
+  const int CH = kb >> 2;  // 16-byte chunks per row
   if (!MN_MAJOR) {
-    // thread -> (row, 16-byte chunk of the contraction): 8 consecutive threads take the 8 rows of a core matrix
-    constexpr int CH = BK / 4;  // chunks per row
-#pragma unroll
-    for (int it = 0; it < ROWS * CH / THREADS; ++it) {
-      const int idx = it * THREADS + tid;
-      const int r = idx % ROWS, c = idx / ROWS;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < rows_valid && k0 + c * 4 < k_valid)
-        v = *reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * row_stride + (k0 + c * 4));
-      *reinterpret_cast<float4*>(smem + ((r & 7) * 4 + (r >> 3) * (CH * 32) + c * 32)) = v;
+    const int n = (ROWS / 8) * (CH / 4);  // warp-sized work items
+#pragma unroll 4
+    for (int hi = tid >> 5; hi < n; hi += THREADS / 32) {
+      const int low = tid & 31;
+      const int r = (low & 7) + 8 * (hi % (ROWS / 8)), c = ((low >> 3) & 3) + 4 * (hi / (ROWS / 8));
+      float* dst = smem + ((r & 7) * 4 + (r >> 3) * (CH * 32) + c * 32);
+      if (row0 + r < rows_valid && k0 + c * 4 < k_valid) {
+        const float* src = g + (size_t)(row0 + r) * row_stride + (k0 + c * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   } else {
-    // global memory is contiguous along the row index: 16-byte loads of 4 rows at one contraction index, transposed on
-    // the way into the same K-major image (4 scalar stores).  Lane bits: [0:1] k & 3, [2] chunk parity, [3:4] (k >> 2) & 3
-    // -> a warp reads 16 contraction rows x 32 contiguous bytes; the 4 stores are issued in an order rotated by
-    // (k >> 2) & 3 so that the 32 lanes of one store instruction hit 32 distinct banks.
-    constexpr int CH = BK / 4, RC = ROWS / 4;
+    constexpr int RC = ROWS / 4;
+    constexpr int U = 8;        // loads in flight per thread
+    const int total = RC * kb;  // (4-row chunk, k) items
+    for (int base = tid; base < total; base += THREADS * U) {
+      float4 v[U];
 #pragma unroll
-    for (int it = 0; it < RC * BK / THREADS; ++it) {
-      const int idx = it * THREADS + tid;
-      const int hi = idx >> 5;
-      const int k = (idx & 3) | (((idx >> 3) & 3) << 2) | ((hi & 1) << 4);
-      const int rc = ((idx >> 2) & 1) | ((hi >> 1) << 1);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + rc * 4 < rows_valid && k0 + k < k_valid)
-        v = *reinterpret_cast<const float4*>(g + (size_t)(k0 + k) * col_stride + (row0 + rc * 4));
-      const int r = rc * 4;
-      float* base = smem + ((r >> 3) * (CH * 32) + (k >> 2) * 32 + (k & 3));
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * THREADS, hi = idx >> 5;
+        const int k = (idx & 3) | (((idx >> 3) & 3) << 2) | ((hi % (kb >> 4)) << 4);
+        const int rc = ((idx >> 2) & 1) | ((hi / (kb >> 4)) << 1);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < total && row0 + rc * 4 < rows_valid && k0 + k < k_valid)
+          v[u] = __ldg(reinterpret_cast<const float4*>(g + (size_t)(k0 + k) * col_stride + (row0 + rc * 4)));
+      }
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = (jj + (k >> 2)) & 3;
-        const float x = j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
-        base[((r + j) & 7) * 4] = x;
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * THREADS, hi = idx >> 5;
+        if (idx >= total) break;
+        const int k = (idx & 3) | (((idx >> 3) & 3) << 2) | ((hi % (kb >> 4)) << 4);
+        const int r = (((idx >> 2) & 1) | ((hi / (kb >> 4)) << 1)) * 4;
+        float* base_p = smem + ((r >> 3) * (CH * 32) + (k >> 2) * 32 + (k & 3));
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = (jj + (k >> 2)) & 3;
+          const float x = j == 0 ? v[u].x : (j == 1 ? v[u].y : (j == 2 ? v[u].z : v[u].w));
+          base_p[((r + j) & 7) * 4] = x;
+        }
       }
     }
   }
 }
 
+constexpr int KMAX = 256;  // contraction length held in shared memory at once (A 128 KB + B 64 KB at BN = 64)
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const Params p) {
   extern __shared__ __align__(128) float smem[];
-  float* sA = smem;                                // [STAGES][BM * BK]
-  float* sB = smem + STAGES * BM * BK;             // [STAGES][BN * BK]
-  __shared__ __align__(8) uint64_t bar[STAGES + 1];
+  float* sA = smem;                 // [BM x kcap]
+  float* sB = smem + BM * p.kcap;   // [BN x kcap]
+  __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int kbeg = blockIdx.z * p.k_split;
   const int kend = min(p.K, kbeg + p.k_split);
+  stamp(p, 0);
 
   if (warp == 0) {  // TMEM: BN fp32 accumulator columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s <= STAGES; ++s) mbar_init(&bar[s], 1);
+    mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base_smem;
+  stamp(p, 1);
 
   // instruction descriptor: D fp32, A / B tf32, both K-major in shared memory (operands that are MN-contiguous in global
   // memory are transposed while being staged: a tf32 MN-major descriptor produced zeros on this part), N >> 3, M >> 4
   constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  // K-major, no swizzle: core matrices (8 rows x 16 B) 128 B apart along K (LBO), 8-row groups BK / 4 * 128 B apart (SBO);
-  // one UMMA_K = 8 step covers two core matrices
-  constexpr uint32_t LBO = 128, SBO = (BK / 4) * 128, KSTEP = 2 * 128;
 
-  const int nkb = (kend - kbeg + BK - 1) / BK;
-  uint32_t phase[STAGES] = {0, 0};
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    if (kb >= STAGES) {  // the MMAs that read this stage two k-blocks ago must have retired
-      mbar_wait(&bar[s], phase[s]);
-      phase[s] ^= 1;
+  // The whole contraction slice (<= KMAX) is staged at once — every global load of the CTA is in flight together, one
+  // round trip instead of one per k-block — then 4 .. 32 back-to-back MMAs (K = 8 each) and one commit.  Longer
+  // contractions repeat the cycle (not on the value-network path: K <= 256, wgrad is split into 256-row slices).
+  uint32_t phase = 0;
+  bool first = true;
+  for (int k0 = kbeg; k0 < kend; k0 += p.kcap) {
+    const int kb = min(p.kcap, ((kend - k0) + BK - 1) / BK * BK);
+    if (!first) {  // the previous block's MMAs must have retired before its operands are overwritten
+      mbar_wait(&bar, phase);
+      phase ^= 1;
     }
-    const int k0 = kbeg + kb * BK;
-    stage_tile<BM, A_MN>(sA + s * BM * BK, p.A, p.a_row, p.a_col, m0, k0, p.M, kend);
-    stage_tile<BN, B_MN>(sB + s * BN * BK, p.B, p.b_row, p.b_col, n0, k0, p.N, kend);
+    stage_tile<BM, A_MN>(sA, p.A, p.a_row, p.a_col, m0, k0, p.M, kend, kb);
+    stage_tile<BN, B_MN>(sB, p.B, p.b_row, p.b_col, n0, k0, p.N, kend, kb);
+    stamp(p, 2);
+    asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;");  // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
+    stamp(p, 3);
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t a_addr = smem_u32(sA + s * BM * BK), b_addr = smem_u32(sB + s * BN * BK);
-#pragma unroll
-      for (int k = 0; k < BK / UMMA_K; ++k) {
-        const uint64_t da = make_desc(a_addr + k * KSTEP, LBO, SBO);
-        const uint64_t db = make_desc(b_addr + k * KSTEP, LBO, SBO);
-        const uint32_t accumulate = (kb > 0 || k > 0) ? 1u : 0u;
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      // K-major, no swizzle: core matrices (8 rows x 16 B) 128 B apart along K (LBO), 8-row groups kb / 4 * 128 B apart
+      // (SBO); one UMMA_K = 8 step covers two core matrices
+      const uint32_t SBO = (uint32_t)(kb >> 2) * 128;
+      for (int k = 0; k < kb / UMMA_K; ++k) {
+        const uint64_t da = make_desc(a_addr + k * 256, 128, SBO);
+        const uint64_t db = make_desc(b_addr + k * 256, 128, SBO);
+        const uint32_t accumulate = (!first || k > 0) ? 1u : 0u;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
       }
-      // arrives on the stage barrier when these (and all earlier) MMAs are done; implies fence::before_thread_sync
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[s])) : "memory");
-      if (kb == nkb - 1)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[STAGES])) : "memory");
+      // arrives on the barrier when these (and all earlier) MMAs are done; implies fence::before_thread_sync
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     }
+    first = false;
   }
-  // ---- epilogue: thread = accumulator row (TMEM lane 32 * warp + lane), 16 columns per tcgen05.ld
-  mbar_wait(&bar[STAGES], 0);
+  stamp(p, 4);
+  mbar_wait(&bar, phase);
   asm volatile("tcgen05.fence::after_thread_sync;");
-  const int row = m0 + warp * 32 + lane;
-  const bool row_ok = row < p.M;
-  float* colsum_s = smem;  // [4 warps][BN] (the operand stages are dead now)
-  const size_t split_off = p.epilogue == EPI_PARTIAL ? (size_t)blockIdx.z * p.M * p.ldd : 0;
+  stamp(p, 5);
+
+  // ---- epilogue, pass 1: TMEM -> shared memory (thread = accumulator row = TMEM lane)
+  constexpr int LDS = BN + 1;       // padded: a warp writes 32 rows of one column without bank conflicts
+  float* sC = smem;                 // [BM][LDS] (the operand image is dead now)
+  // warp w reads TMEM lanes 32 * (w % 4) .. + 31 (the only ones it may touch) and column chunks w / 4, w / 4 + 4, ...
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 16) {
+  for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += (THREADS / 128) * 16) {
     uint32_t r[16];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0;
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-    const int col = n0 + c0;
-    if (p.epilogue == EPI_BIAS_ACT) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float z = v[j] + ((p.bias && col + j < p.N) ? p.bias[col + j] : 0.f);
-        if (row_ok && col + j < p.N) {
-          if (p.Z) p.Z[(size_t)row * p.ldd + col + j] = z;
-          p.D[(size_t)row * p.ldd + col + j] = act_fwd(p.act, z);
-        }
-      }
-    } else if (p.epilogue == EPI_DGRAD) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float g = 0.f;
-        if (row_ok && col + j < p.N) {
-          g = v[j] * act_bwd(p.act, p.act ? p.zprev[(size_t)row * p.ldd + col + j] : 0.f);
-          p.D[(size_t)row * p.ldd + col + j] = g;
-        }
-        if (p.colsum) {  // column sum over this warp's 32 rows (fixed shuffle tree: deterministic)
-#pragma unroll
-          for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-          if (lane == 0) colsum_s[warp * BN + c0 + j] = g;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (row_ok && col + j < p.N) p.D[split_off + (size_t)row * p.ldd + col + j] = v[j];
-    }
+    for (int j = 0; j < 16; ++j) sC[((warp & 3) * 32 + lane) * LDS + c0 + j] = __uint_as_float(r[j]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (p.epilogue == EPI_DGRAD && p.colsum) {
-    for (int c = tid; c < BN; c += THREADS)
-      if (n0 + c < p.N)
-        p.colsum[(size_t)blockIdx.x * p.ldd + n0 + c] = ((colsum_s[c] + colsum_s[BN + c]) + colsum_s[2 * BN + c]) + colsum_s[3 * BN + c];
-  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+  stamp(p, 6);
+
+  // ---- pass 2: fused epilogue with row-contiguous global accesses: thread = (row group tid / 16, 4 columns)
+  constexpr int TPR = BN / 4;                 // threads per row
+  constexpr int RPP = THREADS / TPR;          // rows per pass
+  const int cq = (tid % TPR) * 4, rg = tid / TPR;
+  const int col = n0 + cq;
+  const size_t split_off = p.epilogue == EPI_PARTIAL ? (size_t)blockIdx.z * p.M * p.ldd : 0;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.epilogue == EPI_BIAS_ACT && p.bias)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bias4[j] = col + j < p.N ? p.bias[col + j] : 0.f;
+  const bool vec = col + 3 < p.N;  // ldd % 4 == 0 and 16-byte aligned bases (host-checked): whole float4 in range
+#pragma unroll 1
+  for (int rr = rg; rr < BM; rr += RPP) {
+    const int row = m0 + rr;
+    if (row >= p.M) break;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = sC[rr * LDS + cq + j];
+    const size_t off = (size_t)row * p.ldd + col;
+    if (p.epilogue == EPI_BIAS_ACT) {
+      float z[4], y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { z[j] = v[j] + bias4[j]; y[j] = act_fwd(p.act, z[j]); }
+      if (vec) {
+        if (p.Z) *reinterpret_cast<float4*>(p.Z + off) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4*>(p.D + off) = make_float4(y[0], y[1], y[2], y[3]);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (col + j < p.N) { if (p.Z) p.Z[off + j] = z[j]; p.D[off + j] = y[j]; }
+      }
+    } else if (p.epilogue == EPI_DGRAD) {
+      float zp[4] = {0.f, 0.f, 0.f, 0.f}, gg[4];
+      if (p.act) {
+        if (vec) { const float4 t = *reinterpret_cast<const float4*>(p.zprev + off); zp[0] = t.x; zp[1] = t.y; zp[2] = t.z; zp[3] = t.w; }
+        else for (int j = 0; j < 4; ++j) if (col + j < p.N) zp[j] = p.zprev[off + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { gg[j] = (col + j < p.N) ? v[j] * act_bwd(p.act, zp[j]) : 0.f; cs[j] += gg[j]; }
+      if (vec) *reinterpret_cast<float4*>(p.D + off) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      else for (int j = 0; j < 4; ++j) if (col + j < p.N) p.D[off + j] = gg[j];
+    } else {
+      if (vec) *reinterpret_cast<float4*>(p.D + split_off + off) = make_float4(v[0], v[1], v[2], v[3]);
+      else for (int j = 0; j < 4; ++j) if (col + j < p.N) p.D[split_off + off + j] = v[j];
+    }
+  }
+  stamp(p, 7);
+  if (p.epilogue == EPI_DGRAD && p.colsum) {  // column sums over the CTA's rows: row groups combined in a fixed order
+    __syncthreads();
+    float* red = smem + BM * LDS;  // [RPP][BN]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[rg * BN + cq + j] = cs[j];
+    __syncthreads();
+    for (int c = tid; c < BN; c += THREADS) {
+      float t = 0.f;
+      for (int g2 = 0; g2 < RPP; ++g2) t += red[g2 * BN + c];
+      if (n0 + c < p.N) p.colsum[(size_t)blockIdx.x * p.ldd + n0 + c] = t;
+    }
+  }
 }
 
 // out[i] = sum_{s < S} in[s * stride + i] (in order: deterministic) for several segments in one launch
@@ -276,39 +338,102 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
 // Backward of the scalar output layer v = h . w + b of the value network (256 -> 1: too thin for the tensor core) fused
 // with the activation derivative of the last hidden layer:  dZ[m][j] = g[m] w[j] act'(Z[m][j]);  per-128-row-block
 // partials of colsum(dZ) (bias gradient of the last hidden layer), of dw[j] = sum_m g[m] H[m][j] and of db = sum_m g[m].
-// thread = column j (coalesced rows), block = 128 rows.
+// Block = 128 rows x 64 columns: 16 x 16 threads, a thread owns 4 columns (16-byte accesses) of 8 rows; the 16 row lanes
+// are combined through shared memory in a fixed order (deterministic).  n % 4 == 0, ld % 4 == 0.
 __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ g, const float* __restrict__ w,
                                                            const float* __restrict__ Z, const float* __restrict__ H, int M,
                                                            int n, int ld, int act, float* __restrict__ dZ,
                                                            float* __restrict__ colsum, float* __restrict__ dw_part,
                                                            float* __restrict__ db_part) {
-  const int r0 = blockIdx.x * 128, r1 = min(M, r0 + 128);
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const float wj = w[j];
-    float cs = 0.f, dw = 0.f;
-    for (int m = r0; m < r1; ++m) {
-      const float gm = g[m];
-      const float d = gm * wj * act_bwd(act, act ? Z[(size_t)m * ld + j] : 0.f);
-      dZ[(size_t)m * ld + j] = d;
-      cs += d;
-      dw += gm * H[(size_t)m * ld + j];
+  __shared__ float red[2][16][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int r0 = blockIdx.x * 128, col = blockIdx.y * 64 + tx * 4;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f}, dw[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < n) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w + col);
+    const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = r0 + ty + 16 * i;
+      if (m < M) {
+        const float gm = g[m];
+        const size_t off = (size_t)m * ld + col;
+        const float4 h4 = *reinterpret_cast<const float4*>(H + off);
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) z4 = *reinterpret_cast<const float4*>(Z + off);
+        const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          d[j] = gm * wj[j] * act_bwd(act, zz[j]);
+          cs[j] += d[j];
+          dw[j] += gm * hh[j];
+        }
+        *reinterpret_cast<float4*>(dZ + off) = make_float4(d[0], d[1], d[2], d[3]);
+      }
     }
-    colsum[(size_t)blockIdx.x * ld + j] = cs;
-    dw_part[(size_t)blockIdx.x * n + j] = dw;
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[0][ty][tx * 4 + j] = cs[j]; red[1][ty][tx * 4 + j] = dw[j]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+    for (int y = 0; y < 16; ++y) t += red[which][y][c];
+    const int cc = blockIdx.y * 64 + c;
+    if (cc < n) {
+      if (which == 0) colsum[(size_t)blockIdx.x * ld + cc] = t;
+      else dw_part[(size_t)blockIdx.x * n + cc] = t;
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.x >= 128 && threadIdx.x < 160) {  // one warp: db partial of this row block
+    const int lane = threadIdx.x - 128;
+    float sgm = 0.f;
+    for (int m = r0 + lane; m < min(M, r0 + 128); m += 32) sgm += g[m];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sgm += __shfl_xor_sync(0xffffffffu, sgm, o);
+    if (lane == 0) db_part[blockIdx.x] = sgm;
+  }
+}
+
+// Adam on a list of tensors in one launch (torch.optim.Adam semantics, no weight decay / amsgrad): the trainers' networks
+// have ~24 small tensors; torch's multi-tensor kernel takes 40 us on them.  The step count lives on the device so that a
+// captured CUDA graph advances it on every replay: every block takes a ticket from a 64-bit counter, launch k (k = 0, 1,
+// ...) owns tickets [k * blocks, (k + 1) * blocks) — launches on a stream do not overlap — so t = ticket / blocks + 1 in
+// every block without a second kernel or a read/write race.
+struct AdamSeg { float* p; const float* g; float* m; float* v; int n; };
+constexpr int ADAM_MAXSEG = 32;
+struct AdamArgs { AdamSeg seg[ADAM_MAXSEG]; int nseg; float lr, beta1, beta2, eps, grad_scale; unsigned long long* ticket; };
+__global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
+  __shared__ float t_s;
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int m = r0; m < r1; ++m) s += g[m];
-    db_part[blockIdx.x] = s;
+    const unsigned long long blocks = (unsigned long long)gridDim.x * gridDim.y;
+    t_s = (float)(atomicAdd(a.ticket, 1ull) / blocks + 1ull);
+  }
+  __syncthreads();
+  const AdamSeg& sg = a.seg[blockIdx.y];
+  const float t = t_s;
+  const float bc1 = 1.f - powf(a.beta1, t), bc2 = 1.f - powf(a.beta2, t);
+  const float step_size = a.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
+    const float gr = sg.g[i] * a.grad_scale;
+    const float m = a.beta1 * sg.m[i] + (1.f - a.beta1) * gr;
+    const float v = a.beta2 * sg.v[i] + (1.f - a.beta2) * gr * gr;
+    sg.m[i] = m; sg.v[i] = v;
+    sg.p[i] -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
   }
 }
 
 template <int BN, bool A_MN, bool B_MN>
-inline cudaError_t launch_one(const Params& p, dim3 grid, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * STAGES * (BM + BN) * BK;
+inline cudaError_t launch_one(Params p, dim3 grid, cudaStream_t stream) {
+  const int kslice = std::min(p.K, p.k_split);
+  p.kcap = std::min(KMAX, (kslice + BK - 1) / BK * BK);
+  const size_t epi = sizeof(float) * (BM * (BN + 1) + (THREADS / (BN / 4)) * BN);  // epilogue staging + column-sum scratch
+  const size_t smem = std::max(sizeof(float) * (size_t)(BM + BN) * p.kcap, epi);
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(float) * (BM + BN) * KMAX));
     if (e != cudaSuccess) return e;
     set = true;
   }

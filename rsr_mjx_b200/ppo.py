@@ -423,7 +423,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
           policy_hidden=(32,) * 4, value_hidden=(256,) * 5,
           progress_fn: Callable[[int, Dict[str, float]], None] = lambda *a: None,
           use_cuda_graph: bool = True, fused_head: bool = True, allow_tf32: bool = True, graph_collect: bool = True,
-          epoch_graph: bool = True,
+          epoch_graph: bool = True, tensor_core_value: bool = True,
           max_training_steps: Optional[int] = None, num_resets_per_eval: int = 0, deterministic_eval: bool = False,
           eval_env=None, policy_params_fn: Callable[..., None] = lambda *a: None, run_evals: bool = True,
           training_step_fn: Optional[Callable[[int, Dict[str, float]], None]] = None,
@@ -437,6 +437,8 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     epoch (if num_evals > 1) and after every epoch and calls `progress_fn(env_steps, {eval/..., training/...})` and
     `policy_params_fn(env_steps, make_policy, params)`.  `run_evals=False` skips the evaluator (benchmarks),
     `training_step_fn(step, training_metrics)` is called after every training step.
+    `tensor_core_value` (default, with `fused_head` on CUDA): the value network's forward / backward run on the
+    hand-written tcgen05 linear kernels (fused_mlp.py) instead of torch autograd + cuBLAS.
     Reference arguments that configure the run are honoured or raise, never dropped (train_args.py):
     `network_factory` (a functools.partial over make_ppo_networks: its *_hidden_layer_sizes are used),
     `randomization_fn` (installed on the env with the keys RSR/train.py:212-217 derives from `seed`),
@@ -542,11 +544,81 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                    rsr_loss_scale=rsr_loss_scale)
     last_metrics: Dict[str, torch.Tensor] = {}
 
-    def fwd_bwd(noise=None):
+    def fwd_bwd_autograd(noise=None):
         opt.zero_grad(set_to_none=True)
         loss, metrics = loss_fn(net, normalize, static, static_noise if noise is None else noise, **loss_kw)
         loss.backward()
         return metrics
+
+    # ---- value network on the tensor-core kernels: no autograd through it.  Rows of its batch: the mb * T observations
+    # (sequence-major) followed by the mb bootstrap observations, so that baseline / bootstrap / their gradients are
+    # contiguous views.
+    from . import fused_mlp
+    use_tc = bool(tensor_core_value and fused_head and fused_mlp.supported(net.value, dev))
+    vtc = ptc = None
+    if use_tc:
+        rows_v = mb * T + mb
+        vtc = fused_mlp.TensorCoreMLP(net.value, rows_v, dev)
+        if fused_mlp.warp_supported(net.policy, dev):  # the reference's policy (32,)*4: one launch per direction
+            ptc = fused_mlp.WarpMLP(net.policy, mb * T, dev)
+        # one-launch Adam over all ~22 tensors (same update rule as torch.optim.Adam / optax.adam)
+        opt = fused_mlp.FusedAdam(params, lr=learning_rate, eps=1e-8)
+        head_ws = torch.empty(2 * mb * T, device=dev)
+        head_out = torch.empty(4, device=dev)
+        g_logits_buf = torch.empty(mb, T, 2 * act_size, device=dev)
+        g_values_buf = torch.zeros(rows_v, device=dev)  # the bootstrap rows keep a zero gradient (vs is stop-gradient)
+        hyper = (float(reward_scaling), float(discounting), float(gae_lambda), float(clipping_epsilon), float(entropy_cost),
+                 int(bool(normalize_advantage)))
+
+    def fwd_bwd_tc(noise=None):
+        from . import _lib
+        nz = static_noise if noise is None else noise
+        opt.zero_grad(set_to_none=True)
+        vtc.attach_grads()
+        obs = static["observation"]
+        obs_n = normalize(obs)
+        if ptc is not None:
+            ptc.attach_grads()
+            logits = ptc.forward(obs_n.reshape(mb * T, obs_size)).view(mb, T, 2 * act_size)
+        else:
+            logits = net.policy(obs_n)  # autograd fallback for policies wider than 32
+        with torch.no_grad():
+            xval = torch.cat([obs_n.reshape(mb * T, obs_size), normalize(static["next_observation"][:, -1])], dim=0)
+            values = vtc.forward(xval)
+            lg = logits.detach()
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().rsrx_ppo_head(
+                    lg.data_ptr(), values.data_ptr(), values[mb * T:].data_ptr(), static["raw_action"].data_ptr(),
+                    static["log_prob"].data_ptr(), static["reward"].data_ptr(), static["discount"].data_ptr(),
+                    static["truncation"].data_ptr(), nz.data_ptr(), mb, T, act_size, *hyper, head_ws.data_ptr(),
+                    head_out.data_ptr(), g_logits_buf.data_ptr(), g_values_buf.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream), "rsrx_ppo_head")
+            vtc.backward(g_values_buf)
+        if ptc is not None:
+            # the RSR term acts on mode(logits) (RSR/losses.py:186-195): its gradient w.r.t. the logits joins the head's
+            g_total = g_logits_buf
+            if past_data is not None and rsr_loss_scale != 0:
+                leaf = logits.detach().requires_grad_(True)
+                sim2real_loss, distance = rsr.compute_rsr_loss(obs, NormalTanh.mode(leaf), static["next_observation"], past_data,
+                                                               loss_scale=rsr_loss_scale)
+                (g_extra,) = torch.autograd.grad(sim2real_loss, leaf)
+                g_total = g_logits_buf + g_extra
+            else:
+                sim2real_loss = distance = torch.zeros((), device=dev)
+            ptc.backward(g_total)
+        else:
+            sim2real_loss, distance = rsr.compute_rsr_loss(obs, NormalTanh.mode(logits), static["next_observation"], past_data,
+                                                           loss_scale=rsr_loss_scale)
+            if sim2real_loss.requires_grad:
+                torch.autograd.backward([logits, sim2real_loss], [g_logits_buf, None])
+            else:
+                torch.autograd.backward([logits], [g_logits_buf])
+        task_loss = head_out[0]
+        return {"total_loss": task_loss + sim2real_loss.detach(), "task_loss": task_loss, "policy_loss": head_out[1],
+                "v_loss": head_out[2], "entropy_loss": head_out[3], "sim2real_loss": sim2real_loss.detach(),
+                "rsr_distribution_distance": distance.detach()}
+
+    fwd_bwd = fwd_bwd_tc if use_tc else fwd_bwd_autograd
 
     # One graph for the whole SGD phase of a training step: num_updates_per_batch x num_minibatches minibatch steps, each
     # = gather + forward/backward + gradient all-reduce (NCCL is graph-capturable) + Adam, replayed with fresh
@@ -555,7 +627,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     n_mb_steps = num_updates_per_batch * num_minibatches
     epoch_graph_enabled = bool(epoch_graph and use_cuda_graph)
     perm_all = torch.empty(num_updates_per_batch, B, dtype=torch.int64, device=dev)
-    noise_all = torch.empty(n_mb_steps, *static_noise.shape, device=dev) if epoch_graph_enabled else None
+    noise_all = torch.empty(n_mb_steps, *static_noise.shape, device=dev)  # entropy noise of a whole SGD phase, one draw
 
     graph_bwd = graph_opt = None
     if use_cuda_graph:
@@ -638,18 +710,18 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         """the SGD phase of one training step (RSR/train.py:279-299): num_updates_per_batch shuffles x num_minibatches"""
         for u_ in range(num_updates_per_batch):
             perm_all[u_].copy_(torch.randperm(B, device=dev, generator=gen))
+        noise_all.normal_(generator=gen)
         if sgd_epoch_graph is not None:
-            noise_all.normal_(generator=gen)
             sgd_epoch_graph.replay()
             return
         for u_ in range(num_updates_per_batch):
             for m_ in range(num_minibatches):
+                static_noise.copy_(noise_all[u_ * num_minibatches + m_])
                 minibatch_step(batch, perm_all[u_, m_ * mb:(m_ + 1) * mb])
 
     def minibatch_step(batch, idx):
         nonlocal last_metrics
         gather_minibatch(batch, idx)
-        static_noise.normal_(generator=gen)
         if graph_bwd is not None:
             graph_bwd.replay()
             _flat_allreduce_mean(params)

@@ -251,3 +251,149 @@ def test_tanh_normal_act_matches_torch():
     torch.testing.assert_close(lp, ppo.NormalTanh.log_prob(logits, raw_ref), rtol=1e-5, atol=2e-5)
     with pytest.raises(ValueError):
         ppo.NormalTanh.act(logits.cpu(), noise.cpu())
+
+
+# ---- round 2: the value network on the hand-written tcgen05 kernels ---------------------------------------------------
+def test_tensor_core_value_net_matches_torch_autograd():
+    """fused_mlp.TensorCoreMLP (tcgen05 TF32 GEMMs with fused bias / swish / swish' / bias-gradient epilogues) against
+    torch autograd on the same MLP in full fp32: values and every parameter gradient within TF32 accuracy."""
+    from rsr_mjx_b200 import fused_mlp
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mlp = ppo.MLP([23, 256, 256, 256, 256, 256, 1]).cuda()
+    for l in mlp.layers:
+        torch.nn.init.normal_(l.bias, 0, 0.1)
+    rows = 2816
+    x = torch.randn(rows, 23, device="cuda")
+    g = torch.randn(rows, device="cuda") / rows
+    tc = fused_mlp.TensorCoreMLP(mlp, rows, "cuda")
+    v = tc.forward(x)
+    tc.attach_grads()
+    tc.backward(g)
+    torch.cuda.synchronize()
+    got = {n: p.grad.clone() for n, p in mlp.named_parameters()}
+    for p in mlp.parameters():
+        p.grad = None
+    ref = ppo.MLP.forward(mlp, x).squeeze(-1) if False else None
+    h = x
+    for i, l in enumerate(mlp.layers):
+        h = torch.nn.functional.linear(h, l.weight, l.bias)
+        if i + 1 < len(mlp.layers):
+            h = torch.nn.functional.silu(h)
+    ref = h.squeeze(-1)
+    ref.backward(g)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    # TF32 inputs (10-bit mantissa) through six layers: ~1e-2 of the output / gradient scale against full fp32
+    assert rel(v, ref.detach()) <= 1.5e-2
+    for n, p in mlp.named_parameters():
+        assert rel(got[n], p.grad) <= 1.5e-2, (n, rel(got[n], p.grad))
+    # ragged rows (not a multiple of 128 or 256) and relu (the SAC critics)
+    class R(ppo.MLP):
+        activation = "relu"
+    mlp2 = R([28, 64, 64, 1]).cuda()
+    x2, g2 = torch.randn(300, 28, device="cuda"), torch.randn(300, device="cuda")
+    tc2 = fused_mlp.TensorCoreMLP(mlp2, 300, "cuda")
+    v2 = tc2.forward(x2)
+    tc2.attach_grads()
+    tc2.backward(g2)
+    got2 = {n: p.grad.clone() for n, p in mlp2.named_parameters()}
+    for p in mlp2.parameters():
+        p.grad = None
+    h = x2
+    for i, l in enumerate(mlp2.layers):
+        h = torch.nn.functional.linear(h, l.weight, l.bias)
+        if i + 1 < len(mlp2.layers):
+            h = torch.relu(h)
+    h.squeeze(-1).backward(g2)
+    # relu: a pre-activation within TF32 noise of 0 flips its derivative, so single entries move more; the gradient as a
+    # whole (relative L2) stays at TF32 accuracy
+    rel2 = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-12))
+    assert rel(v2, h.squeeze(-1).detach()) <= 1e-2
+    for n, p in mlp2.named_parameters():
+        assert rel2(got2[n], p.grad) <= 1e-2, (n, rel2(got2[n], p.grad))
+
+
+def test_tensor_core_value_path_trains_like_the_autograd_path():
+    """one training step with the value network on the tcgen05 kernels vs on torch autograd (both TF32): same parameters
+    up to TF32 rounding of the two implementations, same losses"""
+    def run(tc):
+        env = AirbotPlayBase("sf", num_envs=128, episode_length=1200)
+        _, (norm, net), m = ppo.train(env, num_timesteps=10**9, episode_length=1200, past_data=_rsr_data(), num_envs=128,
+                                      learning_rate=1e-3, entropy_cost=2e-2, discounting=0.96, unroll_length=5, batch_size=16,
+                                      num_minibatches=8, num_updates_per_batch=2, num_evals=1, normalize_observations=True,
+                                      reward_scaling=0.1, max_training_steps=1, run_evals=False, tensor_core_value=tc)
+        return net, m
+    net_a, ma = run(True)
+    net_b, mb_ = run(False)
+    for k in ("training/policy_loss", "training/v_loss", "training/entropy_loss", "training/sim2real_loss"):
+        assert ma[k] == pytest.approx(mb_[k], rel=2e-2, abs=1e-5), k
+    for (n1, p1), (n2, p2) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        # Adam normalises the step size, so parameters move by ~lr per step whatever the gradient scale: compare the
+        # displacement direction loosely and the values tightly
+        torch.testing.assert_close(p1, p2, rtol=0, atol=3e-3, msg=n1)
+
+
+def test_warp_policy_net_matches_torch_autograd():
+    """fused_mlp.WarpMLP (one warp per row, lane = neuron; csrc/rsrx_mlp.cuh) against torch autograd in fp32: logits and
+    every parameter gradient to fp32 accuracy (no tensor cores involved), for the reference policy 23 -> 32 x 4 -> 10 and a
+    ragged relu net"""
+    from rsr_mjx_b200 import fused_mlp
+    torch.manual_seed(1)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+    class R(ppo.MLP):
+        activation = "relu"
+    for cls, sizes, rows in ((ppo.MLP, [23, 32, 32, 32, 32, 10], 2560), (R, [28, 17, 32, 6], 333), (ppo.MLP, [23, 10], 40)):
+        mlp = cls(sizes).cuda()
+        for l in mlp.layers:
+            torch.nn.init.normal_(l.bias, 0, 0.1)
+        x = torch.randn(rows, sizes[0], device="cuda")
+        g = torch.randn(rows, sizes[-1], device="cuda")
+        wm = fused_mlp.WarpMLP(mlp, rows, "cuda")
+        out = wm.forward(x).clone()
+        wm.attach_grads()
+        wm.backward(g)
+        torch.cuda.synchronize()
+        got = {n: p.grad.clone() for n, p in mlp.named_parameters()}
+        for p in mlp.parameters():
+            p.grad = None
+        h = x
+        for i, l in enumerate(mlp.layers):
+            h = torch.nn.functional.linear(h, l.weight, l.bias)
+            if i + 1 < len(mlp.layers):
+                h = torch.nn.functional.silu(h) if cls is ppo.MLP else torch.relu(h)
+        h.backward(g)
+        assert rel(out, h.detach()) <= 1e-5, sizes
+        for n, p in mlp.named_parameters():
+            assert rel(got[n], p.grad) <= 1e-4, (sizes, n, rel(got[n], p.grad))
+
+
+def test_fused_adam_matches_torch_adam():
+    from rsr_mjx_b200 import fused_mlp
+    torch.manual_seed(2)
+    shapes = [(32, 23), (32,), (256, 256), (256,), (1, 256), (1,)]
+    pa = [torch.randn(*s, device="cuda") for s in shapes]
+    pb = [p.clone().requires_grad_(True) for p in pa]
+    fa = fused_mlp.FusedAdam(pa, lr=1e-3, eps=1e-8)
+    tb = torch.optim.Adam(pb, lr=1e-3, eps=1e-8)
+    g = torch.cuda.CUDAGraph()
+    grads = [torch.zeros_like(p) for p in pa]
+    for p, gr in zip(pa, grads):
+        p.grad = gr
+    fa.step()                      # warm-up outside the graph (restored below)
+    for p, q in zip(pa, pb):
+        p.copy_(q.detach())
+    fa.reset_state()
+    with torch.cuda.graph(g):
+        fa.step()
+    for it in range(7):
+        for gr, q in zip(grads, pb):
+            gr.normal_()
+            q.grad = gr.clone()
+        g.replay()                 # the captured step keeps counting: bias correction of step it + 1
+        tb.step()
+    torch.cuda.synchronize()
+    assert fa.steps_taken == 7
+    for p, q in zip(pa, pb):
+        torch.testing.assert_close(p, q.detach(), rtol=2e-5, atol=2e-6)

@@ -3,20 +3,30 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import torch
 from rsr_mjx_b200 import _lib
 L = _lib.lib()
-torch.set_printoptions(linewidth=250, precision=0, sci_mode=False)
 s = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
-M, N, K = 128, 64, 64   # dz [M,N], w [N,K] -> dzp [M,K]
-w = (torch.arange(N, device="cuda")[:, None] * 100 + torch.arange(K, device="cuda")[None, :] + 1).float()
-dump = torch.full((64 * 32,), -1.0, device="cuda")
-for cfg in ["0,0,0,0"]:
-    os.environ["RSRX_GEMM_DBG"] = cfg + f",{dump.data_ptr()}"
-    print("=== LBO,SBO,KSTEP,IDESC_XOR =", cfg)
-    for sel in (0, 9):
-        dz = torch.zeros(M, N, device="cuda"); dz[:, sel] = 1.0
-        dzp = torch.full((M, K), -7.0, device="cuda")
-        _lib.check(L.rsrx_linear_dgrad(dz.data_ptr(), N, w.data_ptr(), K, None, M, K, N, 0, dzp.data_ptr(), K, None, s()))
-        torch.cuda.synchronize()
-        print(f" sel {sel}: expect {sel*100+1}..{sel*100+64}:", dzp[3, :24].tolist(), "...", dzp[3, 60:64].tolist())
-print("staged B tile image (first 3 core matrices = 96 floats):")
-print(dump[:96].reshape(-1, 4))
-print("floats 512..544:", dump[512:544].tolist())
+stamps = torch.zeros(8, dtype=torch.int64, device="cuda")
+os.environ["RSRX_GEMM_STAMPS"] = str(stamps.data_ptr())
+g = torch.Generator("cuda").manual_seed(0)
+R = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+names = ["start", "alloc+init", "stage issued", "staged+sync", "mma issued", "mma done", "tmem->smem", "epilogue"]
+def show(tag):
+    torch.cuda.synchronize()
+    t = stamps.cpu().tolist()
+    print(tag, " ".join(f"{n}:{(t[i]-t[0])/1e3:.2f}" for i, n in enumerate(names)), "(us since start)")
+for (M, N, K) in [(2816, 256, 256), (128, 8, 32), (2816, 256, 32)]:
+    x, w, b = R(M, K), R(N, K) * 0.1, R(N)
+    z, y = torch.zeros(M, N, device="cuda"), torch.zeros(M, N, device="cuda")
+    for rep in range(3):
+        _lib.check(L.rsrx_linear_forward(x.data_ptr(), K, w.data_ptr(), K, b.data_ptr(), M, N, K, 1, z.data_ptr(), y.data_ptr(), N, s()))
+    show(f"fwd {M}x{N}x{K}:")
+    if N % 4 == 0:
+        dz, zp = R(M, N), R(M, K)
+        dzp = torch.zeros(M, K, device="cuda"); cs = torch.zeros((M + 127) // 128, K, device="cuda")
+        for rep in range(3):
+            _lib.check(L.rsrx_linear_dgrad(dz.data_ptr(), N, w.data_ptr(), K, zp.data_ptr(), M, K, N, 1, dzp.data_ptr(), K, cs.data_ptr(), s()))
+        show(f"dgrad {M}x{N}x{K}:")
+        S = (M + 255) // 256
+        part = torch.zeros(S, N, K, device="cuda")
+        for rep in range(3):
+            _lib.check(L.rsrx_linear_wgrad(dz.data_ptr(), N, x.data_ptr(), K, M, N, K, 256, part.data_ptr(), K, s()))
+        show(f"wgrad {M}x{N}x{K}:")
