@@ -503,13 +503,19 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     # bake their addresses in
     batch_static = {k: torch.empty(B, T, *v.shape[3:], device=dev) for k, v in buf.items()}
 
+    # actor-step policy forward: one warp-per-row launch instead of ~10 (csrc/rsrx_mlp.cuh) when the policy fits (<= 32 wide)
+    from . import fused_mlp as _fm
+    actor_mlp = None
+    if tensor_core_value and fused_head and dev.type == "cuda" and _fm.warp_supported(net.policy, dev):
+        actor_mlp = _fm.WarpMLP(net.policy, num_envs, dev)
+
     @torch.no_grad()
     def collect_body():
         for u in range(n_unrolls):
             for t in range(T):
                 obs = state.obs
                 buf["observation"][u, t].copy_(obs)
-                logits = net.policy(normalize(obs))
+                logits = actor_mlp.forward(normalize(obs).contiguous()) if actor_mlp is not None else net.policy(normalize(obs))
                 # raw action, its log-prob (straight into the rollout buffers) and the tanh action: one launch
                 NormalTanh.act(logits, act_noise[u, t], buf["raw_action"][u, t], action_buf, buf["log_prob"][u, t])
                 env.step(state, action_buf)
