@@ -152,8 +152,10 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_oracle_rate(kind, n_envs, n_steps, dense, threads=0, precision="f32"):
-    """env-steps/s of the CPU oracle (OpenMP over envs) on a bounded sample of the same workload"""
+def cpu_oracle_rate(kind, n_envs, n_steps, dense, threads=0, precision="f32", stationary=True):
+    """env-steps/s of the CPU oracle (OpenMP over envs) on a bounded sample of the same workload.  stationary: like the
+    GPU arm, the envs are first advanced (untimed) by one episode with staggered step counters, so that the timed steps
+    see every episode phase (contact load) in the proportion a running job does."""
     import ctypes as C
     from oracle import oracle as O
     from rsr_mjx_b200 import airbot_spec as A, prng
@@ -170,6 +172,12 @@ def cpu_oracle_rate(kind, n_envs, n_steps, dense, threads=0, precision="f32"):
         s = O.env_reset(blob, cfg, q[i], v[i], c[i], precision=precision)
         C.memmove(C.byref(states[i]), C.byref(s), C.sizeof(s))
     actions = np.random.default_rng(1).uniform(-1, 1, (n_steps, n_envs, m.nu))
+    if stationary:
+        view = np.ctypeslib.as_array(states)
+        view["steps"][:] = np.random.default_rng(2).integers(0, 1200, n_envs).astype(np.float64)
+        pre = np.random.default_rng(3).uniform(-1, 1, (64, n_envs, m.nu))
+        for c in range(0, 1200, 64):  # active-set rows for the untimed advance, whatever the timed variant
+            O.rollout(blob, cfg, states, pre[:min(64, 1200 - c)], precision=precision, dense=False, nthreads=threads)
     O.rollout(blob, cfg, states, actions[:2], precision=precision, dense=dense, nthreads=threads)  # warm-up
     t0 = time.perf_counter()
     O.rollout(blob, cfg, states, actions, precision=precision, dense=dense, nthreads=threads)
@@ -186,12 +194,14 @@ def run_reference(args):
     # warm-up steps are part of cpu_oracle_rate (2 untimed steps); W extra rollouts are not needed on a CPU
     rate, dt, thr = cpu_oracle_rate(args.kind, n_envs, n_steps, dense=False)
     rate_dense, dt_dense, _ = cpu_oracle_rate(args.kind, max(n_envs // 8, thr), max(n_steps // 2, 1), dense=True)
-    sample = f"{n_envs} envs x {n_steps} steps of the same reset/action law, oracle port (C, float32, OpenMP over envs), active-set rows"
+    sample = (f"{n_envs} envs x {n_steps} steps of the same reset/action law on the stationary episode-phase distribution (one "
+              "untimed episode with staggered step counters first), oracle port (C, float32, OpenMP over envs), active-set rows")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": n_steps,
         "warmup": args.warmup, "ms_per_step": dt / n_steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"airbot_{args.kind} env.step (test/airbot.py + sf.xml), CPU oracle port, {n_envs} envs",
+                   "episode_phase": "stationary (same protocol as the GPU arm)",
                    "note": "MJX itself cannot be installed here (SURVEY.md §8c); this is the oracle restatement, not MJX"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": thr, "kind": "port", "sample": sample,
                          "mjx_work_pattern_value": rate_dense,
@@ -436,9 +446,10 @@ def main():
             "sub": sub,
         }
         if not args.no_cpu_baseline and world == 1:
-            rate, dt, thr = cpu_oracle_rate(args.kind, args.cpu_envs, 1000, dense=False)  # ~10 s on 16 host threads
+            rate, dt, thr = cpu_oracle_rate(args.kind, args.cpu_envs, 300, dense=False)  # ~14 s untimed advance + ~4 s timed on 16 threads
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": thr, "kind": "port",
-                                    "sample": f"{args.cpu_envs} envs x 1000 steps, oracle port (C float32, OpenMP), active-set rows; {dt:.1f} s"}
+                                    "sample": f"{args.cpu_envs} envs x 300 steps on the stationary episode-phase distribution (one untimed "
+                                              f"episode first), oracle port (C float32, OpenMP), active-set rows; {dt:.1f} s timed"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

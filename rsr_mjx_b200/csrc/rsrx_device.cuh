@@ -318,7 +318,7 @@ __device__ __forceinline__ void make_frame(float* f, const float* n) {
   f[3] = b[0]; f[4] = b[1]; f[5] = b[2];
   f[6] = c[0]; f[7] = c[1]; f[8] = c[2];
 }
-__device__ __forceinline__ float pw(float x, float p) {
+__device__ __noinline__ float pw(float x, float p) {  // (noinline: four inlined powf expansions were 6 KB of the kernel)
   if (p == 1.f) return x;
   if (p == 2.f) return x * x;
   return powf(x, p);

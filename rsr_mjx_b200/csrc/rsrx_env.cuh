@@ -47,13 +47,20 @@ __device__ __noinline__ void load_env(const DModel* __restrict__ dm, float* sm, 
 // write the pipeline_state row (qpos/qvel/ctrl/warmstart/time + lagged kinematics)
 __device__ __noinline__ void store_env(const DModel* __restrict__ dm, const float* sm, int lane, float* __restrict__ row, float time) {
   const rsrx_layout& L = dm->lay;
+#pragma unroll 1
   for (int i = lane; i < dm->nq; i += 32) row[L.qpos + i] = sm[ar::QPOS + i];
+#pragma unroll 1
   for (int i = lane; i < dm->nv; i += 32) { row[L.qvel + i] = sm[ar::QVEL + i]; row[L.qacc_warmstart + i] = sm[ar::WARM + i]; }
+#pragma unroll 1
   for (int i = lane; i < dm->nu; i += 32) row[L.ctrl + i] = sm[ar::CTRL + i];
   if (lane == 0) row[L.time] = time;
+#pragma unroll 1
   for (int i = lane; i < dm->nbody * 3; i += 32) row[L.xpos + i] = sm[ar::XPOS + i];
+#pragma unroll 1
   for (int i = lane; i < dm->nbody * 4; i += 32) row[L.xquat + i] = sm[ar::XQUAT + i];
+#pragma unroll 1
   for (int i = lane; i < dm->nsite * 3; i += 32) row[L.site_xpos + i] = sm[ar::SXPOS + i];
+#pragma unroll 1
   for (int g = lane; g < dm->ngeom; g += 32) {
     float gp[3];
     geom_pose(dm, sm, g, gp, nullptr);
@@ -120,9 +127,12 @@ __device__ __forceinline__ bool env_reset_body(const DModel* __restrict__ dm, fl
   const rsrx_layout& L = dm->lay;
   float* row = st.data + (size_t)e * L.data_stride;
   // stage a row: qpos, qvel, ctrl = 0, warm = 0
+#pragma unroll 1
   for (int i = lane; i < L.data_stride; i += 32) row[i] = 0.f;
   RSRX_SYNC();
+#pragma unroll 1
   for (int i = lane; i < dm->nq; i += 32) row[L.qpos + i] = qpos[(size_t)e * dm->nq + i];
+#pragma unroll 1
   for (int i = lane; i < dm->nv; i += 32) row[L.qvel + i] = qvel[(size_t)e * dm->nv + i];
   RSRX_SYNC();
   load_env(dm, sm, lane, e, spill_slot, row, pe);
@@ -131,6 +141,7 @@ __device__ __forceinline__ bool env_reset_body(const DModel* __restrict__ dm, fl
   forward<false>(dm, sm, lane, &sd, &status);
   status = __reduce_or_sync(0xffffffffu, status);
   if (status & RSRX_STATUS_CONTACT_OVERFLOW) return false;
+#pragma unroll 1
   for (int i = lane; i < dm->nu; i += 32) sm[ar::CTRL + i] = ctrl[(size_t)e * dm->nu + i];
   RSRX_SYNC();
   store_env(dm, sm, lane, row, 0.f);
@@ -158,6 +169,7 @@ __device__ __forceinline__ bool env_reset_body(const DModel* __restrict__ dm, fl
     st.status[e] = status;
   }
   RSRX_SYNC();
+#pragma unroll 1
   for (int i = lane; i < OBS_STRIDE; i += 32) {
     st.obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
     st.first_obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
@@ -165,6 +177,7 @@ __device__ __forceinline__ bool env_reset_body(const DModel* __restrict__ dm, fl
   __threadfence_block();
   RSRX_SYNC();
   float* frow = st.first_data + (size_t)e * L.data_stride;
+#pragma unroll 1
   for (int i = lane; i < L.data_stride; i += 32) frow[i] = row[i];
   return true;
 }
@@ -318,7 +331,9 @@ __device__ __forceinline__ bool env_step_body(const DModel* __restrict__ dm, flo
   done = __shfl_sync(0xffffffffu, done, 0);
   // non-finite guard
   bool bad = false;
+#pragma unroll 1
   for (int i = lane; i < dm->nq; i += 32) bad |= !isfinite(sm[ar::QPOS + i]);
+#pragma unroll 1
   for (int i = lane; i < dm->nv; i += 32) bad |= !isfinite(sm[ar::QVEL + i]);
   if (__any_sync(0xffffffffu, bad)) status |= RSRX_STATUS_NONFINITE;
   if (lane == 0 && status) st.status[e] |= status;
@@ -326,10 +341,13 @@ __device__ __forceinline__ bool env_step_body(const DModel* __restrict__ dm, flo
   // ---- AutoReset post: pipeline_state and obs only (episode_length <= 0: bare env, no wrappers)
   if (done != 0.f && dm->episode_length > 0) {
     const float* frow = st.first_data + (size_t)e * L.data_stride;
+#pragma unroll 1
     for (int i = lane; i < L.data_stride; i += 32) row[i] = frow[i];
+#pragma unroll 1
     for (int i = lane; i < OBS_STRIDE; i += 32) st.obs[(size_t)e * OBS_STRIDE + i] = st.first_obs[(size_t)e * OBS_STRIDE + i];
   } else {
     store_env(dm, sm, lane, row, time);
+#pragma unroll 1
     for (int i = lane; i < OBS_STRIDE; i += 32) st.obs[(size_t)e * OBS_STRIDE + i] = sm[ar::OBSBUF + i];
   }
   return true;
@@ -352,10 +370,12 @@ __device__ __forceinline__ bool physics_body(const DModel* __restrict__ dm, floa
     if (dump) {
       float* dp = dump + (size_t)e * dbg::STRIDE;
       const int nv = dm->nv;
+#pragma unroll 1
       for (int i = lane; i < nv * nv; i += 32) {
         const int r = i / nv, c = i % nv, hi = r > c ? r : c, lo = r > c ? c : r;
         dp[dbg::M + i] = sm[ar::MM + ((hi * (hi + 1)) >> 1) + lo];
       }
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         dp[dbg::BIAS + i] = sm[ar::V_BIAS + i];
         dp[dbg::QACC_SMOOTH + i] = sm[ar::V_QACCS + i];

@@ -1501,8 +1501,13 @@ __device__ __noinline__ int solve(const DModel* __restrict__ dm, float* sm, int 
 // phase boundaries lets one fetch serve all of them.  RSRX_SYNC_MASK selects the boundaries (bit 0: substep
 // start, 1: collision, 2: make_constraint, 3: velocity/forces, 4: solve, 5: integrate).
 #ifndef RSRX_SYNC_MASK
-#define RSRX_SYNC_MASK 33  // substep start + after the solver (where the warps are spread the most, so that the integration
-                          // phase streams aligned too): 2.37 ms vs 2.51 with the substep-start barrier alone at 19 warps per CTA
+#define RSRX_SYNC_MASK 37  // substep start + before make_constraint + after the solver.  Round 1 timed the first steps after
+                          // reset, where start + after-solver (33) was best (2.37 vs 2.51 ms with the start barrier alone);
+                          // on the stationary episode-phase distribution bench.py times since round 2 the contact load and
+                          // its spread across the 19 envs of a CTA are larger, the instruction-cache hit rate drops to 79 %,
+                          // and a third alignment point pays: 2.41 vs 2.50 ms at 8192 envs, 3.20 vs 3.30 on the T-shape env,
+                          // equal or better down to 128 envs (profiles/README.md; every 3+-barrier mask lands at 2.40-2.42,
+                          // no barrier at all: 5.9 ms)
 #endif
 #ifndef RSRX_BAR_GROUPS
 #define RSRX_BAR_GROUPS 1
