@@ -24,10 +24,12 @@
 //   No TMA: the operands are small, L2-resident activations whose rows are not all 16-byte multiples apart; plain
 //   coalesced 16-byte loads keep the kernel free of tensor-map plumbing.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstring>
 
 namespace rsrx {
 namespace gemm {
@@ -41,6 +43,10 @@ enum Epilogue { EPI_BIAS_ACT = 0, EPI_DGRAD = 1, EPI_PARTIAL = 2 };
 enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
 
 struct Params {
+  // TMA descriptors of the operands that are contiguous along the contraction (box 32 floats x 128 | BN rows, 128-byte
+  // swizzle); unused (zeroed) for operands that are transposed while being staged
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
   const float* A; int a_row, a_col;   // element (i, k) of A at A[i * a_row + k * a_col]; one of the two strides is 1
   const float* B; int b_row, b_col;   // element (j, k) of B at B[j * b_row + k * b_col]
   int M, N, K;                        // D is M x N, contraction length K (per split)
@@ -164,12 +170,24 @@ __device__ __forceinline__ void stage_tile(float* smem, const float* __restrict_
 
 constexpr int KMAX = 256;  // contraction length held in shared memory at once (A 128 KB + B 64 KB at BN = 64)
 
+// shared-memory descriptor of a K-major tile in the 128-byte-swizzle layout TMA writes: rows 128 B apart, 16-byte chunk
+// index XOR (row & 7), 8-row groups 1024 B apart (SBO); LBO is not used inside one swizzle span; layout type 2
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// A_MN / B_MN: the operand is contiguous along its row index in global memory -> staged by the threads with an in-flight
+// transposition (no-swizzle image).  Otherwise (contiguous along the contraction) -> loaded by TMA (cp.async.bulk.tensor)
+// into the 128-byte-swizzled image, one 32-float slab of all rows per copy.
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const Params p) {
-  extern __shared__ __align__(128) float smem[];
+__global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) float smem_raw[];
+  // 1024-byte alignment for the swizzled slabs (the launch adds 1 KB of slack)
+  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sA = smem;                 // [BM x kcap]
   float* sB = smem + BM * p.kcap;   // [BN x kcap]
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t tma_bar;
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -183,7 +201,10 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const Params p) {
   }
   if (tid == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&tma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
+    if (!A_MN) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA)) : "memory");
+    if (!B_MN) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -198,7 +219,7 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const Params p) {
   // The whole contraction slice (<= KMAX) is staged at once — every global load of the CTA is in flight together, one
   // round trip instead of one per k-block — then 4 .. 32 back-to-back MMAs (K = 8 each) and one commit.  Longer
   // contractions repeat the cycle (not on the value-network path: K <= 256, wgrad is split into 256-row slices).
-  uint32_t phase = 0;
+  uint32_t phase = 0, tma_phase = 0;
   bool first = true;
   for (int k0 = kbeg; k0 < kend; k0 += p.kcap) {
     const int kb = min(p.kcap, ((kend - k0) + BK - 1) / BK * BK);
@@ -206,22 +227,42 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const Params p) {
       mbar_wait(&bar, phase);
       phase ^= 1;
     }
-    stage_tile<BM, A_MN>(sA, p.A, p.a_row, p.a_col, m0, k0, p.M, kend, kb);
-    stage_tile<BN, B_MN>(sB, p.B, p.b_row, p.b_col, n0, k0, p.N, kend, kb);
+    if ((!A_MN || !B_MN) && tid == 0) {
+      // TMA: one copy per 32-float slab and operand, all in flight at once; out-of-range rows / columns arrive as zeros
+      const int nslab = kb / BK;
+      const uint32_t bytes = (uint32_t)nslab * BK * 4u * ((A_MN ? 0u : (uint32_t)BM) + (B_MN ? 0u : (uint32_t)BN));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tma_bar)), "r"(bytes) : "memory");
+      for (int sl = 0; sl < nslab; ++sl) {
+        if (!A_MN)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(smem_u32(sA + sl * BM * BK)), "l"(reinterpret_cast<uint64_t>(&p.tmA)), "r"(k0 + sl * BK), "r"(m0),
+                         "r"(smem_u32(&tma_bar)) : "memory");
+        if (!B_MN)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(smem_u32(sB + sl * BN * BK)), "l"(reinterpret_cast<uint64_t>(&p.tmB)), "r"(k0 + sl * BK), "r"(n0),
+                         "r"(smem_u32(&tma_bar)) : "memory");
+      }
+    }
+    if (A_MN) stage_tile<BM, true>(sA, p.A, p.a_row, p.a_col, m0, k0, p.M, kend, kb);
+    if (B_MN) stage_tile<BN, true>(sB, p.B, p.b_row, p.b_col, n0, k0, p.N, kend, kb);
     stamp(p, 2);
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;");  // generic-proxy writes -> visible to the tensor core (async proxy)
+    if (A_MN || B_MN) asm volatile("fence.proxy.async.shared::cta;");  // generic-proxy writes -> visible to the tensor core
     __syncthreads();
+    if (!A_MN || !B_MN) {
+      mbar_wait(&tma_bar, tma_phase);
+      tma_phase ^= 1;
+    }
     stamp(p, 3);
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-      // K-major, no swizzle: core matrices (8 rows x 16 B) 128 B apart along K (LBO), 8-row groups kb / 4 * 128 B apart
-      // (SBO); one UMMA_K = 8 step covers two core matrices
+      // transposed operands: K-major, no swizzle: core matrices (8 rows x 16 B) 128 B apart along K (LBO), 8-row groups
+      // kb / 4 * 128 B apart (SBO), one UMMA_K = 8 step = two core matrices.  TMA operands: slab k / 4, 32 B per step inside
+      // the 128-byte swizzle span.
       const uint32_t SBO = (uint32_t)(kb >> 2) * 128;
       for (int k = 0; k < kb / UMMA_K; ++k) {
-        const uint64_t da = make_desc(a_addr + k * 256, 128, SBO);
-        const uint64_t db = make_desc(b_addr + k * 256, 128, SBO);
+        const uint64_t da = A_MN ? make_desc(a_addr + k * 256, 128, SBO) : make_desc_sw128(a_addr + (k >> 2) * (BM * BK * 4) + (k & 3) * 32);
+        const uint64_t db = B_MN ? make_desc(b_addr + k * 256, 128, SBO) : make_desc_sw128(b_addr + (k >> 2) * (BN * BK * 4) + (k & 3) * 32);
         const uint32_t accumulate = (!first || k > 0) ? 1u : 0u;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -424,16 +465,48 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+// row-major fp32 matrix [rows][cols], leading dimension ld: box = 32 columns (128 B, the swizzle span) x box_rows rows
+inline cudaError_t make_tmap(CUtensorMap* tm, const float* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 inline cudaError_t launch_one(Params p, dim3 grid, cudaStream_t stream) {
   const int kslice = std::min(p.K, p.k_split);
   p.kcap = std::min(KMAX, (kslice + BK - 1) / BK * BK);
   const size_t epi = sizeof(float) * (BM * (BN + 1) + (THREADS / (BN / 4)) * BN);  // epilogue staging + column-sum scratch
-  const size_t smem = std::max(sizeof(float) * (size_t)(BM + BN) * p.kcap, epi);
+  const size_t smem = std::max(sizeof(float) * (size_t)(BM + BN) * p.kcap, epi) + 1024;  // + alignment slack
+  memset(&p.tmA, 0, sizeof(p.tmA));
+  memset(&p.tmB, 0, sizeof(p.tmB));
+  if (!A_MN) { cudaError_t e = make_tmap(&p.tmA, p.A, p.M, p.K, p.a_row, BM); if (e != cudaSuccess) return e; }
+  if (!B_MN) { cudaError_t e = make_tmap(&p.tmB, p.B, p.N, p.K, p.b_row, BN); if (e != cudaSuccess) return e; }
   static bool set = false;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(float) * (BM + BN) * KMAX));
+                                         (int)(sizeof(float) * (BM + BN) * KMAX + 1024));
     if (e != cudaSuccess) return e;
     set = true;
   }
