@@ -206,33 +206,38 @@ int rsrx_ppo_head(const float* logits, const float* baseline, const float* boots
                   float clipping_epsilon, float entropy_cost, int normalize_advantage, float* workspace, float* out,
                   float* grad_logits, float* grad_baseline, void* stream);
 
-/* ---- tensor-core linear layers for the trainers' value networks (csrc/rsrx_gemm.cuh: tcgen05.mma kind::tf32, fp32
- * accumulation in TMEM, fused epilogues).  Replaces torch.addmm + SiLU + SiLU' + bias-gradient launches of the value
+/* ---- tensor-core linear layers for the trainers' value networks (csrc/rsrx_gemm.cuh: TMA loads, tcgen05.mma kind::tf32,
+ * fp32 accumulation in TMEM, fused epilogues).  Replaces torch.addmm + SiLU + SiLU' + bias-gradient launches of the value
  * MLP of RSR/train.py (brax make_ppo_networks, value_hidden_layer_sizes (256,)*5) / the critics of RSR/sac_train.py.
  * Row-major device float32 arrays; every pointer 16-byte aligned, every leading dimension a multiple of 4.
- * activation: 0 none, 1 silu (brax swish), 2 relu.
- *   forward : z[M][N] = x[M][K] w[N][K]^T + bias (z may be NULL), y = act(z)
- *   dgrad   : dzprev[M][Nin] = (dz[M][Nout] w[Nout][Nin]) * act'(zprev), and, if colsum_partials != NULL, the column sums
- *             of dzprev over each block of 128 rows -> colsum_partials[ceil(M/128)][ld] (the previous layer's bias
- *             gradient, finished by rsrx_reduce_partials)
+ * activation: 0 none, 1 silu (brax swish), 2 relu.  Operands that are contiguous along the contraction are loaded by TMA
+ * (cp.async.bulk.tensor, 128-byte swizzle); the others are transposed by the threads while being staged (slower), which
+ * is why the epilogues can also write TRANSPOSED copies (yT / dzprevT: [N][ldt >= M]) for the weight-gradient GEMM.
+ *   forward : z[M][N] = x[M][K] w[N][K]^T + bias (z may be NULL), y = act(z), optional yT
+ *   dgrad   : dzprev[M][Nin] = (dz[M][Nout] w[Nout][Nin]) * act'(zprev); pass wT [Nin][ldwt >= Nout] (a transposed copy
+ *             of w, e.g. kept by rsrx_adam_step) to use TMA for it, else w; if colsum_partials != NULL the column sums of
+ *             dzprev over each block of 128 rows -> colsum_partials[ceil(M/128)][ld] (the previous layer's bias gradient,
+ *             finished by rsrx_reduce_partials); optional dzprevT
  *   wgrad   : partials[s][Nout][ldp] = dz[rows_s][Nout]^T x[rows_s][Nin] for row slices of rows_per_split rows
- *             (ceil(rows / rows_per_split) slices); summed in slice order by rsrx_reduce_partials: deterministic
+ *             (ceil(rows / rows_per_split) slices); summed in slice order by rsrx_reduce_partials: deterministic.
+ *             transposed_inputs != 0: dz / x are the transposed copies dzT [Nout][lddz >= rows], xT [Nin][ldx >= rows]
  *   reduce  : out_k[i] = sum_{s < S_k} in_k[s * stride_k + i], i < n_k, for up to 24 segments in one launch; in / out /
  *             n / S / stride are HOST arrays
  *   value_head_backward: the scalar output layer v = h . w + b fused with the last hidden layer's activation derivative:
- *             dz[m][j] = g[m] w[j] act'(z[m][j]) and per-128-row partials of colsum(dz), dw[j] = sum g[m] h[m][j],
- *             db = sum g[m] (colsum_partials [blocks][ld], dw_partials [blocks][n], db_partials [blocks]) */
+ *             dz[m][j] = g[m] w[j] act'(z[m][j]) (+ optional dzT) and per-128-row partials of colsum(dz), dw[j] = sum g[m]
+ *             h[m][j], db = sum g[m] (colsum_partials [blocks][ld], dw_partials [blocks][n], db_partials [blocks]) */
 int rsrx_linear_forward(const float* x, int ldx, const float* w, int ldw, const float* bias, int M, int N, int K,
-                        int activation, float* z, float* y, int ldy, void* stream);
-int rsrx_linear_dgrad(const float* dz, int lddz, const float* w, int ldw, const float* zprev, int M, int Nin, int Nout,
-                      int activation, float* dzprev, int ld, float* colsum_partials, void* stream);
-int rsrx_linear_wgrad(const float* dz, int lddz, const float* x, int ldx, int rows, int Nout, int Nin, int rows_per_split,
-                      float* partials, int ldp, void* stream);
+                        int activation, float* z, float* y, int ldy, float* yT, int ldt, void* stream);
+int rsrx_linear_dgrad(const float* dz, int lddz, const float* w, int ldw, const float* wT, int ldwt, const float* zprev, int M,
+                      int Nin, int Nout, int activation, float* dzprev, int ld, float* colsum_partials, float* dzprevT, int ldt,
+                      void* stream);
+int rsrx_linear_wgrad(const float* dz, int lddz, const float* x, int ldx, int transposed_inputs, int rows, int Nout, int Nin,
+                      int rows_per_split, float* partials, int ldp, void* stream);
 int rsrx_reduce_partials(const float* const* in, float* const* out, const int32_t* n, const int32_t* S,
                          const int64_t* stride, int nseg, void* stream);
 int rsrx_value_head_backward(const float* g, const float* w, const float* z, const float* h, int M, int n, int ld,
                              int activation, float* dz, float* colsum_partials, float* dw_partials, float* db_partials,
-                             void* stream);
+                             float* dzT, int ldt, void* stream);
 
 /* ---- the trainers' policy network (brax make_ppo_networks policy_hidden_layer_sizes (32,)*4; csrc/rsrx_mlp.cuh):
  * an MLP with every width <= 32 and <= 8 layers, hidden activation 1 silu / 2 relu, linear output, one warp per row.
@@ -251,12 +256,14 @@ int rsrx_small_mlp_backward_ctas(int rows);
 /* Adam (torch.optim.Adam / optax.adam semantics: bias-corrected moments, no weight decay) on up to 32 tensors in ONE
  * launch — the optimiser step of RSR/train.py:244-262 (optax.adam(learning_rate)) for the trainers' small networks.
  * params / grads / exp_avg / exp_avg_sq / sizes are HOST arrays of device pointers / element counts; the gradient is read
- * as grads[k][i] * grad_scale (1 / world_size after a sum all-reduce).  step_ticket: one device uint64, zero before the
- * first step, advanced by the kernel itself (so a captured CUDA graph keeps counting on every replay); the number of
- * steps taken is *step_ticket / (8 * ntensors): keep ntensors fixed for a given ticket. */
+ * as grads[k][i] * grad_scale (1 / world_size after a sum all-reduce).  params_t / cols (both may be NULL): where
+ * params_t[k] != NULL the updated tensor, seen as [sizes[k] / cols[k]][cols[k]], is also written transposed to
+ * params_t[k] ([cols][rows]: the weight copy rsrx_linear_dgrad loads by TMA).  step_ticket: one device uint64, zero
+ * before the first step, advanced by the kernel itself (so a captured CUDA graph keeps counting on every replay); the
+ * number of steps taken is *step_ticket / (8 * ntensors): keep ntensors fixed for a given ticket. */
 int rsrx_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                   const int32_t* sizes, int ntensors, float lr, float beta1, float beta2, float eps, float grad_scale,
-                   uint64_t* step_ticket, void* stream);
+                   const int32_t* sizes, float* const* params_t, const int32_t* cols, int ntensors, float lr, float beta1,
+                   float beta2, float eps, float grad_scale, uint64_t* step_ticket, void* stream);
 
 const char* rsrx_last_error(void);
 const char* rsrx_version(void);

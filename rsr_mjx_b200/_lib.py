@@ -88,16 +88,16 @@ def lib():
     L.rsrx_tanh_normal_act.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     L.rsrx_gather_rows.argtypes = [vp, vp, vp, i32, vp, i32, vp]
     L.rsrx_ppo_head.argtypes = [vp] * 9 + [i32] * 3 + [f32] * 5 + [i32] + [vp] * 5
-    L.rsrx_linear_forward.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp]
-    L.rsrx_linear_dgrad.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, vp]
-    L.rsrx_linear_wgrad.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]
+    L.rsrx_linear_forward.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp]
+    L.rsrx_linear_dgrad.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, vp, i32, vp]
+    L.rsrx_linear_wgrad.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]
     L.rsrx_reduce_partials.argtypes = [vp, vp, vp, vp, vp, i32, vp]
-    L.rsrx_value_head_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.rsrx_value_head_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
     L.rsrx_small_mlp_forward.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp]
     L.rsrx_small_mlp_backward.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp]
     L.rsrx_small_mlp_backward_ctas.argtypes = [i32]
     L.rsrx_small_mlp_backward_ctas.restype = i32
-    L.rsrx_adam_step.argtypes = [vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, vp, vp]
+    L.rsrx_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, vp, vp]
     if L.rsrx_model_blob_size() != C.sizeof(ModelBlob) or L.rsrx_env_cfg_size() != C.sizeof(EnvCfg):
         raise RuntimeError("librsrx.so and rsr_mjx_b200/model.py disagree on the blob layout; rebuild the library")
     _LIB = L

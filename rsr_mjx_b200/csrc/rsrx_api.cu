@@ -633,50 +633,60 @@ static int gemm_check(const char* what, const void* a, const void* b, int lda, i
 }
 
 extern "C" int rsrx_linear_forward(const float* x, int ldx, const float* w, int ldw, const float* bias, int M, int N, int K,
-                                   int activation, float* z, float* y, int ldy, void* stream) {
+                                   int activation, float* z, float* y, int ldy, float* yT, int ldt, void* stream) {
   if (!x || !w || !y) return fail("rsrx_linear_forward: null argument");
   if (M <= 0 || N <= 0 || K <= 0 || (K & 3) || activation < 0 || activation > 2) return fail("rsrx_linear_forward: bad sizes (K % 4 == 0)");
   if (gemm_check("rsrx_linear_forward", x, w, ldx, ldw)) return 1;
   gemm::Params p{};
   p.A = x; p.a_row = ldx; p.a_col = 1; p.B = w; p.b_row = ldw; p.b_col = 1; p.M = M; p.N = N; p.K = K; p.k_split = K;
-  p.epilogue = gemm::EPI_BIAS_ACT; p.act = activation; p.bias = bias; p.D = y; p.Z = z; p.ldd = ldy;
+  p.epilogue = gemm::EPI_BIAS_ACT; p.act = activation; p.bias = bias; p.D = y; p.Z = z; p.ldd = ldy; p.DT = yT; p.ldt = ldt;
   if (((uintptr_t)y & 15) || ((uintptr_t)z & 15) || (ldy & 3)) return fail("rsrx_linear_forward: outputs must be 16-byte aligned, ldy % 4 == 0");
+  if (yT && ldt < M) return fail("rsrx_linear_forward: ldt < M");
   p.dbg_t = gemm_dbg();
   CUDA_OK(gemm::launch(p, 0, (cudaStream_t)stream));
   return 0;
 }
 
-extern "C" int rsrx_linear_dgrad(const float* dz, int lddz, const float* w, int ldw, const float* zprev, int M, int Nin, int Nout,
-                                 int activation, float* dzprev, int ld, float* colsum_partials, void* stream) {
-  if (!dz || !w || !dzprev) return fail("rsrx_linear_dgrad: null argument");
+extern "C" int rsrx_linear_dgrad(const float* dz, int lddz, const float* w, int ldw, const float* wT, int ldwt, const float* zprev,
+                                 int M, int Nin, int Nout, int activation, float* dzprev, int ld, float* colsum_partials,
+                                 float* dzprevT, int ldt, void* stream) {
+  if (!dz || (!w && !wT) || !dzprev) return fail("rsrx_linear_dgrad: null argument");
   if (M <= 0 || Nin <= 0 || Nout <= 0 || (Nout & 3) || (Nin & 3) || activation < 0 || activation > 2 || (activation && !zprev))
     return fail("rsrx_linear_dgrad: bad sizes");
-  if (gemm_check("rsrx_linear_dgrad", dz, w, lddz, ldw)) return 1;
+  if (gemm_check("rsrx_linear_dgrad", dz, wT ? wT : w, lddz, wT ? ldwt : ldw)) return 1;
   gemm::Params p{};
   p.A = dz; p.a_row = lddz; p.a_col = 1;          // [M][Nout], contraction over the layer's outputs
-  p.B = w; p.b_row = 1; p.b_col = ldw;            // B[k'][n'] = w[n'][k']
+  if (wT) { p.B = wT; p.b_row = ldwt; p.b_col = 1; }  // wT[k'][n']: contiguous along the contraction -> TMA
+  else { p.B = w; p.b_row = 1; p.b_col = ldw; }       // B[k'][n'] = w[n'][k']: transposed while staged
   p.M = M; p.N = Nin; p.K = Nout; p.k_split = Nout;
   p.epilogue = gemm::EPI_DGRAD; p.act = activation; p.zprev = zprev; p.D = dzprev; p.colsum = colsum_partials; p.ldd = ld;
+  p.DT = dzprevT; p.ldt = ldt;
   if (((uintptr_t)dzprev & 15) || ((uintptr_t)zprev & 15) || (ld & 3)) return fail("rsrx_linear_dgrad: outputs must be 16-byte aligned, ld % 4 == 0");
+  if (dzprevT && ldt < M) return fail("rsrx_linear_dgrad: ldt < M");
   p.dbg_t = gemm_dbg();
-  CUDA_OK(gemm::launch(p, 1, (cudaStream_t)stream));
+  CUDA_OK(gemm::launch(p, wT ? 0 : 1, (cudaStream_t)stream));
   return 0;
 }
 
-extern "C" int rsrx_linear_wgrad(const float* dz, int lddz, const float* x, int ldx, int rows, int Nout, int Nin,
-                                 int rows_per_split, float* partials, int ldp, void* stream) {
+extern "C" int rsrx_linear_wgrad(const float* dz, int lddz, const float* x, int ldx, int transposed_inputs, int rows, int Nout,
+                                 int Nin, int rows_per_split, float* partials, int ldp, void* stream) {
   if (!dz || !x || !partials) return fail("rsrx_linear_wgrad: null argument");
   if (rows <= 0 || Nout <= 0 || Nin <= 0 || (Nout & 3) || (Nin & 3) || rows_per_split <= 0 || (rows_per_split % gemm::BK))
     return fail("rsrx_linear_wgrad: bad sizes (rows_per_split % 32 == 0)");
   if (gemm_check("rsrx_linear_wgrad", dz, x, lddz, ldx)) return 1;
   gemm::Params p{};
-  p.A = dz; p.a_row = 1; p.a_col = lddz;          // A[n'][m] = dz[m][n']
-  p.B = x; p.b_row = 1; p.b_col = ldx;            // B[k'][m] = x[m][k']
+  if (transposed_inputs) {  // dz = dZ^T [Nout][lddz >= rows], x = X^T [Nin][ldx >= rows]: contiguous along the contraction -> TMA
+    p.A = dz; p.a_row = lddz; p.a_col = 1;
+    p.B = x; p.b_row = ldx; p.b_col = 1;
+  } else {
+    p.A = dz; p.a_row = 1; p.a_col = lddz;        // A[n'][m] = dz[m][n']
+    p.B = x; p.b_row = 1; p.b_col = ldx;          // B[k'][m] = x[m][k']
+  }
   p.M = Nout; p.N = Nin; p.K = rows; p.k_split = rows_per_split;
   p.epilogue = gemm::EPI_PARTIAL; p.D = partials; p.ldd = ldp;
   if (((uintptr_t)partials & 15) || (ldp & 3)) return fail("rsrx_linear_wgrad: partials must be 16-byte aligned, ldp % 4 == 0");
   p.dbg_t = gemm_dbg();
-  CUDA_OK(gemm::launch(p, 2, (cudaStream_t)stream));
+  CUDA_OK(gemm::launch(p, transposed_inputs ? 0 : 2, (cudaStream_t)stream));
   return 0;
 }
 
@@ -699,20 +709,21 @@ extern "C" int rsrx_reduce_partials(const float* const* in, float* const* out, c
 
 extern "C" int rsrx_value_head_backward(const float* g, const float* w, const float* z, const float* h, int M, int n, int ld,
                                         int activation, float* dz, float* colsum_partials, float* dw_partials,
-                                        float* db_partials, void* stream) {
+                                        float* db_partials, float* dzT, int ldt, void* stream) {
   if (!g || !w || !h || !dz || !colsum_partials || !dw_partials || !db_partials || (activation && !z))
     return fail("rsrx_value_head_backward: null argument");
-  if (M <= 0 || n <= 0 || ld < n || activation < 0 || activation > 2) return fail("rsrx_value_head_backward: bad sizes");
+  if (M <= 0 || n <= 0 || ld < n || activation < 0 || activation > 2 || (dzT && ldt < M)) return fail("rsrx_value_head_backward: bad sizes");
   if ((n & 3) || (ld & 3)) return fail("rsrx_value_head_backward: n and ld must be multiples of 4");
   gemm::head_backward_kernel<<<dim3((M + 127) / 128, (n + 63) / 64), 256, 0, (cudaStream_t)stream>>>(g, w, z, h, M, n, ld, activation, dz,
-                                                                                colsum_partials, dw_partials, db_partials);
+                                                                                                  colsum_partials, dw_partials, db_partials,
+                                                                                                  dzT, ldt);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 extern "C" int rsrx_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                              const int32_t* sizes, int ntensors, float lr, float beta1, float beta2, float eps,
-                              float grad_scale, uint64_t* step_ticket, void* stream) {
+                              const int32_t* sizes, float* const* params_t, const int32_t* cols, int ntensors, float lr,
+                              float beta1, float beta2, float eps, float grad_scale, uint64_t* step_ticket, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !sizes || !step_ticket) return fail("rsrx_adam_step: null argument");
   if (ntensors <= 0 || ntensors > gemm::ADAM_MAXSEG) return fail("rsrx_adam_step: 1..32 tensors");
   gemm::AdamArgs a;
@@ -720,7 +731,10 @@ extern "C" int rsrx_adam_step(float* const* params, const float* const* grads, f
   a.ticket = reinterpret_cast<unsigned long long*>(step_ticket);
   for (int k = 0; k < ntensors; k++) {
     if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || sizes[k] <= 0) return fail("rsrx_adam_step: bad tensor");
-    a.seg[k] = {params[k], grads[k], exp_avg[k], exp_avg_sq[k], sizes[k]};
+    float* pt = params_t ? params_t[k] : nullptr;
+    const int c = (pt && cols) ? cols[k] : 1;
+    if (pt && (c <= 0 || sizes[k] % c)) return fail("rsrx_adam_step: bad transposed-copy shape");
+    a.seg[k] = {params[k], grads[k], exp_avg[k], exp_avg_sq[k], sizes[k], pt, c};
   }
   // a FIXED grid per tensor count: the step count is derived from tickets / blocks (see adam_kernel)
   const dim3 grid(8, ntensors);

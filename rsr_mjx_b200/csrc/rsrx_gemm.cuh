@@ -58,6 +58,8 @@ struct Params {
   float* Z;                           // [M][ldd]       (EPI_BIAS_ACT: pre-activation, may be null)
   float* colsum;                      // [gridDim.x][ldd] (EPI_DGRAD: per-CTA column sums of dZprev, may be null)
   int ldd;
+  float* DT; int ldt;                 // optional transposed copy of D: DT[col][row] ([N][ldt]) — the K-contiguous operand of
+                                      // the weight-gradient GEMM, written with row-contiguous (coalesced) stores
   int kcap;                           // contraction length staged at once (multiple of 32, <= KMAX): sizes the shared memory
   unsigned long long* dbg_t;          // profiling aid: 8 globaltimer stamps of CTA 0 (nullptr = off)
 };
@@ -333,6 +335,9 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
         for (int j = 0; j < 4; ++j)
           if (col + j < p.N) { if (p.Z) p.Z[off + j] = z[j]; p.D[off + j] = y[j]; }
       }
+      if (p.DT)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sC[rr * LDS + cq + j] = y[j];
     } else if (p.epilogue == EPI_DGRAD) {
       float zp[4] = {0.f, 0.f, 0.f, 0.f}, gg[4];
       if (p.act) {
@@ -343,9 +348,19 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
       for (int j = 0; j < 4; ++j) { gg[j] = (col + j < p.N) ? v[j] * act_bwd(p.act, zp[j]) : 0.f; cs[j] += gg[j]; }
       if (vec) *reinterpret_cast<float4*>(p.D + off) = make_float4(gg[0], gg[1], gg[2], gg[3]);
       else for (int j = 0; j < 4; ++j) if (col + j < p.N) p.D[off + j] = gg[j];
+      if (p.DT)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sC[rr * LDS + cq + j] = gg[j];
     } else {
       if (vec) *reinterpret_cast<float4*>(p.D + split_off + off) = make_float4(v[0], v[1], v[2], v[3]);
       else for (int j = 0; j < 4; ++j) if (col + j < p.N) p.D[split_off + off + j] = v[j];
+    }
+  }
+  if (p.DT && p.epilogue != EPI_PARTIAL) {  // pass 3: the transposed copy, a warp per column, lanes over 32 consecutive rows
+    __syncthreads();
+    for (int task = warp; task < BN * (BM / 32); task += THREADS / 32) {
+      const int c = task / (BM / 32), rr = (task % (BM / 32)) * 32 + lane;
+      if (n0 + c < p.N && m0 + rr < p.M) p.DT[(size_t)(n0 + c) * p.ldt + m0 + rr] = sC[rr * LDS + c];
     }
   }
   stamp(p, 7);
@@ -385,8 +400,9 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
                                                            const float* __restrict__ Z, const float* __restrict__ H, int M,
                                                            int n, int ld, int act, float* __restrict__ dZ,
                                                            float* __restrict__ colsum, float* __restrict__ dw_part,
-                                                           float* __restrict__ db_part) {
+                                                           float* __restrict__ db_part, float* __restrict__ dZT, int ldt) {
   __shared__ float red[2][16][64];
+  __shared__ float tile[128][65];  // for the transposed copy dZT[col][row]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int r0 = blockIdx.x * 128, col = blockIdx.y * 64 + tx * 4;
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, dw[4] = {0.f, 0.f, 0.f, 0.f};
@@ -409,6 +425,7 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
           d[j] = gm * wj[j] * act_bwd(act, zz[j]);
           cs[j] += d[j];
           dw[j] += gm * hh[j];
+          tile[ty + 16 * i][tx * 4 + j] = d[j];
         }
         *reinterpret_cast<float4*>(dZ + off) = make_float4(d[0], d[1], d[2], d[3]);
       }
@@ -417,6 +434,13 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
 #pragma unroll
   for (int j = 0; j < 4; ++j) { red[0][ty][tx * 4 + j] = cs[j]; red[1][ty][tx * 4 + j] = dw[j]; }
   __syncthreads();
+  if (dZT) {  // a warp per column, lanes over 32 consecutive rows: coalesced
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int task = warp; task < 64 * 4; task += 8) {
+      const int c = task >> 2, rr = (task & 3) * 32 + lane, cc = blockIdx.y * 64 + c;
+      if (cc < n && r0 + rr < M) dZT[(size_t)cc * ldt + r0 + rr] = tile[rr][c];
+    }
+  }
   if (threadIdx.x < 128) {
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
     float t = 0.f;
@@ -442,7 +466,7 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
 // captured CUDA graph advances it on every replay: every block takes a ticket from a 64-bit counter, launch k (k = 0, 1,
 // ...) owns tickets [k * blocks, (k + 1) * blocks) — launches on a stream do not overlap — so t = ticket / blocks + 1 in
 // every block without a second kernel or a read/write race.
-struct AdamSeg { float* p; const float* g; float* m; float* v; int n; };
+struct AdamSeg { float* p; const float* g; float* m; float* v; int n; float* pT; int cols; };  // pT: optional [cols][n / cols] copy
 constexpr int ADAM_MAXSEG = 32;
 struct AdamArgs { AdamSeg seg[ADAM_MAXSEG]; int nseg; float lr, beta1, beta2, eps, grad_scale; unsigned long long* ticket; };
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
@@ -461,7 +485,9 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     const float m = a.beta1 * sg.m[i] + (1.f - a.beta1) * gr;
     const float v = a.beta2 * sg.v[i] + (1.f - a.beta2) * gr * gr;
     sg.m[i] = m; sg.v[i] = v;
-    sg.p[i] -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+    const float pn = sg.p[i] - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+    sg.p[i] = pn;
+    if (sg.pT) sg.pT[(size_t)(i % sg.cols) * (sg.n / sg.cols) + i / sg.cols] = pn;  // transposed weights for the dgrad GEMM's TMA
   }
 }
 
@@ -514,7 +540,8 @@ inline cudaError_t launch_one(Params p, dim3 grid, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// mode 0 forward (A, B K-major), 1 dgrad (A K-major, B MN-major), 2 wgrad (A, B MN-major)
+// mode 0: A and B contiguous along the contraction (both by TMA: forward, dgrad with a transposed weight copy, wgrad on
+// transposed activation copies); 1: B contiguous along its rows (dgrad straight from W); 2: both (wgrad from dZ and X)
 inline cudaError_t launch(const Params& p, int mode, cudaStream_t stream) {
   constexpr int BN = 64;  // 128 x 64 tiles: 88 CTAs for a 2816 x 256 output
   const int splits = (p.K + p.k_split - 1) / p.k_split;

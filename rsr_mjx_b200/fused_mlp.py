@@ -48,12 +48,20 @@ class TensorCoreMLP:
         self.k0p = (self.k0 + 31) // 32 * 32
         z = lambda *s: torch.zeros(*s, device=self.dev)
         M = self.rows
+        self.ldt = (M + 3) // 4 * 4   # leading dimension of the transposed copies ([width][rows]: contraction-contiguous for wgrad)
         self.x_pad = z(M, self.k0p)
+        self.xT = z(self.k0p, self.ldt)
         self.w0_pad = z(self.hidden[0].out_features, self.k0p)
         self.Z = [z(M, l.out_features) for l in self.hidden]
         self.H = [z(M, l.out_features) for l in self.hidden]
+        self.HT = [z(l.out_features, self.ldt) for l in self.hidden[:-1]]  # inputs of layers 1 .. (the last H only feeds the head)
         wmax = max(l.out_features for l in self.hidden)
-        self.dZ = [z(M, wmax), z(M, wmax)]  # ping-pong, used with the layer's own leading dimension
+        self.dZ = [z(M, wmax), z(M, wmax)]     # ping-pong, used with the layer's own leading dimension
+        self.dZT = [z(wmax, self.ldt), z(wmax, self.ldt)]
+        # transposed weight copies [in][out] of layers 1 .. for the dgrad GEMM's TMA; kept current by FusedAdam (wT_of), or
+        # refreshed at the start of forward() when another optimiser is used
+        self.WT = {l.weight: z(l.in_features, l.out_features) for l in self.hidden[1:]}
+        self.wt_fresh = False
         self.mtiles = (M + 127) // 128
         self.splits = (M + self.ROWS_PER_SPLIT - 1) // self.ROWS_PER_SPLIT
         self.colsum = [z(self.mtiles, l.out_features) for l in self.hidden]
@@ -70,6 +78,10 @@ class TensorCoreMLP:
         for p, g in self.grads.items():
             p.grad = g
 
+    def refresh_transposed_weights(self) -> None:
+        for w, wt in self.WT.items():
+            wt.copy_(w.detach().t())
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
@@ -80,14 +92,18 @@ class TensorCoreMLP:
         L, M, s = _lib.lib(), self.rows, self._stream()
         if tuple(x.shape) != (M, self.k0):
             raise ValueError(f"expected input [{M}, {self.k0}], got {tuple(x.shape)}")
+        if not self.wt_fresh:
+            self.refresh_transposed_weights()
         self.x_pad[:, :self.k0].copy_(x)
+        self.xT[:self.k0, :M].copy_(x.t())
         self.w0_pad[:, :self.k0].copy_(self.hidden[0].weight)
         h, ldh, k = self.x_pad, self.k0p, self.k0p
         for i, l in enumerate(self.hidden):
             w = self.w0_pad if i == 0 else l.weight
             n = l.out_features
+            ht = self.HT[i].data_ptr() if i < len(self.HT) else None
             _lib.check(L.rsrx_linear_forward(h.data_ptr(), ldh, w.data_ptr(), k, l.bias.data_ptr(), M, n, k, self.act,
-                                             self.Z[i].data_ptr(), self.H[i].data_ptr(), n, s), "rsrx_linear_forward")
+                                             self.Z[i].data_ptr(), self.H[i].data_ptr(), n, ht, self.ldt, s), "rsrx_linear_forward")
             h, ldh, k = self.H[i], n, n
         out = self.layers[-1]
         return torch.addmv(out.bias.expand(M), h, out.weight[0])
@@ -103,17 +119,20 @@ class TensorCoreMLP:
         cur = 0
         _lib.check(L.rsrx_value_head_backward(g.data_ptr(), out.weight.data_ptr(), self.Z[-1].data_ptr(), self.H[-1].data_ptr(),
                                               M, n, n, self.act, self.dZ[cur].data_ptr(), self.colsum[-1].data_ptr(),
-                                              self.dw_out_part.data_ptr(), self.db_out_part.data_ptr(), s),
-                   "rsrx_value_head_backward")
+                                              self.dw_out_part.data_ptr(), self.db_out_part.data_ptr(),
+                                              self.dZT[cur].data_ptr(), self.ldt, s), "rsrx_value_head_backward")
         for i in range(nh - 1, -1, -1):
             l = self.hidden[i]
             n, kin = l.out_features, (self.k0p if i == 0 else l.in_features)
-            x = self.x_pad if i == 0 else self.H[i - 1]
-            _lib.check(L.rsrx_linear_wgrad(self.dZ[cur].data_ptr(), n, x.data_ptr(), kin, M, n, kin, self.ROWS_PER_SPLIT,
-                                           self.wpart[i].data_ptr(), kin, s), "rsrx_linear_wgrad")
+            xt = self.xT if i == 0 else self.HT[i - 1]
+            # dW_l partials = dZ_l^T X_{l-1}: both operands from their transposed copies (contraction-contiguous, TMA)
+            _lib.check(L.rsrx_linear_wgrad(self.dZT[cur].data_ptr(), self.ldt, xt.data_ptr(), self.ldt, 1, M, n, kin,
+                                           self.ROWS_PER_SPLIT, self.wpart[i].data_ptr(), kin, s), "rsrx_linear_wgrad")
             if i > 0:
-                _lib.check(L.rsrx_linear_dgrad(self.dZ[cur].data_ptr(), n, l.weight.data_ptr(), kin, self.Z[i - 1].data_ptr(), M,
-                                               kin, n, self.act, self.dZ[1 - cur].data_ptr(), kin, self.colsum[i - 1].data_ptr(), s),
+                wt = self.WT[l.weight]
+                _lib.check(L.rsrx_linear_dgrad(self.dZ[cur].data_ptr(), n, l.weight.data_ptr(), kin, wt.data_ptr(), n,
+                                               self.Z[i - 1].data_ptr(), M, kin, n, self.act, self.dZ[1 - cur].data_ptr(), kin,
+                                               self.colsum[i - 1].data_ptr(), self.dZT[1 - cur].data_ptr(), self.ldt, s),
                            "rsrx_linear_dgrad")
                 cur = 1 - cur
         if self._reduce_args is None:
@@ -141,7 +160,9 @@ class FusedAdam:
     (1 / world_size after a sum all-reduce).  Same update rule as torch / optax.adam (bias-corrected first and second
     moments, eps outside the square root)."""
 
-    def __init__(self, params, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
+    def __init__(self, params, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0, transposed=None):
+        """transposed: {parameter: tensor [cols, rows]} — 2-D parameters whose transposed copy the step keeps current
+        (TensorCoreMLP.WT: the weight operand of the dgrad GEMM)"""
         self.params: List[torch.Tensor] = [p for p in params]
         if not self.params or len(self.params) > 32:
             raise ValueError("FusedAdam takes 1..32 parameter tensors")
@@ -156,6 +177,13 @@ class FusedAdam:
         self._m = (C.c_void_p * k)(*[t.data_ptr() for t in self.exp_avg])
         self._v = (C.c_void_p * k)(*[t.data_ptr() for t in self.exp_avg_sq])
         self._n = (C.c_int32 * k)(*[p.numel() for p in self.params])
+        tr = dict(transposed or {})
+        for p, t in tr.items():
+            if p.dim() != 2 or tuple(t.shape) != (p.shape[1], p.shape[0]) or not t.is_contiguous():
+                raise ValueError("FusedAdam: a transposed copy must be a contiguous [cols, rows] tensor of a 2-D parameter")
+        self._keep_t = tr
+        self._pt = (C.c_void_p * k)(*[(tr[p].data_ptr() if p in tr else None) for p in self.params])
+        self._cols = (C.c_int32 * k)(*[(p.shape[1] if p in tr else 1) for p in self.params])
 
     @property
     def state(self):
@@ -188,7 +216,7 @@ class FusedAdam:
         gp = (C.c_void_p * k)(*[g.data_ptr() for g in gs])
         dev = self.params[0].device
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().rsrx_adam_step(self._p, gp, self._m, self._v, self._n, k, self.lr, self.betas[0], self.betas[1],
+            _lib.check(_lib.lib().rsrx_adam_step(self._p, gp, self._m, self._v, self._n, self._pt, self._cols, k, self.lr, self.betas[0], self.betas[1],
                                                  self.eps, self.grad_scale, self.ticket.data_ptr(),
                                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "rsrx_adam_step")
 

@@ -568,7 +568,10 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         if fused_mlp.warp_supported(net.policy, dev):  # the reference's policy (32,)*4: one launch per direction
             ptc = fused_mlp.WarpMLP(net.policy, mb * T, dev)
         # one-launch Adam over all ~22 tensors (same update rule as torch.optim.Adam / optax.adam)
-        opt = fused_mlp.FusedAdam(params, lr=learning_rate, eps=1e-8)
+        # (its step also keeps the transposed weight copies of the value network current: the dgrad GEMM's TMA operand)
+        opt = fused_mlp.FusedAdam(params, lr=learning_rate, eps=1e-8, transposed=vtc.WT)
+        vtc.refresh_transposed_weights()
+        vtc.wt_fresh = True
         head_ws = torch.empty(2 * mb * T, device=dev)
         head_out = torch.empty(4, device=dev)
         g_logits_buf = torch.empty(mb, T, 2 * act_size, device=dev)
