@@ -259,8 +259,8 @@ int rsrx_small_mlp_backward_ctas(int rows);
  * as grads[k][i] * grad_scale (1 / world_size after a sum all-reduce).  params_t / cols (both may be NULL): where
  * params_t[k] != NULL the updated tensor, seen as [sizes[k] / cols[k]][cols[k]], is also written transposed to
  * params_t[k] ([cols][rows]: the weight copy rsrx_linear_dgrad loads by TMA).  step_ticket: one device uint64, zero
- * before the first step, advanced by the kernel itself (so a captured CUDA graph keeps counting on every replay); the
- * number of steps taken is *step_ticket / (8 * ntensors): keep ntensors fixed for a given ticket. */
+ * before the first step, advanced by the kernel itself (so a captured CUDA graph keeps counting on every replay): its low
+ * 32 bits are the number of steps taken, the high 32 bits a scratch counter that is zero between launches. */
 int rsrx_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                    const int32_t* sizes, float* const* params_t, const int32_t* cols, int ntensors, float lr, float beta1,
                    float beta2, float eps, float grad_scale, uint64_t* step_ticket, void* stream);

@@ -728,7 +728,7 @@ extern "C" int rsrx_adam_step(float* const* params, const float* const* grads, f
   if (ntensors <= 0 || ntensors > gemm::ADAM_MAXSEG) return fail("rsrx_adam_step: 1..32 tensors");
   gemm::AdamArgs a;
   a.nseg = ntensors; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
-  a.ticket = reinterpret_cast<unsigned long long*>(step_ticket);
+  a.counters = reinterpret_cast<unsigned int*>(step_ticket);  // {steps taken, blocks done}
   for (int k = 0; k < ntensors; k++) {
     if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || sizes[k] <= 0) return fail("rsrx_adam_step: bad tensor");
     float* pt = params_t ? params_t[k] : nullptr;
@@ -736,8 +736,7 @@ extern "C" int rsrx_adam_step(float* const* params, const float* const* grads, f
     if (pt && (c <= 0 || sizes[k] % c)) return fail("rsrx_adam_step: bad transposed-copy shape");
     a.seg[k] = {params[k], grads[k], exp_avg[k], exp_avg_sq[k], sizes[k], pt, c};
   }
-  // a FIXED grid per tensor count: the step count is derived from tickets / blocks (see adam_kernel)
-  const dim3 grid(8, ntensors);
+  const dim3 grid(gemm::ADAM_BLOCKS_X, ntensors);
   gemm::adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -761,12 +760,14 @@ static int small_net(const float* const* weights, const float* const* biases, co
   if (total) *total = t;
   return 0;
 }
-static int small_grid(int rows) {
+// CTAs of the warp-per-row kernels: a row is a ~1000-instruction dependent chain on its warp, so the rows are spread as
+// widely as the chip allows (one CTA per SM at 2560 rows: ~2 rows per warp; 40 CTAs of 8 rows per warp measured 94 vs 51 us)
+static int small_grid(int rows, int rows_per_warp) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return std::max(1, std::min(sms, (rows + smallmlp::WARPS - 1) / smallmlp::WARPS));
+  return std::max(1, std::min(sms, (rows + smallmlp::WARPS * rows_per_warp - 1) / (smallmlp::WARPS * rows_per_warp)));
 }
-extern "C" int rsrx_small_mlp_backward_ctas(int rows) { return small_grid(rows); }
+extern "C" int rsrx_small_mlp_backward_ctas(int rows) { return small_grid(rows, 2); }
 
 extern "C" int rsrx_small_mlp_forward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
                                       int activation, const float* x, int ldx, int rows, float* zs, float* out, int ldo,
@@ -777,7 +778,7 @@ extern "C" int rsrx_small_mlp_forward(const float* const* weights, const float* 
   const size_t smem = smallmlp::fwd_smem(nlayers);
   static bool set = false;
   if (!set) { CUDA_OK(cudaFuncSetAttribute(smallmlp::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smallmlp::fwd_smem(smallmlp::MAXL))); set = true; }
-  smallmlp::forward_kernel<<<small_grid(rows), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, out, ldo);
+  smallmlp::forward_kernel<<<small_grid(rows, 2), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, out, ldo);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -793,7 +794,7 @@ extern "C" int rsrx_small_mlp_backward(const float* const* weights, const float*
   if (smem > 227 * 1024) return fail("rsrx_small_mlp_backward: too many layers for the shared-memory accumulators");
   static bool set = false;
   if (!set) { CUDA_OK(cudaFuncSetAttribute(smallmlp::backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-  smallmlp::backward_kernel<<<small_grid(rows), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, grad_out, ldg,
+  smallmlp::backward_kernel<<<small_grid(rows, 2), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, grad_out, ldg,
                                                                                                  partials, total);
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -386,7 +386,15 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
   const ReduceSeg& sg = a.seg[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
     float t = 0.f;
-    for (int s = 0; s < sg.S; ++s) t += sg.in[(size_t)s * sg.stride + i];
+    int s = 0;
+    for (; s + 8 <= sg.S; s += 8) {  // 8 loads in flight; added in slice order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = sg.in[(size_t)(s + u) * sg.stride + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
+    for (; s < sg.S; ++s) t += sg.in[(size_t)s * sg.stride + i];
     sg.out[i] = t;
   }
 }
@@ -463,31 +471,58 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
 
 // Adam on a list of tensors in one launch (torch.optim.Adam semantics, no weight decay / amsgrad): the trainers' networks
 // have ~24 small tensors; torch's multi-tensor kernel takes 40 us on them.  The step count lives on the device so that a
-// captured CUDA graph advances it on every replay: every block takes a ticket from a 64-bit counter, launch k (k = 0, 1,
-// ...) owns tickets [k * blocks, (k + 1) * blocks) — launches on a stream do not overlap — so t = ticket / blocks + 1 in
-// every block without a second kernel or a read/write race.
+// captured CUDA graph advances it on every replay: every block READS the count k at its start (plain load) and bumps a
+// `done` counter at its end; the last block to finish publishes k + 1 and clears `done`.  Launches on a stream do not
+// overlap, and the count only changes after every block has read it: no race, no second kernel, and no atomic on any
+// block's critical path.  counters = {step count, done} (two 32-bit words of the caller's uint64 ticket).
 struct AdamSeg { float* p; const float* g; float* m; float* v; int n; float* pT; int cols; };  // pT: optional [cols][n / cols] copy
 constexpr int ADAM_MAXSEG = 32;
-struct AdamArgs { AdamSeg seg[ADAM_MAXSEG]; int nseg; float lr, beta1, beta2, eps, grad_scale; unsigned long long* ticket; };
+constexpr int ADAM_BLOCKS_X = 16;
+struct AdamArgs { AdamSeg seg[ADAM_MAXSEG]; int nseg; float lr, beta1, beta2, eps, grad_scale; unsigned int* counters; };
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
-  __shared__ float t_s;
-  if (threadIdx.x == 0) {
-    const unsigned long long blocks = (unsigned long long)gridDim.x * gridDim.y;
-    t_s = (float)(atomicAdd(a.ticket, 1ull) / blocks + 1ull);
-  }
-  __syncthreads();
+  __shared__ float tile[32][33];
   const AdamSeg& sg = a.seg[blockIdx.y];
-  const float t = t_s;
-  const float bc1 = 1.f - powf(a.beta1, t), bc2 = 1.f - powf(a.beta2, t);
+  const unsigned int k_now = *reinterpret_cast<volatile unsigned int*>(a.counters);
+  const float t = (float)(k_now + 1u);
+  const float bc1 = 1.f - expf(t * logf(a.beta1)), bc2 = 1.f - expf(t * logf(a.beta2));
   const float step_size = a.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
+  auto update = [&](int i) {
     const float gr = sg.g[i] * a.grad_scale;
     const float m = a.beta1 * sg.m[i] + (1.f - a.beta1) * gr;
     const float v = a.beta2 * sg.v[i] + (1.f - a.beta2) * gr * gr;
     sg.m[i] = m; sg.v[i] = v;
     const float pn = sg.p[i] - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
     sg.p[i] = pn;
-    if (sg.pT) sg.pT[(size_t)(i % sg.cols) * (sg.n / sg.cols) + i / sg.cols] = pn;  // transposed weights for the dgrad GEMM's TMA
+    return pn;
+  };
+  if (!sg.pT) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) update(i);
+  } else {
+  // 2-D tensor with a transposed copy (the dgrad GEMM's TMA operand): 32 x 32 tiles through shared memory, so that both
+  // the parameter and its transpose are written with contiguous rows
+  const int cols = sg.cols, rows = sg.n / cols;
+  const int tc = (cols + 31) / 32, tr = (rows + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int tl = blockIdx.x; tl < tc * tr; tl += gridDim.x) {
+    const int r0 = (tl / tc) * 32, c0 = (tl % tc) * 32;
+    __syncthreads();
+    for (int y = ty; y < 32; y += 8)
+      if (r0 + y < rows && c0 + tx < cols) tile[y][tx] = update((r0 + y) * cols + c0 + tx);
+    __syncthreads();
+    for (int y = ty; y < 32; y += 8)
+      if (c0 + y < cols && r0 + tx < rows) sg.pT[(size_t)(c0 + y) * rows + r0 + tx] = tile[tx][y];
+  }
+  }
+  // the last block to finish advances the step count
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int blocks = gridDim.x * gridDim.y;
+    if (atomicAdd(a.counters + 1, 1u) == blocks - 1) {
+      a.counters[1] = 0u;
+      a.counters[0] = k_now + 1u;
+      __threadfence();
+    }
   }
 }
 

@@ -39,23 +39,37 @@ __global__ void __launch_bounds__(32 * WARPS) forward_kernel(const Net net, cons
   extern __shared__ float sm[];  // Wt[l][k][j] = W[l][j][k], padded to WD x WD; then bias[l][WD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* sb = sm + net.nl * WD * WD;
+  // all weights of all layers in flight at once (4-byte cp.async straight into the transposed, zero-padded image): one
+  // global round trip for the prologue instead of one per layer
+  for (int i = tid; i < net.nl * WD * WD; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
   for (int l = 0; l < net.nl; ++l) {
     const int win = net.width[l], wout = net.width[l + 1];
-    for (int i = tid; i < WD * WD; i += blockDim.x) {
+    for (int i = tid; i < win * WD; i += blockDim.x) {  // shared-memory order: consecutive lanes write consecutive words
       const int k = i / WD, j = i % WD;
-      sm[l * WD * WD + i] = (k < win && j < wout) ? net.W[l][j * win + k] : 0.f;
+      if (j < wout)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sm + l * WD * WD + i)),
+                     "l"(net.W[l] + j * win + k) : "memory");
     }
     if (tid < WD) sb[l * WD + tid] = tid < wout ? net.b[l][tid] : 0.f;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     float h = lane < net.width[0] ? x[(size_t)row * ldx + lane] : 0.f;
     for (int l = 0; l < net.nl; ++l) {
       const int win = net.width[l];
       const float* wt = sm + l * WD * WD;
-      float z = sb[l * WD + lane];
-#pragma unroll 8
-      for (int k = 0; k < win; ++k) z += __shfl_sync(0xffffffffu, h, k) * wt[k * WD + lane];
+      // four partial sums: the 32-term dot product is otherwise one chain of dependent FMAs behind shared-memory loads
+      float z0 = sb[l * WD + lane], z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll 2
+      for (int k = 0; k < win; k += 4) {  // rows k >= win of wt are zero, h of lanes >= win is zero or unused
+        z0 += __shfl_sync(0xffffffffu, h, k) * wt[k * WD + lane];
+        z1 += __shfl_sync(0xffffffffu, h, k + 1) * wt[(k + 1) * WD + lane];
+        z2 += __shfl_sync(0xffffffffu, h, k + 2) * wt[(k + 2) * WD + lane];
+        z3 += __shfl_sync(0xffffffffu, h, k + 3) * wt[(k + 3) * WD + lane];
+      }
+      const float z = (z0 + z1) + (z2 + z3);
       if (l + 1 < net.nl) {
         zs[((size_t)l * rows + row) * WD + lane] = z;
         h = act_f(net.act, z);
@@ -75,33 +89,57 @@ __global__ void __launch_bounds__(32 * WARPS) backward_kernel(const Net net, con
   const int nl = net.nl, per_warp = nl * WD * WD + nl * WD;
   float* sW = sm;
   float* acc = sm + nl * WD * WD + warp * per_warp;
-  for (int l = 0; l < nl; ++l) {
-    const int win = net.width[l], wout = net.width[l + 1];
-    for (int i = tid; i < WD * WD; i += blockDim.x) {
-      const int j = i / WD, k = i % WD;
-      sW[l * WD * WD + i] = (k < win && j < wout) ? net.W[l][j * win + k] : 0.f;
-    }
-  }
+  for (int i = tid; i < nl * WD * WD; i += blockDim.x) sW[i] = 0.f;
   for (int i = lane; i < per_warp; i += 32) acc[i] = 0.f;
   __syncthreads();
+  for (int l = 0; l < nl; ++l) {  // every layer's weights in flight at once
+    const int win = net.width[l], wout = net.width[l + 1];
+    for (int i = tid; i < wout * win; i += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sW + l * WD * WD + (i / win) * WD + i % win)),
+                   "l"(net.W[l] + i) : "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
   for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
+    // everything this row reads from global memory is requested up front (one latency per row instead of one per layer)
     float dz = lane < net.width[nl] ? g[(size_t)row * ldg + lane] : 0.f;
-    for (int l = nl - 1; l >= 0; --l) {
+    const float xr = lane < net.width[0] ? x[(size_t)row * ldx + lane] : 0.f;
+    float zr[MAXL - 1];
+#pragma unroll
+    for (int l = 0; l < MAXL - 1; ++l) zr[l] = l < nl - 1 ? zs[((size_t)l * rows + row) * WD + lane] : 0.f;
+#pragma unroll
+    for (int l = MAXL - 1; l >= 0; --l) {
+      if (l >= nl) continue;
       const int win = net.width[l], wout = net.width[l + 1];
       float zprev = 0.f, hprev;
-      if (l == 0) hprev = lane < win ? x[(size_t)row * ldx + lane] : 0.f;
-      else { zprev = zs[((size_t)(l - 1) * rows + row) * WD + lane]; hprev = act_f(net.act, zprev); }
+      if (l == 0) hprev = xr;
+      else { zprev = zr[l - 1]; hprev = act_f(net.act, zprev); }
       float* aW = acc + l * WD * WD;
       // dW[j][k] += dz[j] h[k]: lane j owns column j of the transposed accumulator
-#pragma unroll 8
-      for (int k = 0; k < win; ++k) aW[k * WD + lane] += dz * __shfl_sync(0xffffffffu, hprev, k);
+      // read-modify-write in batches of 8 independent entries (the compiler cannot prove the accumulators do not alias
+      // the weights, so a plain loop serialises load -> FMA -> store)
+#pragma unroll 1
+      for (int k0 = 0; k0 < win; k0 += 8) {
+        float t8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t8[u] = aW[(k0 + u) * WD + lane];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t8[u] += dz * __shfl_sync(0xffffffffu, hprev, k0 + u);  // lanes >= win hold hprev = 0
+#pragma unroll
+        for (int u = 0; u < 8; ++u) aW[(k0 + u) * WD + lane] = t8[u];
+      }
       acc[nl * WD * WD + l * WD + lane] += dz;
       if (l > 0) {
         const float* w = sW + l * WD * WD;
-        float dh = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < wout; ++j) dh += __shfl_sync(0xffffffffu, dz, j) * w[j * WD + lane];
-        dz = lane < win ? dh * act_d(net.act, zprev) : 0.f;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < wout; j += 4) {  // rows j >= wout of w are zero
+          d0 += __shfl_sync(0xffffffffu, dz, j) * w[j * WD + lane];
+          d1 += __shfl_sync(0xffffffffu, dz, j + 1) * w[(j + 1) * WD + lane];
+          d2 += __shfl_sync(0xffffffffu, dz, j + 2) * w[(j + 2) * WD + lane];
+          d3 += __shfl_sync(0xffffffffu, dz, j + 3) * w[(j + 3) * WD + lane];
+        }
+        dz = lane < win ? ((d0 + d1) + (d2 + d3)) * act_d(net.act, zprev) : 0.f;
       }
     }
   }
@@ -112,11 +150,14 @@ __global__ void __launch_bounds__(32 * WARPS) backward_kernel(const Net net, con
   const float* acc0 = sm + nl * WD * WD;
   for (int l = 0; l < nl; ++l) {
     const int win = net.width[l], wout = net.width[l + 1];
-    for (int i = tid; i < wout * win; i += blockDim.x) {
-      const int j = i / win, k = i % win;
+    // walk the accumulators in THEIR order (k-major: consecutive threads read consecutive words; the parameter-order walk
+    // was a 32-way bank conflict and 20 us per launch) and scatter the sums to parameter order
+    for (int i = tid; i < win * WD; i += blockDim.x) {
+      const int k = i / WD, j = i % WD;
+      if (j >= wout) continue;
       float t = 0.f;
-      for (int w = 0; w < WARPS; ++w) t += acc0[w * per_warp + l * WD * WD + k * WD + j];
-      outp[off + i] = t;
+      for (int w = 0; w < WARPS; ++w) t += acc0[w * per_warp + l * WD * WD + i];
+      outp[off + j * win + k] = t;
     }
     off += wout * win;
     for (int j = tid; j < wout; j += blockDim.x) {

@@ -192,7 +192,7 @@ class FusedAdam:
 
     @property
     def steps_taken(self) -> int:
-        return int(self.ticket.item()) // (8 * len(self.params))
+        return int(self.ticket.item()) & 0xFFFFFFFF
 
     def reset_state(self) -> None:
         for t in self.exp_avg + self.exp_avg_sq:
