@@ -206,6 +206,13 @@ int rsrx_ppo_head(const float* logits, const float* baseline, const float* boots
                   float clipping_epsilon, float entropy_cost, int normalize_advantage, float* workspace, float* out,
                   float* grad_logits, float* grad_baseline, void* stream);
 
+/* Minibatch input preparation of the fused PPO update (RSR/losses.py:120-131: normalize_fn(data.observation), the
+ * bootstrap observation data.next_observation[-1]) in one launch: obs / next_obs [mb][T][O], running-statistics mean / std
+ * [O] -> obs_n [mb*T][O] (policy input), x_pad [mb*T + mb][ldp] (value input: the normalised observations then the mb
+ * normalised bootstrap observations, zero-padded to ldp >= O columns) and its transpose xT [ldp][ldt >= mb*T + mb]. */
+int rsrx_ppo_prep(const float* obs, const float* next_obs, const float* mean, const float* std, int mb, int T, int O,
+                  float* obs_n, float* x_pad, int ldp, float* xT, int ldt, void* stream);
+
 /* ---- tensor-core linear layers for the trainers' value networks (csrc/rsrx_gemm.cuh: TMA loads, tcgen05.mma kind::tf32,
  * fp32 accumulation in TMEM, fused epilogues).  Replaces torch.addmm + SiLU + SiLU' + bias-gradient launches of the value
  * MLP of RSR/train.py (brax make_ppo_networks, value_hidden_layer_sizes (256,)*5) / the critics of RSR/sac_train.py.

@@ -799,3 +799,12 @@ extern "C" int rsrx_small_mlp_backward(const float* const* weights, const float*
   CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+extern "C" int rsrx_ppo_prep(const float* obs, const float* next_obs, const float* mean, const float* std, int mb, int T, int O,
+                             float* obs_n, float* x_pad, int ldp, float* xT, int ldt, void* stream) {
+  if (!obs || !next_obs || !mean || !std || !obs_n || !x_pad || !xT) return fail("rsrx_ppo_prep: null argument");
+  if (mb <= 0 || T <= 0 || O <= 0 || ldp < O || ldt < mb * T + mb) return fail("rsrx_ppo_prep: bad sizes");
+  return ppo::launch_prep(obs, next_obs, mean, std, mb, T, O, obs_n, x_pad, ldp, xT, ldt, (cudaStream_t)stream)
+             ? fail(std::string("rsrx_ppo_prep: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}

@@ -281,3 +281,48 @@ inline int launch_act(const float* logits, const float* noise, int N, int A, flo
 
 }  // namespace ppo
 }  // namespace rsrx
+
+// ---- minibatch input preparation for the fused PPO update: one launch instead of seven ------------------------------
+// From the gathered minibatch (obs / next_obs [mb][T][O]) and the running-statistics normaliser (mean, std [O]):
+//   obs_n [mb * T][O]                 normalised observations (policy input)
+//   x_pad [mb * T + mb][ldp]          value-network input, zero-padded to ldp columns: the mb * T normalised observations
+//                                     followed by the mb normalised bootstrap observations next_obs[:, T - 1]
+//   xT    [ldp][ldt]                  its transpose (the contraction-contiguous operand of the first layer's weight gradient)
+// 32 x 32 tiles through shared memory so that both layouts are written with contiguous rows.
+namespace rsrx {
+namespace ppo {
+
+__global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ obs, const float* __restrict__ next_obs,
+                                                   const float* __restrict__ mean, const float* __restrict__ stdv, int mb, int T,
+                                                   int O, float* __restrict__ obs_n, float* __restrict__ x_pad, int ldp,
+                                                   float* __restrict__ xT, int ldt) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int rows = mb * T + mb, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int col = c0 + tx;
+  const float mu = col < O ? mean[col] : 0.f, isd = col < O ? 1.f / stdv[col] : 0.f;
+  for (int y = ty; y < 32; y += 8) {
+    const int row = r0 + y;
+    float v = 0.f;
+    if (row < rows && col < O) {
+      const float* src = row < mb * T ? obs + (size_t)row * O : next_obs + ((size_t)(row - mb * T) * T + (T - 1)) * O;
+      v = (src[col] - mu) * isd;
+      if (row < mb * T) obs_n[(size_t)row * O + col] = v;
+    }
+    if (row < rows && col < ldp) x_pad[(size_t)row * ldp + col] = v;
+    tile[y][tx] = v;
+  }
+  __syncthreads();
+  for (int y = ty; y < 32; y += 8)
+    if (c0 + y < ldp && r0 + tx < rows) xT[(size_t)(c0 + y) * ldt + r0 + tx] = tile[tx][y];
+}
+
+inline int launch_prep(const float* obs, const float* next_obs, const float* mean, const float* stdv, int mb, int T, int O,
+                       float* obs_n, float* x_pad, int ldp, float* xT, int ldt, cudaStream_t stream) {
+  const int rows = mb * T + mb;
+  prep_kernel<<<dim3((rows + 31) / 32, (ldp + 31) / 32), 256, 0, stream>>>(obs, next_obs, mean, stdv, mb, T, O, obs_n, x_pad, ldp, xT, ldt);
+  return cudaGetLastError() != cudaSuccess;
+}
+
+}  // namespace ppo
+}  // namespace rsrx

@@ -88,14 +88,16 @@ class TensorCoreMLP:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x [rows, in_features] (CUDA float32) -> values [rows]"""
+        """x [rows, in_features] (CUDA float32) -> values [rows].  x = None: the caller has already written the padded input
+        and its transpose into self.x_pad / self.xT (rsrx_ppo_prep does, in the trainer)."""
         L, M, s = _lib.lib(), self.rows, self._stream()
-        if tuple(x.shape) != (M, self.k0):
-            raise ValueError(f"expected input [{M}, {self.k0}], got {tuple(x.shape)}")
+        if x is not None:
+            if tuple(x.shape) != (M, self.k0):
+                raise ValueError(f"expected input [{M}, {self.k0}], got {tuple(x.shape)}")
+            self.x_pad[:, :self.k0].copy_(x)
+            self.xT[:self.k0, :M].copy_(x.t())
         if not self.wt_fresh:
             self.refresh_transposed_weights()
-        self.x_pad[:, :self.k0].copy_(x)
-        self.xT[:self.k0, :M].copy_(x.t())
         self.w0_pad[:, :self.k0].copy_(self.hidden[0].weight)
         h, ldh, k = self.x_pad, self.k0p, self.k0p
         for i, l in enumerate(self.hidden):

@@ -578,6 +578,10 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         g_values_buf = torch.zeros(rows_v, device=dev)  # the bootstrap rows keep a zero gradient (vs is stop-gradient)
         hyper = (float(reward_scaling), float(discounting), float(gae_lambda), float(clipping_epsilon), float(entropy_cost),
                  int(bool(normalize_advantage)))
+        obs_n_buf = torch.empty(mb * T, obs_size, device=dev)
+        # the normaliser's tensors are updated in place, so the prep kernel can keep reading them; identity when off
+        prep_mean = norm.mean if normalize_observations else torch.zeros(obs_size, device=dev)
+        prep_std = norm.std if normalize_observations else torch.ones(obs_size, device=dev)
 
     def fwd_bwd_tc(noise=None):
         from . import _lib
@@ -585,15 +589,20 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         opt.zero_grad(set_to_none=True)
         vtc.attach_grads()
         obs = static["observation"]
-        obs_n = normalize(obs)
+        # normalised policy / value inputs (+ the padded, transposed copies the tensor-core layers read): one launch
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rsrx_ppo_prep(obs.data_ptr(), static["next_observation"].data_ptr(), prep_mean.data_ptr(),
+                                                prep_std.data_ptr(), mb, T, obs_size, obs_n_buf.data_ptr(), vtc.x_pad.data_ptr(),
+                                                vtc.k0p, vtc.xT.data_ptr(), vtc.ldt, torch.cuda.current_stream(dev).cuda_stream),
+                       "rsrx_ppo_prep")
+        obs_n = obs_n_buf.view(mb, T, obs_size)
         if ptc is not None:
             ptc.attach_grads()
-            logits = ptc.forward(obs_n.reshape(mb * T, obs_size)).view(mb, T, 2 * act_size)
+            logits = ptc.forward(obs_n_buf).view(mb, T, 2 * act_size)
         else:
             logits = net.policy(obs_n)  # autograd fallback for policies wider than 32
         with torch.no_grad():
-            xval = torch.cat([obs_n.reshape(mb * T, obs_size), normalize(static["next_observation"][:, -1])], dim=0)
-            values = vtc.forward(xval)
+            values = vtc.forward(None)
             lg = logits.detach()
             with torch.cuda.device(dev):
                 _lib.check(_lib.lib().rsrx_ppo_head(
