@@ -702,8 +702,7 @@ extern "C" int rsrx_reduce_partials(const float* const* in, float* const* out, c
     nmax = std::max(nmax, n[k]);
   }
   const dim3 grid(std::min((nmax + 255) / 256, 64), nseg);
-  gemm::reduce_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(pdl::launch(gemm::reduce_partials_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a));
   return 0;
 }
 
@@ -714,10 +713,8 @@ extern "C" int rsrx_value_head_backward(const float* g, const float* w, const fl
     return fail("rsrx_value_head_backward: null argument");
   if (M <= 0 || n <= 0 || ld < n || activation < 0 || activation > 2 || (dzT && ldt < M)) return fail("rsrx_value_head_backward: bad sizes");
   if ((n & 3) || (ld & 3)) return fail("rsrx_value_head_backward: n and ld must be multiples of 4");
-  gemm::head_backward_kernel<<<dim3((M + 127) / 128, (n + 63) / 64), 256, 0, (cudaStream_t)stream>>>(g, w, z, h, M, n, ld, activation, dz,
-                                                                                                  colsum_partials, dw_partials, db_partials,
-                                                                                                  dzT, ldt);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(pdl::launch(gemm::head_backward_kernel, dim3((M + 127) / 128, (n + 63) / 64), dim3(256), 0, (cudaStream_t)stream, g, w, z, h, M, n,
+                      ld, activation, dz, colsum_partials, dw_partials, db_partials, dzT, ldt));
   return 0;
 }
 
@@ -737,8 +734,7 @@ extern "C" int rsrx_adam_step(float* const* params, const float* const* grads, f
     a.seg[k] = {params[k], grads[k], exp_avg[k], exp_avg_sq[k], sizes[k], pt, c};
   }
   const dim3 grid(gemm::ADAM_BLOCKS_X, ntensors);
-  gemm::adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(pdl::launch(gemm::adam_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a));
   return 0;
 }
 
@@ -778,8 +774,8 @@ extern "C" int rsrx_small_mlp_forward(const float* const* weights, const float* 
   const size_t smem = smallmlp::fwd_smem(nlayers);
   static bool set = false;
   if (!set) { CUDA_OK(cudaFuncSetAttribute(smallmlp::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smallmlp::fwd_smem(smallmlp::MAXL))); set = true; }
-  smallmlp::forward_kernel<<<small_grid(rows, 2), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, out, ldo);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(pdl::launch(smallmlp::forward_kernel, dim3(small_grid(rows, 2)), dim3(32 * smallmlp::WARPS), smem, (cudaStream_t)stream, net, x, ldx,
+                      rows, zs, out, ldo));
   return 0;
 }
 
@@ -794,9 +790,8 @@ extern "C" int rsrx_small_mlp_backward(const float* const* weights, const float*
   if (smem > 227 * 1024) return fail("rsrx_small_mlp_backward: too many layers for the shared-memory accumulators");
   static bool set = false;
   if (!set) { CUDA_OK(cudaFuncSetAttribute(smallmlp::backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-  smallmlp::backward_kernel<<<small_grid(rows, 2), 32 * smallmlp::WARPS, smem, (cudaStream_t)stream>>>(net, x, ldx, rows, zs, grad_out, ldg,
-                                                                                                 partials, total);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(pdl::launch(smallmlp::backward_kernel, dim3(small_grid(rows, 2)), dim3(32 * smallmlp::WARPS), smem, (cudaStream_t)stream, net, x,
+                      ldx, rows, zs, grad_out, ldg, partials, total));
   return 0;
 }
 

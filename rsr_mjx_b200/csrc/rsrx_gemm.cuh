@@ -31,6 +31,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include "rsrx_pdl.cuh"
+
 namespace rsrx {
 namespace gemm {
 
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int kbeg = blockIdx.z * p.k_split;
   const int kend = min(p.K, kbeg + p.k_split);
+  pdl::launch_dependents();
   stamp(p, 0);
 
   if (warp == 0) {  // TMEM: BN fp32 accumulator columns
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base_smem;
+  pdl::wait();  // everything above (TMEM allocation, barriers, descriptor prefetch) overlaps the predecessor's tail
   stamp(p, 1);
 
   // instruction descriptor: D fp32, A / B tf32, both K-major in shared memory (operands that are MN-contiguous in global
@@ -383,6 +387,8 @@ struct ReduceSeg { const float* in; float* out; int n, S; long long stride; };
 constexpr int MAXSEG = 24;
 struct ReduceArgs { ReduceSeg seg[MAXSEG]; int nseg; };
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
+  pdl::launch_dependents();
+  pdl::wait();
   const ReduceSeg& sg = a.seg[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
     float t = 0.f;
@@ -411,6 +417,8 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
                                                            float* __restrict__ db_part, float* __restrict__ dZT, int ldt) {
   __shared__ float red[2][16][64];
   __shared__ float tile[128][65];  // for the transposed copy dZT[col][row]
+  pdl::launch_dependents();
+  pdl::wait();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int r0 = blockIdx.x * 128, col = blockIdx.y * 64 + tx * 4;
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, dw[4] = {0.f, 0.f, 0.f, 0.f};
@@ -481,6 +489,8 @@ constexpr int ADAM_BLOCKS_X = 16;
 struct AdamArgs { AdamSeg seg[ADAM_MAXSEG]; int nseg; float lr, beta1, beta2, eps, grad_scale; unsigned int* counters; };
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   __shared__ float tile[32][33];
+  pdl::launch_dependents();
+  pdl::wait();
   const AdamSeg& sg = a.seg[blockIdx.y];
   const unsigned int k_now = *reinterpret_cast<volatile unsigned int*>(a.counters);
   const float t = (float)(k_now + 1u);
@@ -571,8 +581,7 @@ inline cudaError_t launch_one(Params p, dim3 grid, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     set = true;
   }
-  gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, THREADS, smem, stream>>>(p);
-  return cudaGetLastError();
+  return pdl::launch(gemm_tf32_kernel<BN, A_MN, B_MN>, grid, dim3(THREADS), smem, stream, p);
 }
 
 // mode 0: A and B contiguous along the contraction (both by TMA: forward, dgrad with a transposed weight copy, wgrad on

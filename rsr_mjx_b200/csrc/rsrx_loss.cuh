@@ -23,6 +23,8 @@
 
 #include <algorithm>
 
+#include "rsrx_pdl.cuh"
+
 namespace rsrx {
 namespace loss {
 
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(THREADS) kde_kernel(const float* __restrict__ 
   float* wmx = sg + max(M * D, (int)gridDim.x * M * 2);  // [WARPS][M]
   float* wsm = wmx + WARPS * M;          // [WARPS][M]
   __shared__ bool last;
+  pdl::launch_dependents();
+  pdl::wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = Nref + Nb;
   const float inv2h2 = 1.f / (2.f * bandwidth * bandwidth);
@@ -198,6 +202,8 @@ __global__ void __launch_bounds__(THREADS) grad_kernel(const float* __restrict__
   float* sg = sh;             // [M][D]
   float* lse = sg + M * D;    // [M]
   float* am = lse + M;        // [M]
+  pdl::launch_dependents();
+  pdl::wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < M * D; i += THREADS) sg[i] = grid[i];
   if (tid < M) { lse[tid] = ws.lse[tid]; am[tid] = ws.am[tid]; }
@@ -282,15 +288,16 @@ inline int launch(const float* grid, int M, int D, const float* ref, int Nref, c
     cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
-  kde_kernel<<<g1, THREADS, smem1, stream>>>(grid, M, D, ref, Nref, batch, Nb, refdens, bandwidth, divergence, loss_scale,
-                                            density_out, out, ws);
-  if (cudaGetLastError() != cudaSuccess) return 1;
+  if (pdl::launch(kde_kernel, dim3(g1), dim3(THREADS), smem1, stream, grid, M, D, ref, Nref, batch, Nb, refdens, bandwidth, divergence,
+                  loss_scale, density_out, out, ws) != cudaSuccess)
+    return 1;
   if (grad && refdens) {
     int g2 = (Nb + 2 * WARPS - 1) / (2 * WARPS);
     g2 = g2 < 1 ? 1 : (g2 > 2 * MAXCTA ? 2 * MAXCTA : g2);
     const size_t smem2 = sizeof(float) * ((size_t)M * D + 2 * M);
-    grad_kernel<<<g2, THREADS, smem2, stream>>>(grid, M, D, Nref, batch, Nb, bandwidth, divergence, loss_scale, grad, ws);
-    if (cudaGetLastError() != cudaSuccess) return 1;
+    if (pdl::launch(grad_kernel, dim3(g2), dim3(THREADS), smem2, stream, grid, M, D, Nref, batch, Nb, bandwidth, divergence, loss_scale,
+                    grad, ws) != cudaSuccess)
+      return 1;
   }
   return 0;
 }

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "rsrx_pdl.cuh"
+
 namespace rsrx {
 namespace smallmlp {
 
@@ -39,10 +41,12 @@ __global__ void __launch_bounds__(32 * WARPS) forward_kernel(const Net net, cons
   extern __shared__ float sm[];  // Wt[l][k][j] = W[l][j][k], padded to WD x WD; then bias[l][WD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* sb = sm + net.nl * WD * WD;
+  pdl::launch_dependents();
   // all weights of all layers in flight at once (4-byte cp.async straight into the transposed, zero-padded image): one
   // global round trip for the prologue instead of one per layer
   for (int i = tid; i < net.nl * WD * WD; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
+  pdl::wait();  // the zero fill above overlaps the predecessor's tail
   for (int l = 0; l < net.nl; ++l) {
     const int win = net.width[l], wout = net.width[l + 1];
     for (int i = tid; i < win * WD; i += blockDim.x) {  // shared-memory order: consecutive lanes write consecutive words
@@ -89,9 +93,11 @@ __global__ void __launch_bounds__(32 * WARPS) backward_kernel(const Net net, con
   const int nl = net.nl, per_warp = nl * WD * WD + nl * WD;
   float* sW = sm;
   float* acc = sm + nl * WD * WD + warp * per_warp;
+  pdl::launch_dependents();
   for (int i = tid; i < nl * WD * WD; i += blockDim.x) sW[i] = 0.f;
   for (int i = lane; i < per_warp; i += 32) acc[i] = 0.f;
   __syncthreads();
+  pdl::wait();  // the accumulator zero fill (0.2 MB of shared memory per CTA) overlaps the predecessor's tail
   for (int l = 0; l < nl; ++l) {  // every layer's weights in flight at once
     const int win = net.width[l], wout = net.width[l + 1];
     for (int i = tid; i < wout * win; i += blockDim.x)

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "rsrx_pdl.cuh"
+
 namespace rsrx {
 namespace ppo {
 
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(THREADS) head_kernel(
     float* __restrict__ grad_logits,       // [B][T][2A]  d task_loss / d logits
     float* __restrict__ grad_baseline) {   // [B][T]
   __shared__ float red[THREADS / 32];
+  pdl::launch_dependents();
+  pdl::wait();
   const int n = B * T, tid = threadIdx.x;
   float* adv = ws;
   float* vs = ws + n;
@@ -140,9 +144,8 @@ inline int launch(const float* logits, const float* baseline, const float* boots
                   const float* noise, int B, int T, int A, Hyper h, float* ws, float* out, float* grad_logits,
                   float* grad_baseline, cudaStream_t stream) {
   if (A > MAXA || A <= 0 || B <= 0 || T <= 0) return 1;
-  head_kernel<<<1, THREADS, 0, stream>>>(logits, baseline, bootstrap, raw_action, behaviour_lp, reward, discount,
-                                         truncation, noise, B, T, A, h, ws, out, grad_logits, grad_baseline);
-  return cudaGetLastError() != cudaSuccess;
+  return pdl::launch(head_kernel, dim3(1), dim3(THREADS), 0, stream, logits, baseline, bootstrap, raw_action, behaviour_lp, reward,
+                     discount, truncation, noise, B, T, A, h, ws, out, grad_logits, grad_baseline) != cudaSuccess;
 }
 
 }  // namespace ppo
@@ -232,6 +235,8 @@ struct Fields {
 };
 
 __global__ void __launch_bounds__(256) gather_kernel(Fields f, const long long* __restrict__ idx, int nrows) {
+  pdl::launch_dependents();
+  pdl::wait();
   const int r = blockIdx.x;
   if (r >= nrows) return;
   const long long s = idx[r];
@@ -243,8 +248,7 @@ __global__ void __launch_bounds__(256) gather_kernel(Fields f, const long long* 
 }
 
 inline int launch(const Fields& f, const long long* idx, int nrows, cudaStream_t stream) {
-  gather_kernel<<<nrows, 256, 0, stream>>>(f, idx, nrows);
-  return cudaGetLastError() != cudaSuccess;
+  return pdl::launch(gather_kernel, dim3(nrows), dim3(256), 0, stream, f, idx, nrows) != cudaSuccess;
 }
 
 }  // namespace gather
@@ -297,6 +301,8 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ obs
                                                    int O, float* __restrict__ obs_n, float* __restrict__ x_pad, int ldp,
                                                    float* __restrict__ xT, int ldt) {
   __shared__ float tile[32][33];
+  pdl::launch_dependents();
+  pdl::wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int rows = mb * T + mb, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int col = c0 + tx;
@@ -320,8 +326,8 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ obs
 inline int launch_prep(const float* obs, const float* next_obs, const float* mean, const float* stdv, int mb, int T, int O,
                        float* obs_n, float* x_pad, int ldp, float* xT, int ldt, cudaStream_t stream) {
   const int rows = mb * T + mb;
-  prep_kernel<<<dim3((rows + 31) / 32, (ldp + 31) / 32), 256, 0, stream>>>(obs, next_obs, mean, stdv, mb, T, O, obs_n, x_pad, ldp, xT, ldt);
-  return cudaGetLastError() != cudaSuccess;
+  return pdl::launch(prep_kernel, dim3((rows + 31) / 32, (ldp + 31) / 32), dim3(256), 0, stream, obs, next_obs, mean, stdv, mb, T, O, obs_n,
+                     x_pad, ldp, xT, ldt) != cudaSuccess;
 }
 
 }  // namespace ppo
