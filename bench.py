@@ -51,7 +51,9 @@ def kernel_source_hash():
     h = hashlib.sha256()
     d = os.path.join(ROOT, "rsr_mjx_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f in ("rsrx_device.cuh", "rsrx_physics.cuh", "rsrx_env.cuh", "rsrx_api.cu", "rsrx_redo.cu", "rsrx_redo.h"):
+        # (rsrx_api.cu holds every trainer entry point too and changes with them; the launch geometry it chooses is in the
+        # summary's .meta.json)
+        if f in ("rsrx_device.cuh", "rsrx_physics.cuh", "rsrx_env.cuh", "rsrx_redo.cu", "rsrx_redo.h"):
             with open(os.path.join(d, f), "rb") as fh:
                 h.update(fh.read())
     return h.hexdigest()[:16]
@@ -256,6 +258,9 @@ def time_env(env, state, actions_fn, W, K, flush, barrier, episode_profile=True)
     barrier()
     out["stationary_1200_step_mean_ms_l2_warm"] = e0.elapsed_time(e1) / EP
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    # cudaProfilerStart/Stop around the timed region: `ncu --profile-from-start off` lists exactly these launches
+    # (profiles/r2_launches_bench_sf8192.csv); a no-op without a profiler attached
+    torch.cuda.profiler.start()
     for t in range(K):
         if flush is not None:
             flush.fill_(t & 0xFF)
@@ -263,22 +268,52 @@ def time_env(env, state, actions_fn, W, K, flush, barrier, episode_profile=True)
         env.step(state, actions_fn(t + 3))
         evs[t][1].record()
     barrier()
+    torch.cuda.profiler.stop()
     out["step_ms"] = np.array([a.elapsed_time(b) for a, b in evs])
     return out
 
 
-def synthetic_rsr_files(obs_size, act_size, n=51, seed=2):
+def synthetic_rsr_files(obs_size, act_size, n=51, seed=2, rollout=None):
     """BASELINE config 4: six synthetic tables (real / past-sim / current-sim observations and actions, 51 rows each)
-    -> the five arrays `policy_params_training` takes.  Values are smooth random walks around the reset observation
-    scale; the loss kernel's cost does not depend on them."""
+    -> the five arrays `policy_params_training` takes.  `rollout` = (obs [n, obs_size], actions [n, act_size]) of one env
+    under random actions puts the tables where the policy's transitions live, so the KDE sees the online batch and the RSR
+    term is non-zero (tables far from the data give exactly 0: every online row underflows out of the density); without it,
+    smooth random walks around 0.  "real" / "past sim" / "current sim" differ by noise of 1e-3 / 5e-3 / 2e-3."""
     rng = np.random.default_rng(seed)
-    base = np.cumsum(rng.normal(0, 0.01, (n, obs_size)), axis=0).astype(np.float32)
+    if rollout is not None:
+        base, act = np.asarray(rollout[0], np.float32)[:n], np.asarray(rollout[1], np.float32)[:n]
+    else:
+        base = np.cumsum(rng.normal(0, 0.01, (n, obs_size)), axis=0).astype(np.float32)
+        act = rng.uniform(-1, 1, (n, act_size)).astype(np.float32)
     real = base + rng.normal(0, 1e-3, base.shape).astype(np.float32)
     past = base + rng.normal(0, 5e-3, base.shape).astype(np.float32)
     cur = base + rng.normal(0, 2e-3, base.shape).astype(np.float32)
-    act = rng.uniform(-1, 1, (n, act_size)).astype(np.float32)
     m = min(n - 1, 50)
     return real[:m], act[:m], real[1:m + 1], past[1:m + 1], cur[1:m + 1]
+
+
+# KDE bandwidth of the bench's RSR term.  With the reference default (h = 0.1, 10 grid points uniform in [-3, 3]^51,
+# rsr_pipeline.py:286-289) the squared distances data -> grid points differ by ~30 / (2 h^2) = 1500 nats, every softmax over
+# the grid is one-hot for the reference AND the online density and the term is exactly 0 (true of the reference too); h = 3
+# keeps it alive so the gradient path is exercised.  The kernels' cost does not depend on h.
+RSR_BENCH_BANDWIDTH = 3.0
+
+
+def random_action_rollout(kind, dev, n=51, seed=5):
+    """observations and actions of env 0 over n steps of U(-1,1) actions (input of synthetic_rsr_files)"""
+    import torch
+    from rsr_mjx_b200 import prng
+    from rsr_mjx_b200.envs import AirbotPlayBase
+    env = AirbotPlayBase(kind, num_envs=32, episode_length=1200, device=dev)
+    st = env.reset(prng.split(prng.PRNGKey(seed), 32))
+    g = torch.Generator(device=dev).manual_seed(seed)
+    obs, act = [], []
+    for _ in range(n):
+        a = torch.rand(32, env.action_size, device=dev, generator=g) * 2 - 1
+        obs.append(st.obs[0].cpu().numpy().copy())
+        act.append(a[0].cpu().numpy().copy())
+        st = env.step(st, a)
+    return np.stack(obs), np.stack(act)
 
 
 def ppo_sub_record(dev, rank, world, training_steps=5):
@@ -291,7 +326,9 @@ def ppo_sub_record(dev, rank, world, training_steps=5):
     N = 1024 // world
     env = AirbotPlayBase("cube", num_envs=N, episode_length=1200, device=dev, randomization_fn=DR.domain_randomize,
                          randomization_rng=prng.split(prng.PRNGKey(1), N))
-    past = RP.build_policy_rsr_data(*synthetic_rsr_files(env.observation_size, env.action_size), device=dev)
+    past = RP.build_policy_rsr_data(*synthetic_rsr_files(env.observation_size, env.action_size,
+                                                         rollout=random_action_rollout("cube", dev)),
+                                    bandwidth=RSR_BENCH_BANDWIDTH, device=dev)
     sps, split, rsr = [], [], []
     ppo.train(env, num_timesteps=10**9, episode_length=1200, past_data=past, num_envs=N, learning_rate=1e-4,
               entropy_cost=2e-2, discounting=0.96, unroll_length=10, batch_size=256 // world, num_minibatches=32,
@@ -306,7 +343,7 @@ def ppo_sub_record(dev, rank, world, training_steps=5):
             "rsr_term": True, "sim2real_loss_last": rsr[-1],
             "config": {"workload": "PPO on cube_env + domain randomisation with the RSR KDE+Wasserstein term (BASELINE configs 3+4)",
                        "global_envs": 1024, "unroll_length": 10, "minibatches": "32 x 256 sequences", "updates_per_batch": 8,
-                       "past_data": "synthetic six-table set, 50 transitions, grid 10 x 51, h = 0.1"}}
+                       "past_data": "synthetic six-table set from a 51-step random-action rollout of one env + noise, 50 transitions, grid 10 x 51, h = 3.0 (the default 0.1 makes the term identically 0)"}}
 
 
 def main():
@@ -373,7 +410,7 @@ def main():
     h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
     h_done = torch.empty(N, dtype=torch.float32).pin_memory()
     for t in range(3):
-        env.step_host(state, h_act[t], h_obs, h_rew, h_done)
+        env.step_host(state, h_act[t % K], h_obs, h_rew, h_done)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

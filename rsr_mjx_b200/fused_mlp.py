@@ -55,9 +55,11 @@ class TensorCoreMLP:
         self.Z = [z(M, l.out_features) for l in self.hidden]
         self.H = [z(M, l.out_features) for l in self.hidden]
         self.HT = [z(l.out_features, self.ldt) for l in self.hidden[:-1]]  # inputs of layers 1 .. (the last H only feeds the head)
-        wmax = max(l.out_features for l in self.hidden)
-        self.dZ = [z(M, wmax), z(M, wmax)]     # ping-pong, used with the layer's own leading dimension
-        self.dZT = [z(wmax, self.ldt), z(wmax, self.ldt)]
+        # one gradient buffer (+ transposed copy) per hidden layer rather than a ping-pong pair: the weight-gradient GEMM of
+        # layer l runs on a side stream while the main stream already computes dZ of layer l - 2
+        self.dZ = [z(M, l.out_features) for l in self.hidden]
+        self.dZT = [z(l.out_features, self.ldt) for l in self.hidden]
+        self._side = None
         # transposed weight copies [in][out] of layers 1 .. for the dgrad GEMM's TMA; kept current by FusedAdam (wT_of), or
         # refreshed at the start of forward() when another optimiser is used
         self.WT = {l.weight: z(l.in_features, l.out_features) for l in self.hidden[1:]}
@@ -112,31 +114,41 @@ class TensorCoreMLP:
 
     # ----------------------------------------------------------------- backward
     @torch.no_grad()
-    def backward(self, g: torch.Tensor) -> None:
-        """g = d loss / d values [rows]; fills the .grad buffers of every value-network parameter"""
-        L, M, s = _lib.lib(), self.rows, self._stream()
+    def backward(self, g: torch.Tensor, overlap: bool = True) -> None:
+        """g = d loss / d values [rows]; fills the .grad buffers of every value-network parameter.
+        overlap: the weight-gradient GEMMs (dW_l = dZ_l^T X_{l-1}) go to a side stream and run beside the data-gradient
+        chain (dZ_{l-1} = dZ_l W_l * act'), which is the critical path; both are forked from and joined back into the
+        current stream (inside a stream capture this becomes two parallel branches of the graph)."""
+        L, M = _lib.lib(), self.rows
+        main = torch.cuda.current_stream(self.dev)
+        if overlap and self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        side = self._side if overlap else main
+        s, s2 = C.c_void_p(main.cuda_stream), C.c_void_p(side.cuda_stream)
         g = g.contiguous()
         out, nh = self.layers[-1], len(self.hidden)
         n = self.hidden[-1].out_features
-        cur = 0
         _lib.check(L.rsrx_value_head_backward(g.data_ptr(), out.weight.data_ptr(), self.Z[-1].data_ptr(), self.H[-1].data_ptr(),
-                                              M, n, n, self.act, self.dZ[cur].data_ptr(), self.colsum[-1].data_ptr(),
+                                              M, n, n, self.act, self.dZ[-1].data_ptr(), self.colsum[-1].data_ptr(),
                                               self.dw_out_part.data_ptr(), self.db_out_part.data_ptr(),
-                                              self.dZT[cur].data_ptr(), self.ldt, s), "rsrx_value_head_backward")
+                                              self.dZT[-1].data_ptr(), self.ldt, s), "rsrx_value_head_backward")
         for i in range(nh - 1, -1, -1):
             l = self.hidden[i]
             n, kin = l.out_features, (self.k0p if i == 0 else l.in_features)
             xt = self.xT if i == 0 else self.HT[i - 1]
+            if overlap:
+                side.wait_stream(main)  # dZ_i / dZT_i are complete
             # dW_l partials = dZ_l^T X_{l-1}: both operands from their transposed copies (contraction-contiguous, TMA)
-            _lib.check(L.rsrx_linear_wgrad(self.dZT[cur].data_ptr(), self.ldt, xt.data_ptr(), self.ldt, 1, M, n, kin,
-                                           self.ROWS_PER_SPLIT, self.wpart[i].data_ptr(), kin, s), "rsrx_linear_wgrad")
+            _lib.check(L.rsrx_linear_wgrad(self.dZT[i].data_ptr(), self.ldt, xt.data_ptr(), self.ldt, 1, M, n, kin,
+                                           self.ROWS_PER_SPLIT, self.wpart[i].data_ptr(), kin, s2), "rsrx_linear_wgrad")
             if i > 0:
                 wt = self.WT[l.weight]
-                _lib.check(L.rsrx_linear_dgrad(self.dZ[cur].data_ptr(), n, l.weight.data_ptr(), kin, wt.data_ptr(), n,
-                                               self.Z[i - 1].data_ptr(), M, kin, n, self.act, self.dZ[1 - cur].data_ptr(), kin,
-                                               self.colsum[i - 1].data_ptr(), self.dZT[1 - cur].data_ptr(), self.ldt, s),
+                _lib.check(L.rsrx_linear_dgrad(self.dZ[i].data_ptr(), n, l.weight.data_ptr(), kin, wt.data_ptr(), n,
+                                               self.Z[i - 1].data_ptr(), M, kin, n, self.act, self.dZ[i - 1].data_ptr(), kin,
+                                               self.colsum[i - 1].data_ptr(), self.dZT[i - 1].data_ptr(), self.ldt, s),
                            "rsrx_linear_dgrad")
-                cur = 1 - cur
+        if overlap:
+            main.wait_stream(side)
         if self._reduce_args is None:
             ins, outs, ns, Ss, strides = [], [], [], [], []
             for i, l in enumerate(self.hidden):

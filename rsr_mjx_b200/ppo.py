@@ -579,6 +579,7 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         hyper = (float(reward_scaling), float(discounting), float(gae_lambda), float(clipping_epsilon), float(entropy_cost),
                  int(bool(normalize_advantage)))
         obs_n_buf = torch.empty(mb * T, obs_size, device=dev)
+        policy_stream = torch.cuda.Stream(device=dev)
         # the normaliser's tensors are updated in place, so the prep kernel can keep reading them; identity when off
         prep_mean = norm.mean if normalize_observations else torch.zeros(obs_size, device=dev)
         prep_std = norm.std if normalize_observations else torch.ones(obs_size, device=dev)
@@ -596,13 +597,32 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                                                 vtc.k0p, vtc.xT.data_ptr(), vtc.ldt, torch.cuda.current_stream(dev).cuda_stream),
                        "rsrx_ppo_prep")
         obs_n = obs_n_buf.view(mb, T, obs_size)
+        main = torch.cuda.current_stream(dev)
+        # The policy branch (its forward, the RSR term, its backward) and the value branch (five tensor-core layers each way)
+        # only meet at the loss head: the policy branch runs on its own stream, forked from and joined back into the current
+        # one (two parallel branches of the graph when captured), so the critical path of a minibatch step is
+        # prep -> value forward -> head -> value data-gradients -> reduce -> Adam.
+        pol = policy_stream if ptc is not None else main
         if ptc is not None:
             ptc.attach_grads()
-            logits = ptc.forward(obs_n_buf).view(mb, T, 2 * act_size)
+            pol.wait_stream(main)
+            with torch.cuda.stream(pol):
+                logits = ptc.forward(obs_n_buf).view(mb, T, 2 * act_size)
+                if past_data is not None and rsr_loss_scale != 0:
+                    # the RSR term acts on mode(logits) (RSR/losses.py:186-195): its gradient w.r.t. the logits joins the head's
+                    leaf = logits.detach().requires_grad_(True)
+                    sim2real_loss, distance = rsr.compute_rsr_loss(obs, NormalTanh.mode(leaf), static["next_observation"], past_data,
+                                                                   loss_scale=rsr_loss_scale)
+                    (g_extra,) = torch.autograd.grad(sim2real_loss, leaf)
+                else:
+                    g_extra = None
+                    sim2real_loss = distance = torch.zeros((), device=dev)
         else:
             logits = net.policy(obs_n)  # autograd fallback for policies wider than 32
         with torch.no_grad():
             values = vtc.forward(None)
+            if ptc is not None:
+                main.wait_stream(pol)  # the head needs the logits
             lg = logits.detach()
             with torch.cuda.device(dev):
                 _lib.check(_lib.lib().rsrx_ppo_head(
@@ -610,21 +630,15 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                     static["log_prob"].data_ptr(), static["reward"].data_ptr(), static["discount"].data_ptr(),
                     static["truncation"].data_ptr(), nz.data_ptr(), mb, T, act_size, *hyper, head_ws.data_ptr(),
                     head_out.data_ptr(), g_logits_buf.data_ptr(), g_values_buf.data_ptr(),
-                    torch.cuda.current_stream(dev).cuda_stream), "rsrx_ppo_head")
+                    main.cuda_stream), "rsrx_ppo_head")
+            if ptc is not None:
+                pol.wait_stream(main)  # the head's logit gradients
+                with torch.cuda.stream(pol):
+                    ptc.backward(g_logits_buf if g_extra is None else g_logits_buf + g_extra)
             vtc.backward(g_values_buf)
-        if ptc is not None:
-            # the RSR term acts on mode(logits) (RSR/losses.py:186-195): its gradient w.r.t. the logits joins the head's
-            g_total = g_logits_buf
-            if past_data is not None and rsr_loss_scale != 0:
-                leaf = logits.detach().requires_grad_(True)
-                sim2real_loss, distance = rsr.compute_rsr_loss(obs, NormalTanh.mode(leaf), static["next_observation"], past_data,
-                                                               loss_scale=rsr_loss_scale)
-                (g_extra,) = torch.autograd.grad(sim2real_loss, leaf)
-                g_total = g_logits_buf + g_extra
-            else:
-                sim2real_loss = distance = torch.zeros((), device=dev)
-            ptc.backward(g_total)
-        else:
+            if ptc is not None:
+                main.wait_stream(pol)
+        if ptc is None:
             sim2real_loss, distance = rsr.compute_rsr_loss(obs, NormalTanh.mode(logits), static["next_observation"], past_data,
                                                            loss_scale=rsr_loss_scale)
             if sim2real_loss.requires_grad:

@@ -24,4 +24,6 @@ for N in [int(x) for x in (sys.argv[2:] or ["8192"])]:
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     ms = np.array(ms[10:])
-    print(f" N={N}: {ms.mean():.3f} ms/step (min {ms.min():.3f}) -> {N / ms.mean() * 1e3:.3e} env-steps/s")
+    import hashlib
+    digest = hashlib.sha256(st._buf["data"].cpu().numpy().tobytes() + st.obs.cpu().numpy().tobytes()).hexdigest()[:12]
+    print(f" N={N}: {ms.mean():.3f} ms/step (min {ms.min():.3f}) -> {N / ms.mean() * 1e3:.3e} env-steps/s   state sha {digest}")
