@@ -8,7 +8,10 @@
 // launches of the eager/graph path (1.3 ms per minibatch step -> see profiles/).
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math.h>
+
+#include <cstdlib>
 
 #include "rsrx_pdl.cuh"
 
@@ -139,11 +142,181 @@ __global__ void __launch_bounds__(THREADS) head_kernel(
   if (tid == 0) { out[0] = pol + vl + en; out[1] = pol; out[2] = vl; out[3] = en; }
 }
 
+// ---- the same head on a thread-block cluster of 8 CTAs -----------------------------------------------------------------
+// The single-CTA kernel above is a 35 us serial section in the middle of every minibatch step (147 SMs idle).  Here CTA r
+// of the cluster owns sequences [r B/8, (r+1) B/8): it stages their reward / value / discount / mask in shared memory
+// with coalesced loads, runs the GAE recurrences from there, and handles their transitions; the five sums over all
+// transitions (advantage mean and variance, the three losses) are CTA partials exchanged through distributed shared
+// memory and added in rank order by every CTA (identical bits everywhere, deterministic).
+namespace cg = cooperative_groups;
+constexpr int CL = 8;     // CTAs per cluster (the portable maximum)
+constexpr int CT = 512;   // threads per CTA
+
+__device__ __forceinline__ float cta_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < CT / 32; w++) s += red[w];
+  return s;
+}
+// part: [8] slots of this CTA's shared memory, one per reduction (never reused within a launch)
+__device__ __forceinline__ float cluster_sum(cg::cluster_group& cl, float v, float* red, float* part, int slot) {
+  const float s = cta_sum(v, red);
+  if (threadIdx.x == 0) part[slot] = s;
+  cl.sync();
+  float t = 0.f;
+#pragma unroll
+  for (int r = 0; r < CL; r++) t += cl.map_shared_rank(part, r)[slot];
+  return t;
+}
+
+__global__ void __launch_bounds__(CT) head_cluster_kernel(
+    const float* __restrict__ logits, const float* __restrict__ baseline, const float* __restrict__ bootstrap,
+    const float* __restrict__ raw_action, const float* __restrict__ behaviour_lp, const float* __restrict__ reward,
+    const float* __restrict__ discount, const float* __restrict__ truncation, const float* __restrict__ noise, int B, int T,
+    int A, Hyper h, int cap, float* __restrict__ out, float* __restrict__ grad_logits, float* __restrict__ grad_baseline) {
+  extern __shared__ float dyn[];  // [4][cap]: reward -> advantage, baseline, discount factor -> vs, mask
+  __shared__ float red[CT / 32];
+  __shared__ float part[8];
+  cg::cluster_group cl = cg::this_cluster();
+  pdl::launch_dependents();
+  pdl::wait();
+  const int tid = threadIdx.x, rank = (int)cl.block_rank();
+  const int bper = (B + CL - 1) / CL, b0 = min(B, rank * bper), b1 = min(B, b0 + bper);
+  const int i0 = b0 * T, nloc = (b1 - b0) * T, n = B * T;
+  float* s_r = dyn;
+  float* s_v = dyn + cap;
+  float* s_c = dyn + 2 * cap;
+  float* s_m = dyn + 3 * cap;
+  for (int j = tid; j < nloc; j += CT) {
+    const int i = i0 + j;
+    const float trunc = truncation[i];
+    const float term = (1.f - discount[i]) * (1.f - trunc);
+    s_r[j] = reward[i] * h.reward_scaling;
+    s_v[j] = baseline[i];
+    s_c[j] = h.discounting * (1.f - term);
+    s_m[j] = 1.f - trunc;
+  }
+  __syncthreads();
+  // ---- GAE: thread per sequence, from shared memory (same arithmetic, in the same order, as head_kernel)
+  float s1 = 0.f;
+  for (int b = b0 + tid; b < b1; b += CT) {
+    float acc = 0.f, vs_next = bootstrap[b], v_next = vs_next;
+    for (int t = T - 1; t >= 0; --t) {
+      const int j = (b - b0) * T + t;
+      const float r = s_r[j], v = s_v[j], c = s_c[j], mask = s_m[j];
+      const float delta = (r + c * v_next - v) * mask;
+      acc = delta + c * mask * h.gae_lambda * acc;
+      const float vs_t = acc + v;
+      const float a = (r + c * vs_next - v) * mask;
+      s_r[j] = a;     // advantage
+      s_c[j] = vs_t;  // value target
+      s1 += a;
+      vs_next = vs_t;
+      v_next = v;
+    }
+  }
+  float mean = 0.f, inv_std = 1.f;
+  if (h.normalize_advantage) {
+    mean = cluster_sum(cl, s1, red, part, 0) / (float)n;
+    float s2 = 0.f;
+    for (int j = tid; j < nloc; j += CT) { const float d = s_r[j] - mean; s2 += d * d; }
+    inv_std = 1.f / (sqrtf(cluster_sum(cl, s2, red, part, 1) / (float)n) + 1e-8f);
+  } else {
+    __syncthreads();
+  }
+  // ---- per-transition losses and gradients
+  const float inv_n = 1.f / (float)n;
+  float l_pol = 0.f, l_v = 0.f, l_ent = 0.f;
+  for (int j = tid; j < nloc; j += CT) {
+    const int i = i0 + j;
+    const float* lg = logits + (size_t)i * 2 * A;
+    const float* ra = raw_action + (size_t)i * A;
+    const float* nz = noise + (size_t)i * A;
+    float lp = 0.f, ent = 0.f;
+    float scale[MAXA], z[MAXA], sg[MAXA], dldj[MAXA];
+#pragma unroll 1
+    for (int k = 0; k < A; k++) {
+      const float loc = lg[k], s = lg[A + k];
+      const float sc = softplus(s) + MIN_STD;
+      const float zz = (ra[k] - loc) / sc;
+      lp += -0.5f * zz * zz - 0.5f * LOG_2PI - logf(sc) - log_det_jac(ra[k]);
+      const float x = loc + sc * nz[k];
+      ent += 0.5f + 0.5f * LOG_2PI + logf(sc) + log_det_jac(x);
+      scale[k] = sc; z[k] = zz; sg[k] = sigmoid(s); dldj[k] = -2.f * tanhf(x);
+    }
+    const float a = (s_r[j] - mean) * inv_std;
+    const float rho = expf(lp - behaviour_lp[i]);
+    const float lo = 1.f - h.clip_eps, hi = 1.f + h.clip_eps;
+    const bool in_range = rho >= lo && rho <= hi;
+    const float l1 = rho * a, l2 = fminf(fmaxf(rho, lo), hi) * a;
+    l_pol += fminf(l1, l2);
+    const float dmin_drho = (in_range || l1 < l2) ? a : 0.f;
+    const float g_lp = -inv_n * dmin_drho * rho;
+    const float g_ent = -h.entropy_cost * inv_n;
+    const float verr = s_c[j] - s_v[j];
+    l_v += verr * verr;
+    l_ent += ent;
+    grad_baseline[i] = -0.5f * verr * inv_n;
+    float* gl = grad_logits + (size_t)i * 2 * A;
+#pragma unroll 1
+    for (int k = 0; k < A; k++) {
+      const float d_loc = g_lp * (z[k] / scale[k]) + g_ent * dldj[k];
+      const float d_scale = g_lp * ((z[k] * z[k] - 1.f) / scale[k]) + g_ent * (1.f / scale[k] + dldj[k] * nz[k]);
+      gl[k] = d_loc;
+      gl[A + k] = d_scale * sg[k];
+    }
+  }
+  // the three loss sums: one exchange (slots 2..4), one cluster barrier
+  const float p0 = cta_sum(l_pol, red), p1 = cta_sum(l_v, red), p2 = cta_sum(l_ent, red);
+  if (tid == 0) { part[2] = p0; part[3] = p1; part[4] = p2; }
+  cl.sync();
+  if (rank == 0 && tid == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int r = 0; r < CL; r++) {
+      const float* q = cl.map_shared_rank(part, r);
+      t0 += q[2]; t1 += q[3]; t2 += q[4];
+    }
+    const float pol = -t0 * inv_n, vl = t1 * inv_n * 0.25f, en = -h.entropy_cost * t2 * inv_n;
+    out[0] = pol + vl + en; out[1] = pol; out[2] = vl; out[3] = en;
+  }
+  cl.sync();  // nobody leaves while its shared memory may still be read
+}
+
 inline int launch(const float* logits, const float* baseline, const float* bootstrap, const float* raw_action,
                   const float* behaviour_lp, const float* reward, const float* discount, const float* truncation,
                   const float* noise, int B, int T, int A, Hyper h, float* ws, float* out, float* grad_logits,
                   float* grad_baseline, cudaStream_t stream) {
   if (A > MAXA || A <= 0 || B <= 0 || T <= 0) return 1;
+  // cluster version whenever a CTA's slice fits its shared memory (RSRX_PPO_HEAD_CLUSTER=0: the single-CTA kernel)
+  static const bool want_cluster = [] { const char* e = getenv("RSRX_PPO_HEAD_CLUSTER"); return !(e && e[0] == '0'); }();
+  const int cap = ((B + CL - 1) / CL) * T;
+  const size_t smem = sizeof(float) * 4 * (size_t)cap;
+  if (want_cluster && smem <= 160 * 1024) {
+    static bool set = false;
+    if (!set) {
+      if (cudaFuncSetAttribute(head_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return 1;
+      set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL);
+    cfg.blockDim = dim3(CT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl::enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, head_cluster_kernel, logits, baseline, bootstrap, raw_action, behaviour_lp, reward, discount,
+                              truncation, noise, B, T, A, h, cap, out, grad_logits, grad_baseline) != cudaSuccess;
+  }
   return pdl::launch(head_kernel, dim3(1), dim3(THREADS), 0, stream, logits, baseline, bootstrap, raw_action, behaviour_lp, reward,
                      discount, truncation, noise, B, T, A, h, ws, out, grad_logits, grad_baseline) != cudaSuccess;
 }
