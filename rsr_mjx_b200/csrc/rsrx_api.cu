@@ -701,7 +701,7 @@ extern "C" int rsrx_reduce_partials(const float* const* in, float* const* out, c
     a.seg[k] = {in[k], out[k], n[k], S[k], (long long)stride[k]};
     nmax = std::max(nmax, n[k]);
   }
-  const dim3 grid(std::min((nmax + 255) / 256, 64), nseg);
+  const dim3 grid(std::min((nmax + 255) / 256, 256), nseg);  // one output per thread on the 256 x 256 weight gradients
   CUDA_OK(pdl::launch(gemm::reduce_partials_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a));
   return 0;
 }

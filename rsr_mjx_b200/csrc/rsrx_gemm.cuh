@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
 // block's critical path.  counters = {step count, done} (two 32-bit words of the caller's uint64 ticket).
 struct AdamSeg { float* p; const float* g; float* m; float* v; int n; float* pT; int cols; };  // pT: optional [cols][n / cols] copy
 constexpr int ADAM_MAXSEG = 32;
-constexpr int ADAM_BLOCKS_X = 16;
+constexpr int ADAM_BLOCKS_X = 64;  // one 32 x 32 tile per block on the 256 x 256 weights: no serial tile loop
 struct AdamArgs { AdamSeg seg[ADAM_MAXSEG]; int nseg; float lr, beta1, beta2, eps, grad_scale; unsigned int* counters; };
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   __shared__ float tile[32][33];

@@ -100,12 +100,13 @@ def test_policy_params_training_end_to_end():
     assert a.shape == (64, 5)
 
 
-@pytest.mark.parametrize("normalize_advantage", [True, False])
-def test_fused_head_matches_torch_reference(normalize_advantage):
+@pytest.mark.parametrize("normalize_advantage,B", [(True, 64), (False, 64), (True, 13), (True, 3)])
+def test_fused_head_matches_torch_reference(normalize_advantage, B):
     """csrc/rsrx_ppo.cuh (GAE + tanh-normal log-prob + clipped surrogate + value + entropy, fwd and bwd in one launch)
-    against the plain torch fp32 restatement of RSR/losses.py (`compute_ppo_loss`): losses 1e-5 rel, grads 1e-4 rel"""
+    against the plain torch fp32 restatement of RSR/losses.py (`compute_ppo_loss`): losses 1e-5 rel, grads 1e-4 rel.
+    The head runs on an 8-CTA cluster, sequences split across the CTAs: B = 13 leaves the last CTA empty, B = 3 five."""
     torch.manual_seed(1)
-    B, T = 64, 10
+    T = 10
     net = ppo.PPONetworks(23, 5).cuda()
     g = torch.Generator("cuda").manual_seed(4)
     r = lambda *s: torch.randn(*s, device="cuda", generator=g)
@@ -237,6 +238,33 @@ def test_gather_rows_matches_torch_indexing():
         assert torch.equal(d, s[idx])
     with pytest.raises(RuntimeError):
         _lib.check(_lib.lib().rsrx_gather_rows(None, None, None, 1, idx.data_ptr(), 1, None), "rsrx_gather_rows")
+
+
+def test_minibatch_prep_matches_torch():
+    """rsrx_ppo_prep: normalised policy input, padded value input (observations then bootstrap observations) and its
+    transpose in one launch == the torch ops it replaces, bit for bit ((x - mean) * (1 / std) vs (x - mean) / std: 1 ulp)"""
+    g = torch.Generator("cuda").manual_seed(3)
+    mb, T, O, ldp = 37, 10, 23, 32
+    obs = torch.randn(mb, T, O, device="cuda", generator=g)
+    nxt = torch.randn(mb, T, O, device="cuda", generator=g)
+    mean = torch.randn(O, device="cuda", generator=g) * 0.2
+    std = torch.rand(O, device="cuda", generator=g) + 0.5
+    rows = mb * T + mb
+    ldt = (rows + 3) // 4 * 4
+    obs_n = torch.full((mb * T, O), 7.0, device="cuda")
+    x_pad = torch.full((rows, ldp), 7.0, device="cuda")
+    xT = torch.zeros(ldp, ldt, device="cuda")
+    _lib.check(_lib.lib().rsrx_ppo_prep(obs.data_ptr(), nxt.data_ptr(), mean.data_ptr(), std.data_ptr(), mb, T, O, obs_n.data_ptr(),
+                                        x_pad.data_ptr(), ldp, xT.data_ptr(), ldt, torch.cuda.current_stream().cuda_stream), "prep")
+    torch.cuda.synchronize()
+    ref = torch.cat([((obs - mean) / std).reshape(mb * T, O), (nxt[:, -1] - mean) / std], 0)
+    torch.testing.assert_close(obs_n, ref[:mb * T], rtol=2e-7, atol=1e-7)
+    torch.testing.assert_close(x_pad[:, :O], ref, rtol=2e-7, atol=1e-7)
+    assert (x_pad[:, O:] == 0).all()
+    assert torch.equal(xT[:, :rows], x_pad.t())
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.lib().rsrx_ppo_prep(obs.data_ptr(), nxt.data_ptr(), mean.data_ptr(), std.data_ptr(), mb, T, O, obs_n.data_ptr(),
+                                            x_pad.data_ptr(), 16, xT.data_ptr(), ldt, None), "prep")
 
 
 def test_tanh_normal_act_matches_torch():
