@@ -12,17 +12,20 @@
 //             split-K over blockIdx.z, partial tiles to a workspace (summed in order by reduce_partials_kernel:
 //             deterministic, no atomics)
 //
-// Structure (deliberately plain: these GEMMs are 0.4 GFLOP, 44-88 CTAs, latency-bound):
-//   CTA = 128 threads, tile 128 x BN, accumulators in TMEM (BN columns).  The whole contraction slice (<= 256) of both
-//   operands is staged at once (192 KB of shared memory), so all global loads of a CTA are in flight together.
-//   All threads stage the operand tiles (cp.async, or loads + transposing stores) in the canonical no-swizzle UMMA layout
-//   (8 x 16-byte core matrices, K-major: ((8,n),2):((16B,SBO),LBO); operands whose global layout is contiguous along
-//   M/N instead of K are transposed in flight),
-//   fence.proxy.async, one elected thread issues up to 32 x tcgen05.mma.kind::tf32 (K = 8 each) and tcgen05.commit's them
-//   to an mbarrier.  Epilogue: tcgen05.ld 32x32b (thread = accumulator row) -> padded shared memory -> fused bias /
-//   activation / activation-derivative / column sums with row-contiguous 16-byte global accesses.
-//   No TMA: the operands are small, L2-resident activations whose rows are not all 16-byte multiples apart; plain
-//   coalesced 16-byte loads keep the kernel free of tensor-map plumbing.
+// Structure (deliberately plain: these GEMMs are 0.4 GFLOP, 44-88 CTAs, one wave, latency-bound):
+//   CTA = 512 threads, tile 128 x BN (BN = 64), accumulators in TMEM (BN fp32 columns).  The whole contraction slice
+//   (<= 256) of both operands is staged at once (192 KB of shared memory), so everything a CTA reads is in flight together.
+//   Operands that are contiguous along the contraction are loaded by TMA (cp.async.bulk.tensor.2d, one 32-float slab of
+//   all rows per copy, 128-byte swizzle, completion on an mbarrier by expect_tx); the trainers make EVERY operand
+//   contraction-contiguous by having the producing epilogue (and the Adam step, for the weights) also write the
+//   transposed copy, so the forward, dgrad and wgrad GEMMs are all the <.., false, false> instantiation.  An operand
+//   that is only available contiguous along M/N is staged by the threads with an in-flight transposition into the
+//   canonical no-swizzle UMMA layout (8 x 16-byte core matrices, K-major) — MN-major tf32 shared-memory descriptors
+//   produced zeros on this part, so they are not used.
+//   fence.proxy.async, one elected thread issues up to 32 x tcgen05.mma.cta_group::1.kind::tf32 (K = 8 each) and
+//   tcgen05.commit's them to an mbarrier (bounded wait, __trap on time-out).  Epilogue: tcgen05.ld 32x32b.x16 (thread =
+//   accumulator row) -> padded shared memory -> fused bias / activation / activation-derivative / column sums with
+//   row-contiguous 16-byte global accesses, and optionally the transposed copy of the result through the same tile.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
