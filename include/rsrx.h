@@ -250,11 +250,14 @@ int rsrx_value_head_backward(const float* g, const float* w, const float* z, con
  * an MLP with every width <= 32 and <= 8 layers, hidden activation 1 silu / 2 relu, linear output, one warp per row.
  * weights[l] is [widths[l+1]][widths[l]] row-major (torch nn.Linear), biases[l] [widths[l+1]]; weights / biases / widths
  * are HOST arrays (device pointers / ints).
- *   forward : out[rows][ldo] = MLP(x[rows][ldx]); zs [nlayers-1][rows][32] receives the hidden pre-activations
+ *   forward : out[rows][ldo] = MLP(x[rows][ldx]); zs [nlayers-1][rows][32] receives the hidden pre-activations;
+ *             norm_mean / norm_std (both or neither, [widths[0]]): the input is normalised on the way in,
+ *             (x - mean) / std — the actor step's running-statistics normaliser (RSR/train.py:313) without a launch
  *   backward: from grad_out [rows][ldg] and zs, one partial gradient vector per CTA in parameter order (W_0, b_0, W_1,
  *             b_1, ...): partials [rsrx_small_mlp_backward_ctas(rows)][total]; finish with rsrx_reduce_partials */
 int rsrx_small_mlp_forward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
-                           int activation, const float* x, int ldx, int rows, float* zs, float* out, int ldo, void* stream);
+                           int activation, const float* x, int ldx, int rows, float* zs, float* out, int ldo,
+                           const float* norm_mean, const float* norm_std, void* stream);
 int rsrx_small_mlp_backward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
                             int activation, const float* x, int ldx, int rows, const float* zs, const float* grad_out, int ldg,
                             float* partials, void* stream);

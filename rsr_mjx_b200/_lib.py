@@ -94,7 +94,7 @@ def lib():
     L.rsrx_reduce_partials.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.rsrx_value_head_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
     L.rsrx_ppo_prep.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, i32, vp]
-    L.rsrx_small_mlp_forward.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp]
+    L.rsrx_small_mlp_forward.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp]
     L.rsrx_small_mlp_backward.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp]
     L.rsrx_small_mlp_backward_ctas.argtypes = [i32]
     L.rsrx_small_mlp_backward_ctas.restype = i32

@@ -767,15 +767,16 @@ extern "C" int rsrx_small_mlp_backward_ctas(int rows) { return small_grid(rows, 
 
 extern "C" int rsrx_small_mlp_forward(const float* const* weights, const float* const* biases, const int32_t* widths, int nlayers,
                                       int activation, const float* x, int ldx, int rows, float* zs, float* out, int ldo,
-                                      void* stream) {
+                                      const float* norm_mean, const float* norm_std, void* stream) {
   smallmlp::Net net;
   if (small_net(weights, biases, widths, nlayers, activation, net, nullptr)) return 1;
   if (!x || !out || (nlayers > 1 && !zs) || rows <= 0) return fail("rsrx_small_mlp_forward: bad arguments");
+  if ((norm_mean == nullptr) != (norm_std == nullptr)) return fail("rsrx_small_mlp_forward: norm_mean and norm_std go together");
   const size_t smem = smallmlp::fwd_smem(nlayers);
   static bool set = false;
   if (!set) { CUDA_OK(cudaFuncSetAttribute(smallmlp::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smallmlp::fwd_smem(smallmlp::MAXL))); set = true; }
   CUDA_OK(pdl::launch(smallmlp::forward_kernel, dim3(small_grid(rows, 2)), dim3(32 * smallmlp::WARPS), smem, (cudaStream_t)stream, net, x, ldx,
-                      rows, zs, out, ldo));
+                      rows, zs, out, ldo, norm_mean, norm_std));
   return 0;
 }
 

@@ -36,8 +36,11 @@ __device__ __forceinline__ float act_d(int act, float z) {
 }
 
 // zs: [nl - 1][rows][WD] pre-activations of the hidden layers; out: [rows][ldo]
+// nmean / nstd (optional, [width[0]]): the input is normalised on the way in, (x - mean) / std — the actor step of the
+// trainers (running-statistics normaliser, RSR/train.py:313 through acting.actor_step) without a separate launch
 __global__ void __launch_bounds__(32 * WARPS) forward_kernel(const Net net, const float* __restrict__ x, int ldx, int rows,
-                                                            float* __restrict__ zs, float* __restrict__ out, int ldo) {
+                                                            float* __restrict__ zs, float* __restrict__ out, int ldo,
+                                                            const float* __restrict__ nmean, const float* __restrict__ nstd) {
   extern __shared__ float sm[];  // Wt[l][k][j] = W[l][j][k], padded to WD x WD; then bias[l][WD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* sb = sm + net.nl * WD * WD;
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(32 * WARPS) forward_kernel(const Net net, cons
   __syncthreads();
   for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     float h = lane < net.width[0] ? x[(size_t)row * ldx + lane] : 0.f;
+    if (nmean && lane < net.width[0]) h = (h - nmean[lane]) / nstd[lane];
     for (int l = 0; l < net.nl; ++l) {
       const int win = net.width[l];
       const float* wt = sm + l * WD * WD;

@@ -18,7 +18,7 @@ NVIDIA GPUs by default), accumulation fp32.  No autograd inside: `backward(g)` i
 from __future__ import annotations
 
 import ctypes as C
-from typing import List
+from typing import List, Optional
 
 import torch
 
@@ -281,14 +281,20 @@ class WarpMLP:
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if tuple(x.shape) != (self.rows, self.widths[0]) or not x.is_contiguous():
-            raise ValueError(f"expected a contiguous input [{self.rows}, {self.widths[0]}]")
-        self._x = x
+    def forward(self, x: torch.Tensor, mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [rows, in_features], rows `x.stride(0)` floats apart (a padded observation buffer is fine).  mean / std: the
+        input is normalised inside the launch, (x - mean) / std (forward-only use: the actor step)."""
+        if tuple(x.shape) != (self.rows, self.widths[0]) or x.stride(1) != 1:
+            raise ValueError(f"expected an input [{self.rows}, {self.widths[0]}] with contiguous rows")
+        if (mean is None) != (std is None):
+            raise ValueError("mean and std go together")
+        self._x = x if mean is None else None  # backward() needs the layer-0 input as the kernel saw it
         with torch.cuda.device(self.dev):
             _lib.check(_lib.lib().rsrx_small_mlp_forward(self._W, self._b, self._w, len(self.layers), self.act, x.data_ptr(),
-                                                         self.widths[0], self.rows, self.zs.data_ptr(), self.out.data_ptr(),
-                                                         self.widths[-1], self._stream()), "rsrx_small_mlp_forward")
+                                                         x.stride(0), self.rows, self.zs.data_ptr(), self.out.data_ptr(),
+                                                         self.widths[-1], None if mean is None else mean.data_ptr(),
+                                                         None if std is None else std.data_ptr(), self._stream()),
+                       "rsrx_small_mlp_forward")
         return self.out
 
     @torch.no_grad()
@@ -296,10 +302,12 @@ class WarpMLP:
         g = g.reshape(self.rows, self.widths[-1])
         if not g.is_contiguous():
             g = g.contiguous()
+        if self._x is None:
+            raise RuntimeError("WarpMLP.backward after a forward with in-kernel normalisation: pass the normalised input instead")
         L = _lib.lib()
         with torch.cuda.device(self.dev):
             _lib.check(L.rsrx_small_mlp_backward(self._W, self._b, self._w, len(self.layers), self.act, self._x.data_ptr(),
-                                                 self.widths[0], self.rows, self.zs.data_ptr(), g.data_ptr(), self.widths[-1],
+                                                 self._x.stride(0), self.rows, self.zs.data_ptr(), g.data_ptr(), self.widths[-1],
                                                  self.partials.data_ptr(), self._stream()), "rsrx_small_mlp_backward")
             a = self._reduce
             _lib.check(L.rsrx_reduce_partials(a[0], a[1], a[2], a[3], a[4], a[5], self._stream()), "rsrx_reduce_partials")

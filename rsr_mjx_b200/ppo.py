@@ -509,20 +509,50 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
     if tensor_core_value and fused_head and dev.type == "cuda" and _fm.warp_supported(net.policy, dev):
         actor_mlp = _fm.WarpMLP(net.policy, num_envs, dev)
 
+    copy_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
     @torch.no_grad()
     def collect_body():
+        # Critical path of an actor step: policy forward (observation normalised inside the launch) -> action head ->
+        # env.step.  The copies of the step's results into the rollout buffers run on a second stream (a parallel branch
+        # of the graph when captured) while the next action is being computed; env.step waits for them, since it
+        # overwrites what they read.
+        main = torch.cuda.current_stream(dev) if copy_stream is not None else None
+
+        def store_results(u, t):  # of the env.step that was just queued, + the observation the next actor step sees
+            buf["next_observation"][u, t].copy_(state.obs)
+            buf["reward"][u, t].copy_(state.reward)
+            buf["discount"][u, t].copy_(1 - state.done)
+            buf["truncation"][u, t].copy_(state.info["truncation"])
+
+        prev = None
         for u in range(n_unrolls):
             for t in range(T):
                 obs = state.obs
-                buf["observation"][u, t].copy_(obs)
-                logits = actor_mlp.forward(normalize(obs).contiguous()) if actor_mlp is not None else net.policy(normalize(obs))
+                if copy_stream is not None:
+                    copy_stream.wait_stream(main)
+                    with torch.cuda.stream(copy_stream):
+                        if prev is not None:
+                            store_results(*prev)
+                        buf["observation"][u, t].copy_(obs)
+                else:
+                    buf["observation"][u, t].copy_(obs)
+                if actor_mlp is not None:
+                    logits = (actor_mlp.forward(obs, norm.mean, norm.std) if normalize_observations
+                              else actor_mlp.forward(obs))
+                else:
+                    logits = net.policy(normalize(obs))
                 # raw action, its log-prob (straight into the rollout buffers) and the tanh action: one launch
                 NormalTanh.act(logits, act_noise[u, t], buf["raw_action"][u, t], action_buf, buf["log_prob"][u, t])
+                if copy_stream is not None:
+                    main.wait_stream(copy_stream)
                 env.step(state, action_buf)
-                buf["next_observation"][u, t].copy_(state.obs)
-                buf["reward"][u, t].copy_(state.reward)
-                buf["discount"][u, t].copy_(1 - state.done)
-                buf["truncation"][u, t].copy_(state.info["truncation"])
+                if copy_stream is not None:
+                    prev = (u, t)
+                else:
+                    store_results(u, t)
+        if copy_stream is not None:
+            store_results(*prev)
         # [n_unrolls, T, N, ...] -> [B = n_unrolls * N, T, ...]
         for k, v in buf.items():
             batch_static[k].view(n_unrolls, num_envs, T, *v.shape[3:]).copy_(v.permute(0, 2, 1, *range(3, v.dim())))

@@ -401,6 +401,26 @@ def test_warp_policy_net_matches_torch_autograd():
             assert rel(got[n], p.grad) <= 1e-4, (sizes, n, rel(got[n], p.grad))
 
 
+def test_warp_policy_forward_with_in_kernel_normalisation():
+    """the actor step's form: rows of a padded observation buffer, (x - mean) / std applied inside the launch ==
+    forward of the separately normalised, contiguous input, bit for bit; backward after it is refused"""
+    from rsr_mjx_b200 import fused_mlp
+    torch.manual_seed(4)
+    mlp = ppo.MLP([23, 32, 32, 32, 32, 10]).cuda()
+    rows = 1024
+    padded = torch.randn(rows, 24, device="cuda")
+    x = padded[:, :23]
+    mean, std = torch.randn(23, device="cuda") * 0.3, torch.rand(23, device="cuda") + 0.5
+    wm = fused_mlp.WarpMLP(mlp, rows, "cuda")
+    a = wm.forward(x, mean, std).clone()
+    with pytest.raises(RuntimeError):
+        wm.backward(torch.zeros(rows, 10, device="cuda"))
+    b = wm.forward(((x - mean) / std).contiguous()).clone()
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        wm.forward(x, mean, None)
+
+
 def test_fused_adam_matches_torch_adam():
     from rsr_mjx_b200 import fused_mlp
     torch.manual_seed(2)
