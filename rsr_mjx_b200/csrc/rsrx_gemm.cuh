@@ -269,15 +269,25 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
       // kb / 4 * 128 B apart (SBO), one UMMA_K = 8 step = two core matrices.  TMA operands: slab k / 4, 32 B per step inside
       // the 128-byte swizzle span.
       const uint32_t SBO = (uint32_t)(kb >> 2) * 128;
-      for (int k = 0; k < kb / UMMA_K; ++k) {
-        const uint64_t da = A_MN ? make_desc(a_addr + k * 256, 128, SBO) : make_desc_sw128(a_addr + (k >> 2) * (BM * BK * 4) + (k & 3) * 32);
-        const uint64_t db = B_MN ? make_desc(b_addr + k * 256, 128, SBO) : make_desc_sw128(b_addr + (k >> 2) * (BN * BK * 4) + (k & 3) * 32);
+      // descriptors advance by adding to the 14-bit (address >> 4) field: one 64-bit add per operand per MMA instead of
+      // rebuilding them (the issue loop, not the tensor core, was the limit: 45 ns per 128 x 64 x 8 instruction)
+      uint64_t da = A_MN ? make_desc(a_addr, 128, SBO) : make_desc_sw128(a_addr);
+      uint64_t db = B_MN ? make_desc(b_addr, 128, SBO) : make_desc_sw128(b_addr);
+      // byte steps: inside a 32-float slab / from the last step of a slab to the next slab
+      constexpr uint32_t A_IN = A_MN ? 256 : 32, A_OUT = A_MN ? 256 : BM * BK * 4 - 3 * 32;
+      constexpr uint32_t B_IN = B_MN ? 256 : 32, B_OUT = B_MN ? 256 : BN * BK * 4 - 3 * 32;
+      const int nk = kb / UMMA_K;
+#pragma unroll 4
+      for (int k = 0; k < nk; ++k) {
         const uint32_t accumulate = (!first || k > 0) ? 1u : 0u;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+        const bool last_of_slab = (k & 3) == 3;
+        da += (uint64_t)((last_of_slab ? A_OUT : A_IN) >> 4);
+        db += (uint64_t)((last_of_slab ? B_OUT : B_IN) >> 4);
       }
       // arrives on the barrier when these (and all earlier) MMAs are done; implies fence::before_thread_sync
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -323,7 +333,8 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
 #pragma unroll
     for (int j = 0; j < 4; ++j) bias4[j] = col + j < p.N ? p.bias[col + j] : 0.f;
   const bool vec = col + 3 < p.N;  // ldd % 4 == 0 and 16-byte aligned bases (host-checked): whole float4 in range
-#pragma unroll 1
+  // BM / RPP = 4 passes, unrolled: the global loads of the dgrad epilogue (zprev) are all in flight at once
+#pragma unroll
   for (int rr = rg; rr < BM; rr += RPP) {
     const int row = m0 + rr;
     if (row >= p.M) break;
