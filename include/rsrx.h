@@ -163,6 +163,18 @@ int rsrx_physics_step_debug(const rsrx_model* m, int N, float* data, const rsrx_
 int rsrx_rsr_loss(const float* grid, int M, int D, const float* reference_data, int Nref, const float* batch, int Nb,
                   const float* reference_density, float bandwidth, float divergence, float loss_scale,
                   float* density_out, float* out, float* grad_batch, void* stream);
+/* The RSR term as the PPO loss uses it (RSR/losses.py:186-195: compute_rsr_loss on (observation, mode of the policy,
+ * next_observation)) without host-framework glue.  rsrx_rsr_policy_term: packs transition[r] = [obs[r] (O) |
+ * tanh(logits[r][0:A]) | next_obs[r] (O)] into `transition` [rows][2O+A] and runs rsrx_rsr_loss on it: out[0] = loss,
+ * out[1] = distance, grad_transition [rows][2O+A] = d loss / d transition.  rsrx_rsr_logit_grad: grad_logits_out[r][k] =
+ * grad_logits_in[r][k] (NULL = 0) + d loss / d logits[r][k] (chain rule through tanh for k < A, zero for the scale half);
+ * in and out may alias.  logits are [rows][2A] (location | scale parameters). */
+int rsrx_rsr_policy_term(const float* grid, int M, const float* reference_data, int Nref, const float* reference_density,
+                         float bandwidth, float divergence, float loss_scale, const float* obs, const float* logits,
+                         const float* next_obs, int rows, int O, int A, float* transition, float* grad_transition, float* out,
+                         void* stream);
+int rsrx_rsr_logit_grad(const float* transition, const float* grad_transition, const float* grad_logits_in, int rows, int O, int A,
+                        float* grad_logits_out, void* stream);
 /* KDE density only (evaluate_kde) for build_rsr_data (rsr_loss.py:43-91) */
 int rsrx_kde(const float* grid, int M, int D, const float* data, int Ndata, float bandwidth, float* density_out,
              void* stream);

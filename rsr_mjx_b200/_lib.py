@@ -93,6 +93,8 @@ def lib():
     L.rsrx_linear_wgrad.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]
     L.rsrx_reduce_partials.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.rsrx_value_head_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
+    L.rsrx_rsr_policy_term.argtypes = [vp, i32, vp, i32, vp, f32, f32, f32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.rsrx_rsr_logit_grad.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     L.rsrx_ppo_prep.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, i32, vp]
     L.rsrx_small_mlp_forward.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp]
     L.rsrx_small_mlp_backward.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp]
@@ -114,4 +116,5 @@ EXPORTS = ("rsrx_model_create", "rsrx_model_destroy", "rsrx_model_layout", "rsrx
            "rsrx_env_reset", "rsrx_env_step", "rsrx_env_step_host", "rsrx_physics_step", "rsrx_debug_stride", "rsrx_max_contacts", "rsrx_physics_step_debug",
            "rsrx_rsr_loss", "rsrx_kde", "rsrx_ppo_head", "rsrx_debug_narrowphase", "rsrx_act_bias_backward", "rsrx_act_bias_backward_workspace", "rsrx_gather_rows", "rsrx_tanh_normal_act", "rsrx_last_error", "rsrx_version",
            "rsrx_linear_forward", "rsrx_linear_dgrad", "rsrx_linear_wgrad", "rsrx_reduce_partials", "rsrx_value_head_backward", "rsrx_adam_step",
-           "rsrx_small_mlp_forward", "rsrx_small_mlp_backward", "rsrx_small_mlp_backward_ctas", "rsrx_ppo_prep")
+           "rsrx_small_mlp_forward", "rsrx_small_mlp_backward", "rsrx_small_mlp_backward_ctas", "rsrx_ppo_prep", "rsrx_rsr_policy_term",
+           "rsrx_rsr_logit_grad")

@@ -621,6 +621,34 @@ extern "C" int rsrx_rsr_loss(const float* grid, int M, int D, const float* refer
              : 0;
 }
 
+extern "C" int rsrx_rsr_policy_term(const float* grid, int M, const float* reference_data, int Nref, const float* reference_density,
+                                    float bandwidth, float divergence, float loss_scale, const float* obs, const float* logits,
+                                    const float* next_obs, int rows, int O, int A, float* transition, float* grad_transition,
+                                    float* out, void* stream) {
+  if (!grid || !reference_density || !obs || !logits || !next_obs || !transition || !grad_transition || !out)
+    return fail("rsrx_rsr_policy_term: null argument");
+  if (Nref > 0 && !reference_data) return fail("rsrx_rsr_policy_term: reference_data is null");
+  const int D = 2 * O + A;
+  if (M <= 0 || M > loss::MAXM || rows <= 0 || O <= 0 || A <= 0 || D > loss::MAXD || Nref < 0 || !(bandwidth > 0.f))
+    return fail("rsrx_rsr_policy_term: bad sizes (M <= 64, 2 O + A <= 256)");
+  const int blocks = (int)std::min<size_t>(((size_t)rows * D + 255) / 256, 4 * 148);
+  CUDA_OK(pdl::launch(loss::pack_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, obs, logits, next_obs, rows, O, A, transition));
+  return loss::launch(grid, M, D, reference_data, Nref, transition, rows, reference_density, bandwidth, divergence, loss_scale, nullptr,
+                      out, grad_transition, (cudaStream_t)stream)
+             ? fail(std::string("rsrx_rsr_policy_term: ") + cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+
+extern "C" int rsrx_rsr_logit_grad(const float* transition, const float* grad_transition, const float* grad_logits_in, int rows, int O,
+                                   int A, float* grad_logits_out, void* stream) {
+  if (!transition || !grad_transition || !grad_logits_out || rows <= 0 || O <= 0 || A <= 0)
+    return fail("rsrx_rsr_logit_grad: bad arguments");
+  const int blocks = (int)std::min<size_t>(((size_t)rows * 2 * A + 255) / 256, 4 * 148);
+  CUDA_OK(pdl::launch(loss::unpack_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, transition, grad_transition, grad_logits_in,
+                      rows, O, A, grad_logits_out));
+  return 0;
+}
+
 // ---- tensor-core linear layers (csrc/rsrx_gemm.cuh) -----------------------------------------------------------------
 static unsigned long long* gemm_dbg() {  // RSRX_GEMM_STAMPS = device address of 8 uint64 (profiling aid)
   const char* d = getenv("RSRX_GEMM_STAMPS");

@@ -302,5 +302,41 @@ inline int launch(const float* grid, int M, int D, const float* ref, int Nref, c
   return 0;
 }
 
+// ---- the policy-side glue of the RSR term (RSR/losses.py:186-195) without torch in between --------------------------------
+// pack:   transition[r] = [obs[r] | tanh(logits[r][0:A]) | next_obs[r]]   (the loss acts on the MODE of the tanh-normal policy)
+// unpack: g_out[r][k] = g_in[r][k] + (k < A ? g_transition[r][O + k] * (1 - tanh^2) : 0)   (chain rule through the mode; the
+//         scale half of the logits gets no RSR gradient)
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ obs, const float* __restrict__ logits,
+                                                   const float* __restrict__ next_obs, int rows, int O, int A,
+                                                   float* __restrict__ transition) {
+  pdl::launch_dependents();
+  pdl::wait();
+  const int D = 2 * O + A;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * D; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / D), c = (int)(i % D);
+    float v;
+    if (c < O) v = obs[(size_t)r * O + c];
+    else if (c < O + A) v = tanhf(logits[(size_t)r * 2 * A + (c - O)]);
+    else v = next_obs[(size_t)r * O + (c - O - A)];
+    transition[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) unpack_kernel(const float* __restrict__ transition, const float* __restrict__ g_transition,
+                                                     const float* __restrict__ g_in, int rows, int O, int A,
+                                                     float* __restrict__ g_out) {
+  pdl::launch_dependents();
+  pdl::wait();
+  const int D = 2 * O + A;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * 2 * A; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (2 * A)), k = (int)(i % (2 * A));
+    float g = g_in ? g_in[i] : 0.f;
+    if (k < A) {
+      const float t = transition[(size_t)r * D + O + k];
+      g += g_transition[(size_t)r * D + O + k] * (1.f - t * t);
+    }
+    g_out[i] = g;
+  }
+}
+
 }  // namespace loss
 }  // namespace rsrx

@@ -610,6 +610,11 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
                  int(bool(normalize_advantage)))
         obs_n_buf = torch.empty(mb * T, obs_size, device=dev)
         policy_stream = torch.cuda.Stream(device=dev)
+        zero_scalar = torch.zeros((), device=dev)
+        rsr_term = None
+        if ptc is not None and past_data is not None and rsr_loss_scale != 0:
+            rsr_term = rsr.PolicyTerm(past_data, mb * T, obs_size, act_size, rsr_loss_scale, dev)
+            g_total_buf = torch.empty(mb, T, 2 * act_size, device=dev)
         # the normaliser's tensors are updated in place, so the prep kernel can keep reading them; identity when off
         prep_mean = norm.mean if normalize_observations else torch.zeros(obs_size, device=dev)
         prep_std = norm.std if normalize_observations else torch.ones(obs_size, device=dev)
@@ -638,15 +643,13 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             pol.wait_stream(main)
             with torch.cuda.stream(pol):
                 logits = ptc.forward(obs_n_buf).view(mb, T, 2 * act_size)
-                if past_data is not None and rsr_loss_scale != 0:
-                    # the RSR term acts on mode(logits) (RSR/losses.py:186-195): its gradient w.r.t. the logits joins the head's
-                    leaf = logits.detach().requires_grad_(True)
-                    sim2real_loss, distance = rsr.compute_rsr_loss(obs, NormalTanh.mode(leaf), static["next_observation"], past_data,
-                                                                   loss_scale=rsr_loss_scale)
-                    (g_extra,) = torch.autograd.grad(sim2real_loss, leaf)
+                if rsr_term is not None:
+                    # the RSR term acts on mode(logits) (RSR/losses.py:186-195): pack + KDE + gradient kernels now, its
+                    # gradient w.r.t. the logits joins the head's below
+                    rsr_term.forward(obs, ptc.out, static["next_observation"])
+                    sim2real_loss, distance = rsr_term.loss, rsr_term.distance
                 else:
-                    g_extra = None
-                    sim2real_loss = distance = torch.zeros((), device=dev)
+                    sim2real_loss = distance = zero_scalar
         else:
             logits = net.policy(obs_n)  # autograd fallback for policies wider than 32
         with torch.no_grad():
@@ -664,7 +667,9 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
             if ptc is not None:
                 pol.wait_stream(main)  # the head's logit gradients
                 with torch.cuda.stream(pol):
-                    ptc.backward(g_logits_buf if g_extra is None else g_logits_buf + g_extra)
+                    if rsr_term is not None:
+                        rsr_term.add_logit_grad(g_logits_buf, g_total_buf)
+                    ptc.backward(g_total_buf if rsr_term is not None else g_logits_buf)
             vtc.backward(g_values_buf)
             if ptc is not None:
                 main.wait_stream(pol)

@@ -8,7 +8,7 @@ next_observations (the reference's policy gradient flows through
 from __future__ import annotations
 
 import ctypes as C
-from typing import Any, NamedTuple
+from typing import Any, NamedTuple, Optional
 
 import numpy as np
 import torch
@@ -152,6 +152,45 @@ class _RSRLossFn(torch.autograd.Function):
         if g_dist is not None and ctx.loss_scale * ctx.divergence != 0.0:
             g = g + grad * (g_dist / (ctx.loss_scale * ctx.divergence))
         return g, None, None, None, None, None, None
+
+
+class PolicyTerm:
+    """The RSR term of the PPO loss (RSR/losses.py:186-195) on fixed buffers, without autograd or torch glue:
+    `forward(obs, logits, next_obs)` packs [obs | tanh(loc) | next_obs], runs the KDE + Wasserstein kernels and keeps
+    d loss / d transition; `add_logit_grad(g_in, g_out)` writes g_in + d loss / d logits.  `loss` / `distance` are views of
+    a device buffer (valid after forward, overwritten by the next one).  Same arithmetic as
+    `compute_rsr_loss(obs, NormalTanh.mode(logits), next_obs, past_data, loss_scale=...)` + autograd."""
+
+    def __init__(self, past_data: Any, rows: int, obs_size: int, act_size: int, loss_scale: float, device):
+        self.rsr = prepare_rsr_data(past_data, device)
+        self.rows, self.O, self.A, self.scale = int(rows), int(obs_size), int(act_size), float(loss_scale)
+        D = 2 * self.O + self.A
+        if self.rsr.grid.shape[1] != D or self.rsr.reference_data.shape[1] != D:
+            raise ValueError(f'online transition width does not match RSR reference data: {D} != {self.rsr.reference_data.shape[1]}')
+        self.dev = torch.device(device)
+        self.transition = torch.empty(self.rows, D, device=self.dev)
+        self.grad_transition = torch.empty(self.rows, D, device=self.dev)
+        self.out = torch.zeros(2, device=self.dev)
+        self.loss, self.distance = self.out[0], self.out[1]
+        self.divergence = float(self.rsr.divergence)
+
+    def forward(self, obs: torch.Tensor, logits: torch.Tensor, next_obs: torch.Tensor) -> None:
+        r = self.rsr
+        for t, w in ((obs, self.O), (logits, 2 * self.A), (next_obs, self.O)):
+            if t.numel() != self.rows * w or not t.is_contiguous():
+                raise ValueError("PolicyTerm.forward: contiguous [rows, width] inputs expected")
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().rsrx_rsr_policy_term(
+                r.grid.data_ptr(), r.grid.shape[0], r.reference_data.data_ptr(), r.reference_data.shape[0],
+                r.reference_density.data_ptr(), float(r.bandwidth), self.divergence, self.scale, obs.data_ptr(), logits.data_ptr(),
+                next_obs.data_ptr(), self.rows, self.O, self.A, self.transition.data_ptr(), self.grad_transition.data_ptr(),
+                self.out.data_ptr(), _stream(self.dev)), "rsrx_rsr_policy_term")
+
+    def add_logit_grad(self, g_in: Optional[torch.Tensor], g_out: torch.Tensor) -> None:
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().rsrx_rsr_logit_grad(
+                self.transition.data_ptr(), self.grad_transition.data_ptr(), None if g_in is None else g_in.data_ptr(), self.rows,
+                self.O, self.A, g_out.data_ptr(), _stream(self.dev)), "rsrx_rsr_logit_grad")
 
 
 def compute_rsr_loss(observations, policy_actions, next_observations, past_data: Any, *, loss_scale: float = 1.0):

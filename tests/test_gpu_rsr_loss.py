@@ -114,3 +114,32 @@ def test_validation_errors_match_reference_messages():
         rsr_loss.compute_rsr_loss(torch.zeros(4, 3, device="cuda"), torch.zeros(4, 1, device="cuda"), torch.zeros(4, 2, device="cuda"), d)
     with pytest.raises(TypeError):
         rsr_loss.compute_rsr_loss(torch.zeros(4, 3, device="cuda"), torch.zeros(4, 1, device="cuda"), torch.zeros(4, 3, device="cuda"), 3.0)
+
+
+def test_policy_term_equals_compute_rsr_loss_with_autograd():
+    """rsr_loss.PolicyTerm (pack -> KDE/Wasserstein kernels -> chain rule through tanh, no torch in between: what the PPO
+    update runs) == compute_rsr_loss(obs, tanh(loc), next_obs) + autograd w.r.t. the logits, bit for bit on the loss and
+    to 1 ulp-level on the gradient (same kernels underneath; only the tanh derivative is formed differently)."""
+    g = torch.Generator("cuda").manual_seed(7)
+    O, A, rows = 23, 5, 640
+    D = 2 * O + A
+    real = torch.randn(50, D, device="cuda", generator=g) * 0.4
+    past = rsr_loss.build_rsr_data(real, real + 0.05, real + 0.02, num_samples=10, min_value=-1.0, max_value=1.0, bandwidth=0.7)
+    obs = torch.randn(rows, O, device="cuda", generator=g) * 0.4
+    nxt = torch.randn(rows, O, device="cuda", generator=g) * 0.4
+    logits = torch.randn(rows, 2 * A, device="cuda", generator=g)
+    g_head = torch.randn(rows, 2 * A, device="cuda", generator=g) * 1e-3
+    leaf = logits.clone().requires_grad_(True)
+    loss, dist = rsr_loss.compute_rsr_loss(obs, torch.tanh(leaf[:, :A]), nxt, past, loss_scale=3.0)
+    (g_ref,) = torch.autograd.grad(loss, leaf)
+    term = rsr_loss.PolicyTerm(past, rows, O, A, 3.0, "cuda")
+    term.forward(obs, logits, nxt)
+    out = torch.empty_like(g_head)
+    term.add_logit_grad(g_head, out)
+    torch.cuda.synchronize()
+    assert float(term.loss) == float(loss) and float(term.distance) == float(dist) and float(loss) != 0.0
+    assert (g_ref[:, A:] == 0).all() and torch.equal(out[:, A:], g_head[:, A:])
+    torch.testing.assert_close(out[:, :A] - g_head[:, :A], g_ref[:, :A], rtol=1e-4, atol=1e-9)
+    assert g_ref.abs().max() > 0
+    with pytest.raises(ValueError):
+        rsr_loss.PolicyTerm(past, rows, O + 1, A, 3.0, "cuda")
