@@ -34,7 +34,8 @@ struct rsrx_model {
 };
 
 // Launch shape for N envs: one CTA per SM per round, the rounds as evenly filled as possible.  8192 envs on 148 SMs:
-// 4 rounds of 14 envs per CTA; 1024 envs: one round of 147 CTAs x 7 envs instead of 74 CTAs x 14 on half the SMs.
+// 3 rounds of 19 envs per CTA (432 CTAs); 1024 envs: one round of 147 CTAs x 7 envs instead of 54 CTAs x 19 on a third
+// of the SMs.
 constexpr int kSmallW = WPB < 14 ? WPB : 14;  // CTAs of up to 14 warps use the 128-register instantiation of step_kernel
 struct LaunchCfg { int grid, block; size_t smem; };
 static LaunchCfg launch_cfg(const rsrx_model* m, int N) {
