@@ -14,6 +14,9 @@ What this module reads
     payload), maps containers (flax FrozenDict, dataclass-like records such as RunningStatisticsState / PPONetworkParams)
     to plain dicts, and rejects everything else;
   * this package's own single-file torch checkpoints (`ppo.save_params`).
+What it writes: `save_brax_params` — the same pickle layout from a policy trained here (NumPy leaves, the normaliser as a
+`brax.training.acme.running_statistics.RunningStatisticsState` global reference), so the reference's inference code
+(`model.load_params` + `make_inference_fn`, ppo_inference.py:49-69 with a params file) can load it where brax is installed.
 What it cannot read: Orbax directories (OCDBT / zarr via tensorstore — not present in this image).  Convert them once
 where orbax is installed:  `brax.io.model.save_params(out, ocp.PyTreeCheckpointer().restore(ckpt_dir))`.
 """
@@ -127,7 +130,10 @@ def _normalizer(tree, size, device):
         return norm
     t = tree if isinstance(tree, dict) else dict(zip(("count", "mean", "summed_variance", "std"), tree))
     for k in ("count", "mean", "summed_variance", "std"):
-        v = np.asarray(t[k], np.float32)
+        v = t[k]
+        if isinstance(v, dict) and "hi" in v and "lo" in v:  # brax.training.types.UInt64(hi, lo) step counter
+            v = float(int(np.asarray(v["hi"])) * 2.0 ** 32 + int(np.asarray(v["lo"])))
+        v = np.asarray(v, np.float32)
         getattr(norm, k).copy_(torch.from_numpy(v.reshape(getattr(norm, k).shape)).to(device))
     return norm
 
@@ -178,6 +184,60 @@ def sac_params_from_brax(tree, device="cuda"):
             _fill_mlp(net.q1, _mlp_layers(q[heads[0]]), "q1")
             _fill_mlp(net.q2, _mlp_layers(q[heads[1]]), "q2")
     return _normalizer(parts[0], obs, device), net.to(device)
+
+
+def _flax_mlp(mlp) -> Dict[str, Any]:
+    """torch MLP -> {'params': {'hidden_i': {'kernel' [in, out], 'bias' [out]}}} with NumPy leaves"""
+    return {"params": {f"hidden_{i}": {"kernel": l.weight.detach().t().contiguous().cpu().numpy().astype(np.float32),
+                                       "bias": l.bias.detach().cpu().numpy().astype(np.float32)}
+                       for i, l in enumerate(mlp.layers)}}
+
+
+def save_brax_params(path: str, params, algorithm: str = "ppo") -> None:
+    """Writes `(normalizer, networks)` as returned by `ppo.train` / `sac.train` in the layout of
+    `brax.io.model.save_params`: a pickle of `(RunningStatisticsState, policy_params, value_params)` (PPO) or
+    `(RunningStatisticsState, policy_params, {'params': {'q1': ..., 'q2': ...}})` (SAC; brax's own q-network naming
+    depends on its version, the policy is what inference needs).  The normaliser is pickled as a reference to
+    `brax.training.acme.running_statistics.RunningStatisticsState` (fields count / mean / summed_variance / std), so
+    `brax.io.model.load_params` rebuilds the real class where brax is installed; this package reads the file back
+    through `load_brax_params` without brax."""
+    import sys
+    import types as _types
+    norm, net = params
+    mod_name, cls_name = "brax.training.acme.running_statistics", "RunningStatisticsState"
+    cls = type(cls_name, (), {"__module__": mod_name})
+    state = cls()
+    state.__dict__.update(count=np.float32(float(norm.count)), mean=norm.mean.detach().cpu().numpy().astype(np.float32),
+                          summed_variance=norm.summed_variance.detach().cpu().numpy().astype(np.float32),
+                          std=norm.std.detach().cpu().numpy().astype(np.float32))
+    if algorithm == "ppo":
+        tree = (state, _flax_mlp(net.policy), _flax_mlp(net.value))
+    elif algorithm == "sac":
+        tree = (state, _flax_mlp(net.policy), {"params": {"q1": _flax_mlp(net.q1)["params"], "q2": _flax_mlp(net.q2)["params"]}})
+    else:
+        raise ValueError(f"unsupported algorithm: {algorithm}")
+    # pickle verifies a class by importing its module: stand in for the (absent) brax modules while dumping
+    added = []
+    try:
+        parts = mod_name.split(".")
+        for i in range(1, len(parts) + 1):
+            name = ".".join(parts[:i])
+            if name not in sys.modules:
+                sys.modules[name] = _types.ModuleType(name)
+                added.append(name)
+        had = getattr(sys.modules[mod_name], cls_name, None)
+        setattr(sys.modules[mod_name], cls_name, cls)
+        try:
+            with open(path, "wb") as f:
+                pickle.dump(tree, f, protocol=4)
+        finally:
+            if had is None:
+                delattr(sys.modules[mod_name], cls_name)
+            else:
+                setattr(sys.modules[mod_name], cls_name, had)
+    finally:
+        for name in added:
+            sys.modules.pop(name, None)
 
 
 def restore(path: str, algorithm: str = "ppo", device="cuda"):

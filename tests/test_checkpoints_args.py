@@ -92,6 +92,39 @@ def test_brax_sac_pickle_import_and_restore_dispatch(tmp_path):
         checkpoints.restore(str(d), "ppo", device="cpu")
 
 
+def test_brax_pickle_export_round_trip(tmp_path):
+    """save_brax_params writes the layout `brax.io.model.load_params` expects — the normaliser as a global reference to
+    brax.training.acme.running_statistics.RunningStatisticsState, flax-shaped parameter dicts with [in, out] kernels — and
+    leaves no fake module behind; our own loader reads it back to identical networks.  A step counter stored as
+    brax's UInt64(hi, lo) is accepted on import."""
+    import pickletools
+    from rsr_mjx_b200 import ppo
+    torch.manual_seed(0)
+    norm = ppo.RunningStatistics(23, "cpu")
+    norm.update(torch.randn(100, 23))
+    net = ppo.PPONetworks(23, 5)
+    f = tmp_path / "ppo_params"
+    checkpoints.save_brax_params(str(f), (norm, net), "ppo")
+    assert not any(m.startswith("brax") for m in sys.modules)
+    strings = [a for op, a, _ in pickletools.genops(f.read_bytes()) if op.name in ("SHORT_BINUNICODE", "BINUNICODE")]
+    assert "brax.training.acme.running_statistics" in strings and "RunningStatisticsState" in strings
+    r_norm, r_net = checkpoints.restore(str(f), "ppo", device="cpu")
+    for a, b in zip(net.parameters(), r_net.parameters()):
+        assert torch.equal(a, b)
+    for k in ("count", "mean", "summed_variance", "std"):
+        assert torch.equal(getattr(norm, k), getattr(r_norm, k)), k
+    # UInt64 step counter of newer brax versions
+    tree = checkpoints.load_brax_params(str(f))
+    tree[0]["count"] = {"hi": np.uint32(0), "lo": np.uint32(100)}
+    assert float(checkpoints.ppo_params_from_brax(tree, device="cpu")[0].count) == 100.0
+    from rsr_mjx_b200 import sac
+    snet = sac.SACNetworks(23, 5, (32, 32))
+    checkpoints.save_brax_params(str(tmp_path / "sac_params"), (norm, snet), "sac")
+    _, r_snet = checkpoints.restore(str(tmp_path / "sac_params"), "sac", device="cpu")
+    for a, b in zip(snet.parameters(), r_snet.parameters()):
+        assert torch.equal(a, b)
+
+
 def test_unpickler_refuses_code():
     class Evil:
         def __reduce__(self):
