@@ -346,6 +346,23 @@ def ppo_sub_record(dev, rank, world, training_steps=5):
                        "past_data": "synthetic six-table set from a 51-step random-action rollout of one env + noise, 50 transitions, grid 10 x 51, h = 3.0 (the default 0.1 makes the term identically 0)"}}
 
 
+def sac_sub_record(dev, training_steps=300):
+    """SAC on the sf env at the reference's RSR defaults (test/rsr_policy_training.py:60-68: 512 envs, batch
+    128, min_replay 10 000, max_replay 200 000; one gradient update per actor step), `training/sps` over the steps after
+    the replay prefill.  Single GPU only (the trainer has no multi-rank path)."""
+    from rsr_mjx_b200 import sac
+    from rsr_mjx_b200.envs import AirbotPlayBase
+    env = AirbotPlayBase("sf", num_envs=512, episode_length=1200, device=dev)
+    seen = []
+    sac.train(env, num_timesteps=10**9, episode_length=1200, num_envs=512, batch_size=128, min_replay_size=10_000,
+              max_replay_size=200_000, num_evals=5, max_training_steps=training_steps, use_cuda_graph=True, run_evals=False,
+              progress_fn=lambda n, m: seen.append(m["training/sps"]))
+    return {"metric": "sac_train_env_steps_per_sec", "value": float(seen[-1]), "unit": "env-steps/s", "n_gpus": 1,
+            "training_steps_timed": training_steps,
+            "config": {"workload": "SAC on airbot_sf, 512 envs, batch 128, 1 gradient update per actor step, replay ring on the device",
+                       "update": "torch modules inside CUDA graphs (not the hand-written PPO kernels)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -443,6 +460,8 @@ def main():
         barrier()
         sub["ppo_train_env_steps_per_sec"] = ppo_sub_record(dev, rank, world)
         barrier()
+        if world == 1:
+            sub["sac_train_env_steps_per_sec"] = sac_sub_record(dev)
 
     total_ms, e2e_ms = sharding.reduce_max([total_ms, e2e_ms], device=dev)
     if rank == 0:
