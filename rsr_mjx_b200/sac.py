@@ -236,11 +236,10 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         opt_alpha.zero_grad(set_to_none=True)
         la = alpha_loss(log_alpha, net, normalize, tr, noise[0], target_entropy)
         la.backward()
-        alpha = torch.exp(log_alpha.detach()).clone()  # the OLD alpha feeds critic and actor
         opt_q.zero_grad(set_to_none=True)
-        lq = critic_loss(net, target, normalize, alpha, tr, noise[1], reward_scaling, discounting)
+        lq = critic_loss(net, target, normalize, alpha_static, tr, noise[1], reward_scaling, discounting)  # the OLD alpha
         lq.backward(inputs=q_params)
-        return la, lq, alpha
+        return la, lq, alpha_static
 
     def grads_actor(alpha):
         tr = view(static)
@@ -251,17 +250,35 @@ def train(environment, num_timesteps: int, episode_length: int, past_data: Any =
         lp.backward(inputs=pol_params)
         return lp, s2r, distance
 
+    target_params = list(target.q1.parameters()) + list(target.q2.parameters())
+
     @torch.no_grad()
     def finish():
-        for t, s in zip(list(target.q1.parameters()) + list(target.q2.parameters()), q_params):
-            t.mul_(1 - tau).add_(s, alpha=tau)
+        # polyak step of the target critics, two multi-tensor launches instead of two per tensor (same arithmetic)
+        torch._foreach_mul_(target_params, 1 - tau)
+        torch._foreach_add_(target_params, q_params, alpha=tau)
 
     alpha_static = torch.ones((), device=dev)
+    actor_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
     def sgd_eager():
-        la, lq, alpha = grads_alpha_q()
-        alpha_static.copy_(alpha)
-        lp, s2r, distance = grads_actor(alpha_static)
+        # The three gradients are all taken at the OLD parameters (brax's update order), so the actor branch (policy
+        # forward, both critics, backward through them into the policy: about half of the step's launches) does not
+        # depend on the alpha / critic branch: it runs on its own stream, forked from and joined back into the current
+        # one (two parallel branches of the graph when captured).  The parameter sets the two branches write gradients
+        # for are disjoint.
+        with torch.no_grad():
+            alpha_static.copy_(torch.exp(log_alpha.detach()))
+        if actor_stream is None:
+            la, lq, _ = grads_alpha_q()
+            lp, s2r, distance = grads_actor(alpha_static)
+        else:
+            main = torch.cuda.current_stream(dev)
+            actor_stream.wait_stream(main)
+            with torch.cuda.stream(actor_stream):
+                lp, s2r, distance = grads_actor(alpha_static)
+            la, lq, _ = grads_alpha_q()
+            main.wait_stream(actor_stream)
         return dict(alpha_loss=la, critic_loss=lq, actor_loss=lp, sim2real_loss=s2r, rsr_distribution_distance=distance,
                     alpha=alpha_static)
 
