@@ -95,13 +95,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+// The sigmoid of the fused epilogues uses the hardware exponential and reciprocal (ex2.approx / rcp.approx, ~2 ulp): the
+// activation math of a 128 x 64 tile was 6.4 K warp-instructions with expf + IEEE division, as long as the MMAs and the
+// stores together, and its inputs carry TF32 rounding (2^-11) anyway.
+__device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 __device__ __forceinline__ float act_fwd(int act, float z) {
-  if (act == ACT_SILU) return z / (1.f + expf(-z));
+  if (act == ACT_SILU) return z * fast_sigmoid(z);
   if (act == ACT_RELU) return z > 0.f ? z : 0.f;
   return z;
 }
 __device__ __forceinline__ float act_bwd(int act, float z) {
-  if (act == ACT_SILU) { const float s = 1.f / (1.f + expf(-z)); return s * (1.f + z * (1.f - s)); }
+  if (act == ACT_SILU) { const float s = fast_sigmoid(z); return s * (1.f + z * (1.f - s)); }
   if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
   return 1.f;
 }
@@ -376,6 +380,7 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
   }
   if (p.DT && p.epilogue != EPI_PARTIAL) {  // pass 3: the transposed copy, a warp per column, lanes over 32 consecutive rows
     __syncthreads();
+#pragma unroll 4
     for (int task = warp; task < BN * (BM / 32); task += THREADS / 32) {
       const int c = task / (BM / 32), rr = (task % (BM / 32)) * 32 + lane;
       if (n0 + c < p.N && m0 + rr < p.M) p.DT[(size_t)(n0 + c) * p.ldt + m0 + rr] = sC[rr * LDS + c];
