@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs += [os.path.join(_HERE, "..", "include", f) for f in ("rsrx.h", "rsrx_model.h")]
     if (not force) and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "rsrx_api.cu"), os.path.join(CSRC, "rsrx_redo.cu")]
+    cmd = ["nvcc", *NVCC_FLAGS, "--threads", "3", "-o", LIB_PATH, os.path.join(CSRC, "rsrx_api.cu"),
+           os.path.join(CSRC, "rsrx_redo.cu"), os.path.join(CSRC, "rsrx_mid.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

@@ -11,6 +11,7 @@
 #include "rsrx_loss.cuh"
 #include "rsrx_ppo.cuh"
 #include "rsrx_gemm.cuh"
+#include "rsrx_mid.h"
 #include "rsrx_mlp.cuh"
 #include "rsrx_redo.h"
 
@@ -30,6 +31,10 @@ struct rsrx_model {
   // [1] ticket, [2..] env ids; spill_envs entries)
   void* big_dev = nullptr;
   int big_smem = 0, big_grid = 0;
+  // the mid-capacity step kernel (rsrx_mid.cu: 64 contacts, <= 8 envs per CTA) takes the step launch of small batches
+  // (N <= num_sms * 8), where shared memory is plentiful, so that the redo pass is practically never needed there
+  void* mid_dev = nullptr;
+  int mid_arena_bytes = 0;
   int* redo = nullptr;
 };
 
@@ -373,6 +378,16 @@ extern "C" int rsrx_model_create(const void* blob_host, size_t blob_bytes, const
       return fail(msg);
     }
     m->big_grid = m->num_sms;
+    // not when a test knob reshapes the fast kernel (they are about its spill / redo / launch-shape paths), nor with RSRX_MID=0
+    const char* mid_off = getenv("RSRX_MID");
+    if (!(mid_off && mid_off[0] == '0') && !getenv("RSRX_POOL_LIMIT") && !getenv("RSRX_CONTACT_CAP") && !getenv("RSRX_FORCE_WPB")) {
+      if (rsrx_mid_prepare(&m->host, sizeof(DModel), max_smem, &m->mid_dev, &m->mid_arena_bytes, &err)) {
+        std::string msg = err ? err : "rsrx_mid_prepare failed";
+        if (m->big_dev) cudaFree(m->big_dev);
+        delete m;
+        return fail(msg);
+      }
+    }
   }
   cudaError_t e = cudaMalloc(&m->dev, sizeof(DModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DModel), cudaMemcpyHostToDevice);
@@ -394,6 +409,7 @@ extern "C" void rsrx_model_destroy(rsrx_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
   if (m->big_dev) cudaFree(m->big_dev);
+  if (m->mid_dev) cudaFree(m->mid_dev);
   if (m->spill) cudaFree(m->spill);
   if (m->redo) cudaFree(m->redo);
   delete m;
@@ -476,20 +492,37 @@ extern "C" int rsrx_env_reset(const rsrx_model* m, int N, const float* qpos, con
   return 0;
 }
 
+// step_kernel (the mid-capacity instantiation for small batches, else the fast one) + the redo pass
+static int launch_step(const rsrx_model* m, int N, const float* action, const rsrx_per_env* per_env, const rsrx_state& st,
+                       cudaStream_t s) {
+  if (ensure_spill(m, N)) return 1;
+  if (m->mid_dev && N <= m->num_sms * kMidWarps) {
+    rsrx_mid_launch a;
+    a.N = N; a.action = action;
+    a.geom_friction = per_env ? per_env->geom_friction : nullptr; a.body_mass = per_env ? per_env->body_mass : nullptr;
+    a.dof_damping = per_env ? per_env->dof_damping : nullptr; a.dof_frictionloss = per_env ? per_env->dof_frictionloss : nullptr;
+    a.redo = m->redo;
+    a.data = st.data; a.first_data = st.first_data; a.obs = st.obs; a.first_obs = st.first_obs; a.reward = st.reward;
+    a.done = st.done; a.info = st.info; a.metrics = st.metrics; a.status = st.status;
+    CUDA_OK(rsrx_mid_launch_step(m->mid_dev, a, m->num_sms, m->mid_arena_bytes, s));
+  } else {
+    const LaunchCfg lc = launch_cfg(m, N);
+    if (lc.block <= 32 * kSmallW) step_kernel<kSmallW><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
+    else step_kernel<WPB><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
+    CUDA_OK(cudaGetLastError());
+  }
+  rsrx_redo_launch ra = redo_args(1);
+  ra.action = action;
+  CUDA_OK(launch_redo(m, ra, per_env, &st, s));
+  return 0;
+}
+
 extern "C" int rsrx_env_step(const rsrx_model* m, int N, rsrx_state st, const float* action, const rsrx_per_env* per_env,
                              void* stream) {
   if (!m || !action) return fail("rsrx_env_step: null argument");
   if (N <= 0) return fail("rsrx_env_step: N must be positive");
   if (check_state(st)) return 1;
-  if (ensure_spill(m, N)) return 1;
-  const LaunchCfg lc = launch_cfg(m, N);
-  if (lc.block <= 32 * kSmallW) step_kernel<kSmallW><<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
-  else step_kernel<WPB><<<lc.grid, lc.block, lc.smem, (cudaStream_t)stream>>>(m->dev, N, action, to_pe(m, per_env), to_sp(st));
-  CUDA_OK(cudaGetLastError());
-  rsrx_redo_launch ra = redo_args(1);
-  ra.action = action;
-  CUDA_OK(launch_redo(m, ra, per_env, &st, (cudaStream_t)stream));
-  return 0;
+  return launch_step(m, N, action, per_env, st, (cudaStream_t)stream);
 }
 
 extern "C" int rsrx_env_step_host(const rsrx_model* m, int N, rsrx_state st, const float* host_action,
@@ -501,14 +534,7 @@ extern "C" int rsrx_env_step_host(const rsrx_model* m, int N, rsrx_state st, con
   cudaStream_t s = (cudaStream_t)stream;
   const rsrx_layout& L = m->host.lay;
   CUDA_OK(cudaMemcpyAsync(action_staging, host_action, sizeof(float) * (size_t)N * m->host.nu, cudaMemcpyHostToDevice, s));
-  if (ensure_spill(m, N)) return 1;
-  const LaunchCfg lc = launch_cfg(m, N);
-  if (lc.block <= 32 * kSmallW) step_kernel<kSmallW><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
-  else step_kernel<WPB><<<lc.grid, lc.block, lc.smem, s>>>(m->dev, N, action_staging, to_pe(m, per_env), to_sp(st));
-  CUDA_OK(cudaGetLastError());
-  rsrx_redo_launch ra = redo_args(1);
-  ra.action = action_staging;
-  CUDA_OK(launch_redo(m, ra, per_env, &st, s));
+  if (launch_step(m, N, action_staging, per_env, st, s)) return 1;
   if (host_obs) CUDA_OK(cudaMemcpyAsync(host_obs, st.obs, sizeof(float) * (size_t)N * L.obs_stride, cudaMemcpyDeviceToHost, s));
   if (host_reward) CUDA_OK(cudaMemcpyAsync(host_reward, st.reward, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
   if (host_done) CUDA_OK(cudaMemcpyAsync(host_done, st.done, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));

@@ -409,7 +409,7 @@ __device__ __forceinline__ bool physics_body(const DModel* __restrict__ dm, floa
   return true;
 }
 
-#ifndef RSRX_REDO_ONLY
+#if !defined(RSRX_REDO_ONLY) && !defined(RSRX_STEP_ONLY)
 // ---------------------------------------------------------------- reset kernel
 __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restrict__ dm, int N, const float* __restrict__ qpos,
                                                   const float* __restrict__ qvel, const float* __restrict__ ctrl,
@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(32 * WPB) reset_kernel(const DModel* __restric
   }
 }
 
+#endif
+#ifndef RSRX_REDO_ONLY
 // ----------------------------------------------------------------- step kernel
 // MAXW: the most warps a CTA of this instantiation is launched with.  Up to 14 the register file allows 128 registers
 // per thread; the 19-warp shape (3 rounds at 8192 envs) has to live with 96.
@@ -441,6 +443,8 @@ __global__ void __launch_bounds__(32 * MAXW) step_kernel(const DModel* __restric
   }
 }
 
+#endif
+#if !defined(RSRX_REDO_ONLY) && !defined(RSRX_STEP_ONLY)
 // ------------------------------------------------------------ physics-only kernel
 __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restrict__ dm, int N, float* __restrict__ data,
                                                     int nsteps, PerEnv pe, int* __restrict__ status_out,
@@ -451,8 +455,9 @@ __global__ void __launch_bounds__(32 * WPB) physics_kernel(const DModel* __restr
   if (e >= N) return;
   if (!physics_body(dm, sm, lane, e, e, data, nsteps, pe, status_out, dump, 0) && lane == 0) redo_push(pe, e);
 }
-#endif  // RSRX_REDO_ONLY
+#endif  // RSRX_REDO_ONLY, RSRX_STEP_ONLY
 
+#ifndef RSRX_STEP_ONLY
 // ------------------------------------------------------------------ redo kernel
 // Runs the env bodies for the envs on the redo list (persistent: warp w of the grid takes entries w, w + W, ...); the
 // last CTA to finish clears the list for the next launch.  Meant for the large-capacity instantiation (rsrx_redo.cu),
@@ -492,7 +497,8 @@ __global__ void __launch_bounds__(32 * W) redo_kernel(const DModel* __restrict__
   }
 }
 
-#ifndef RSRX_REDO_ONLY
+#endif  // RSRX_STEP_ONLY
+#if !defined(RSRX_REDO_ONLY) && !defined(RSRX_STEP_ONLY)
 // Debug/parity entry: the cooperative narrow phase on a batch of explicit geom pairs (one half warp per pair, as in
 // collision()).  in: [n][30] = p1(3) m1(9) s1(3) p2(3) m2(9) s2(3); plane != 0: geom 1 is a plane (s1 unused).
 // out: [n][19] = dist(4) pos(4x3) nrm(3).

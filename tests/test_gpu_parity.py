@@ -566,6 +566,31 @@ def test_env_triggered_done_and_autoreset(kind):
         assert dones[:, N // 2:].sum() == 0
 
 
+@pytest.mark.parametrize("kind", ["sf", "T"])
+def test_mid_capacity_kernel_is_bitwise_the_fast_kernel(kind, monkeypatch):
+    """Batches of up to 8 envs per SM are stepped by a second instantiation of step_kernel with room for 64 active
+    contacts (rsrx_mid.cu), so that they practically never need the redo pass.  Same source, same arithmetic: 300
+    contact-rich steps of 700 envs must agree bit for bit with the fast kernel (RSRX_MID=0), whose only difference is the
+    informational RSRX_STATUS_CONTACT_REDO bit on envs that went through its redo pass."""
+    N = 700
+    env, keys, ic = _mk(kind, N, seed=31)
+    monkeypatch.setenv("RSRX_MID", "0")
+    env_fast = AirbotPlayBase(kind, num_envs=N, episode_length=1200)
+    monkeypatch.delenv("RSRX_MID")
+    env_mid = AirbotPlayBase(kind, num_envs=N, episode_length=1200)
+    s1, s2 = env_fast.reset_from(*ic), env_mid.reset_from(*ic)
+    acts = torch.rand(64, N, 5, device="cuda", generator=torch.Generator("cuda").manual_seed(5)) * 2 - 1
+    for t in range(300):
+        env_fast.step(s1, acts[t % 64])
+        env_mid.step(s2, acts[t % 64])
+    torch.cuda.synchronize()
+    for k in ("data", "first_data", "obs", "first_obs", "reward", "done", "info", "metrics"):
+        assert torch.equal(s1._buf[k], s2._buf[k]), k
+    keep = ~_lib.STATUS_CONTACT_REDO
+    assert torch.equal(s1._buf["status"] & keep, s2._buf["status"] & keep)
+    assert int((s2._buf["status"] & _lib.STATUS_CONTACT_OVERFLOW).max()) == 0
+
+
 @pytest.mark.parametrize("cap", ["0", "6", "11"])
 def test_redo_path_is_bitwise_identical(cap, monkeypatch):
     """An env-step with more active contacts than the fast arena holds is not committed by the fast kernel but re-run
