@@ -53,7 +53,7 @@ def kernel_source_hash():
     for f in sorted(os.listdir(d)):
         # (rsrx_api.cu holds every trainer entry point too and changes with them; the launch geometry it chooses is in the
         # summary's .meta.json)
-        if f in ("rsrx_device.cuh", "rsrx_physics.cuh", "rsrx_env.cuh", "rsrx_redo.cu", "rsrx_redo.h"):
+        if f in ("rsrx_device.cuh", "rsrx_physics.cuh", "rsrx_env.cuh", "rsrx_redo.cu", "rsrx_redo.h", "rsrx_mid.cu", "rsrx_mid.h"):
             with open(os.path.join(d, f), "rb") as fh:
                 h.update(fh.read())
     return h.hexdigest()[:16]
