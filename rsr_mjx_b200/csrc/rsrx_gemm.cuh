@@ -116,64 +116,46 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
 
-// Stage one operand tile (ROWS x KB, row index = the operand's M/N index, column = contraction index) into shared memory.
-// The shared-memory image is always K-major, no swizzle: core matrix = 8 rows x 16 B; element (r, k) at byte
+// Stage one operand tile (ROWS x KB, row index = the operand's M/N index, column = contraction index) whose GLOBAL layout is
+// contiguous along the row index (not the contraction) into shared memory, transposing on the way in.  (Operands that
+// are contiguous along the contraction are loaded by TMA instead, see the kernel.)
+// The shared-memory image is K-major, no swizzle: core matrix = 8 rows x 16 B; element (r, k) at byte
 //       (r % 8) * 16 + (r / 8) * SBO + (k / 4) * 128 + (k % 4) * 4,  SBO = KB / 4 * 128, LBO = 128.
-//   MN_MAJOR = false: global memory contiguous along the contraction: 16-byte cp.async straight into place.  Lane bits
-//       [0:2] row & 7, [3:4] chunk & 3: a quarter warp fills the 8 rows of one core matrix (distinct banks), a warp reads
-//       8 rows x 64 contiguous bytes (whole sectors);
-//   MN_MAJOR = true: global memory contiguous along the row index: 16-byte loads of 4 rows at one contraction index,
-//       transposed on the way in (4 scalar stores, issued in an order rotated by (k >> 2) & 3 so that the 32 lanes of one
-//       store instruction hit 32 distinct banks).  Lane bits [0:1] k & 3, [2] chunk parity, [3:4] (k >> 2) & 3.
+// 16-byte loads of 4 rows at one contraction index, 4 scalar stores, issued in an order rotated by (k >> 2) & 3 so that the
+// 32 lanes of one store instruction hit 32 distinct banks.  Lane bits [0:1] k & 3, [2] chunk parity, [3:4] (k >> 2) & 3.
 // Rows >= rows_valid and contraction indices >= k_valid are zero-filled.  The contiguous stride is 1 and every row / k
 // start is 16-byte aligned (host-checked).  kb: contraction length of this block (multiple of 32, <= KMAX).
-template <int ROWS, bool MN_MAJOR>
-__device__ __forceinline__ void stage_tile(float* smem, const float* __restrict__ g, int row_stride, int col_stride, int row0,
-                                           int k0, int rows_valid, int k_valid, int kb) {
+template <int ROWS>
+__device__ __forceinline__ void stage_tile_transposed(float* smem, const float* __restrict__ g, int col_stride, int row0, int k0,
+                                                      int rows_valid, int k_valid, int kb) {
   const int tid = threadIdx.x;
   const int CH = kb >> 2;  // 16-byte chunks per row
-  if (!MN_MAJOR) {
-    const int n = (ROWS / 8) * (CH / 4);  // warp-sized work items
-#pragma unroll 4
-    for (int hi = tid >> 5; hi < n; hi += THREADS / 32) {
-      const int low = tid & 31;
-      const int r = (low & 7) + 8 * (hi % (ROWS / 8)), c = ((low >> 3) & 3) + 4 * (hi / (ROWS / 8));
-      float* dst = smem + ((r & 7) * 4 + (r >> 3) * (CH * 32) + c * 32);
-      if (row0 + r < rows_valid && k0 + c * 4 < k_valid) {
-        const float* src = g + (size_t)(row0 + r) * row_stride + (k0 + c * 4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-      } else {
-        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+  constexpr int RC = ROWS / 4;
+  constexpr int U = 8;        // loads in flight per thread
+  const int total = RC * kb;  // (4-row chunk, k) items
+  for (int base = tid; base < total; base += THREADS * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * THREADS, hi = idx >> 5;
+      const int k = (idx & 3) | (((idx >> 3) & 3) << 2) | ((hi % (kb >> 4)) << 4);
+      const int rc = ((idx >> 2) & 1) | ((hi / (kb >> 4)) << 1);
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < total && row0 + rc * 4 < rows_valid && k0 + k < k_valid)
+        v[u] = __ldg(reinterpret_cast<const float4*>(g + (size_t)(k0 + k) * col_stride + (row0 + rc * 4)));
     }
-  } else {
-    constexpr int RC = ROWS / 4;
-    constexpr int U = 8;        // loads in flight per thread
-    const int total = RC * kb;  // (4-row chunk, k) items
-    for (int base = tid; base < total; base += THREADS * U) {
-      float4 v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int idx = base + u * THREADS, hi = idx >> 5;
-        const int k = (idx & 3) | (((idx >> 3) & 3) << 2) | ((hi % (kb >> 4)) << 4);
-        const int rc = ((idx >> 2) & 1) | ((hi / (kb >> 4)) << 1);
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < total && row0 + rc * 4 < rows_valid && k0 + k < k_valid)
-          v[u] = __ldg(reinterpret_cast<const float4*>(g + (size_t)(k0 + k) * col_stride + (row0 + rc * 4)));
-      }
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * THREADS, hi = idx >> 5;
+      if (idx >= total) break;
+      const int k = (idx & 3) | (((idx >> 3) & 3) << 2) | ((hi % (kb >> 4)) << 4);
+      const int r = (((idx >> 2) & 1) | ((hi / (kb >> 4)) << 1)) * 4;
+      float* base_p = smem + ((r >> 3) * (CH * 32) + (k >> 2) * 32 + (k & 3));
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int idx = base + u * THREADS, hi = idx >> 5;
-        if (idx >= total) break;
-        const int k = (idx & 3) | (((idx >> 3) & 3) << 2) | ((hi % (kb >> 4)) << 4);
-        const int r = (((idx >> 2) & 1) | ((hi / (kb >> 4)) << 1)) * 4;
-        float* base_p = smem + ((r >> 3) * (CH * 32) + (k >> 2) * 32 + (k & 3));
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = (jj + (k >> 2)) & 3;
-          const float x = j == 0 ? v[u].x : (j == 1 ? v[u].y : (j == 2 ? v[u].z : v[u].w));
-          base_p[((r + j) & 7) * 4] = x;
-        }
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = (jj + (k >> 2)) & 3;
+        const float x = j == 0 ? v[u].x : (j == 1 ? v[u].y : (j == 2 ? v[u].z : v[u].w));
+        base_p[((r + j) & 7) * 4] = x;
       }
     }
   }
@@ -256,8 +238,8 @@ __global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constan
                          "r"(smem_u32(&tma_bar)) : "memory");
       }
     }
-    if (A_MN) stage_tile<BM, true>(sA, p.A, p.a_row, p.a_col, m0, k0, p.M, kend, kb);
-    if (B_MN) stage_tile<BN, true>(sB, p.B, p.b_row, p.b_col, n0, k0, p.N, kend, kb);
+    if (A_MN) stage_tile_transposed<BM>(sA, p.A, p.a_col, m0, k0, p.M, kend, kb);
+    if (B_MN) stage_tile_transposed<BN>(sB, p.B, p.b_col, n0, k0, p.N, kend, kb);
     stamp(p, 2);
     if (A_MN || B_MN) asm volatile("fence.proxy.async.shared::cta;");  // generic-proxy writes -> visible to the tensor core
     __syncthreads();
