@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "rsrx_env.cuh"
 #include "rsrx_loss.cuh"
@@ -36,6 +37,9 @@ struct rsrx_model {
   void* mid_dev = nullptr;
   int mid_arena_bytes = 0;
   int* redo = nullptr;
+  // buffers outgrown by a larger batch: launches already queued may still use them, so they are kept until the model is
+  // destroyed instead of synchronising the device inside reset / step
+  std::vector<void*> retired;
 };
 
 // Launch shape for N envs: one CTA per SM per round, the rounds as evenly filled as possible.  8192 envs on 148 SMs:
@@ -412,6 +416,7 @@ extern "C" void rsrx_model_destroy(rsrx_model* m) {
   if (m->mid_dev) cudaFree(m->mid_dev);
   if (m->spill) cudaFree(m->spill);
   if (m->redo) cudaFree(m->redo);
+  for (void* p : m->retired) cudaFree(p);
   delete m;
 }
 
@@ -442,7 +447,7 @@ static int ensure_spill(const rsrx_model* cm, int N) {
     return fail(std::string("rsrx: cannot allocate the Jacobian spill buffer (call reset/step once for this batch size "
                             "before capturing a CUDA graph): ") + cudaGetErrorString(e));
   }
-  if (m->spill) { cudaDeviceSynchronize(); cudaFree(m->spill); cudaFree(m->redo); }
+  if (m->spill) { m->retired.push_back(m->spill); m->retired.push_back(m->redo); }
   m->spill = fresh;
   m->redo = redo;
   m->spill_envs = N;

@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import math
 import time
-from typing import Any, Callable, Dict, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, Optional, Sequence
 
 import torch
 import torch.distributed as dist

@@ -20,7 +20,7 @@ from typing import Any, Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib, prng, rsr_loss
+from . import prng, rsr_loss
 from .envs import AirbotPlayBase
 
 # compute_error weights, rsr_pipeline.py:120

@@ -19,9 +19,8 @@ env shard and samples its own buffer, gradients are averaged with one flat all-r
 """
 from __future__ import annotations
 
-import math
 import time
-from typing import Any, Callable, Dict, Optional, Sequence
+from typing import Any, Callable, Dict, Optional
 
 import torch
 import torch.distributed as dist

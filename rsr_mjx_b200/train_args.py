@@ -4,7 +4,7 @@
 from __future__ import annotations
 
 import functools
-from typing import Any, Dict, Optional, Sequence
+from typing import Any, Dict, Sequence
 
 import numpy as np
 
