@@ -335,7 +335,35 @@ __device__ __forceinline__ bool env_step_body(const DModel* __restrict__ dm, flo
   for (int i = lane; i < dm->nq; i += 32) bad |= !isfinite(sm[ar::QPOS + i]);
 #pragma unroll 1
   for (int i = lane; i < dm->nv; i += 32) bad |= !isfinite(sm[ar::QVEL + i]);
-  if (__any_sync(0xffffffffu, bad)) status |= RSRX_STATUS_NONFINITE;
+  if (__any_sync(0xffffffffu, bad)) {
+    status |= RSRX_STATUS_NONFINITE;
+    // Deliberate deviation from MJX / brax, which would carry the NaN state (and NaN rewards and observations, i.e. NaN
+    // gradients in a trainer) to the end of the episode: a wrapped env whose simulation blew up — an object knocked
+    // off the table at tens of rad/s, ~1 env-step in 3e7 under uniform random actions — is terminated here with zero
+    // reward and auto-reset like any other `done`, its info / metrics put back to their reset values; the sticky
+    // status bit reports it.  The bare env (episode_length <= 0) keeps MJX's behaviour.
+    if (dm->episode_length > 0) {
+      done = 1.f;
+      if (lane == 0) {
+        const float* frow = st.first_data + (size_t)e * L.data_stride;
+        st.reward[e] = 0.f;
+        st.done[e] = 1.f;
+        info[RSRX_INFO_TRUNCATION] = 0.f;
+        info[RSRX_INFO_LAST_ACTION] = 0.f;
+        for (int i = 0; i < 3; i++) {
+          info[RSRX_INFO_SITE + i] = frow[L.site_xpos + dm->site_endpoint * 3 + i];
+          info[RSRX_INFO_OBJ + i] = frow[L.xpos + dm->cube_body * 3 + i];
+        }
+        if (kind == RSRX_ENV_T) {
+          info[RSRX_INFO_NEWPOS] = 0.24739072f; info[RSRX_INFO_NEWPOS + 1] = -0.00496255f;
+          info[RSRX_INFO_XITA] = 0.2876f;
+        } else {
+          info[RSRX_INFO_NEWPOS] = 0.37342f; info[RSRX_INFO_NEWPOS + 1] = -0.07989f;
+        }
+        for (int i = 0; i < METRICS_STRIDE; i++) st.metrics[(size_t)e * METRICS_STRIDE + i] = 0.f;
+      }
+    }
+  }
   if (lane == 0 && status) st.status[e] |= status;
   RSRX_SYNC();
   // ---- AutoReset post: pipeline_state and obs only (episode_length <= 0: bare env, no wrappers)

@@ -204,6 +204,49 @@ def test_autoreset_and_episode_semantics():
     np.testing.assert_array_equal(b["first_data"], first["first_data"])
 
 
+@pytest.mark.parametrize("kind,N", [("sf", 40), ("T", 40), ("sf", 3000)])
+def test_nonfinite_env_is_terminated_and_reset(kind, N):
+    """Deliberate deviation from MJX / brax: a wrapped env whose state turns non-finite is terminated
+    with zero reward and auto-reset in the same step — data / obs back to first_*, info / metrics to their reset values,
+    RSRX_STATUS_NONFINITE set — instead of feeding NaN to the trainer for the rest of the episode.  Neighbours are
+    untouched (bit-equal to a run without the poisoned env), and the env steps normally afterwards.  N = 3000 takes the
+    19-warp fast kernel, N = 40 the mid-capacity one."""
+    env, keys, ic = _mk(kind, N, seed=8)
+    st, ref = env.reset(keys), env.reset(keys)
+    L = env.layout
+    g = torch.Generator("cuda").manual_seed(3)
+    acts = torch.rand(12, N, 5, device="cuda", generator=g) * 2 - 1
+    for t in range(5):
+        env.step(st, acts[t]); env.step(ref, acts[t])
+    victim = 7
+    st._buf["data"][victim, L.qvel + 1] = float("nan")
+    env.step(st, acts[5]); env.step(ref, acts[5])
+    torch.cuda.synchronize()
+    b, r = P.buffers_to_numpy(st), P.buffers_to_numpy(ref)
+    assert b["status"][victim] & _lib.STATUS_NONFINITE and b["done"][victim] == 1 and b["reward"][victim] == 0
+    np.testing.assert_array_equal(b["data"][victim], b["first_data"][victim])
+    np.testing.assert_array_equal(b["obs"][victim], b["first_obs"][victim])
+    assert np.isfinite(b["info"][victim]).all() and np.isfinite(b["metrics"][victim]).all()
+    assert b["info"][victim, _lib.INFO["TRUNCATION"]] == 0
+    others = np.arange(N) != victim
+    for k in ("data", "obs", "reward", "done", "info", "metrics"):
+        np.testing.assert_array_equal(b[k][others], r[k][others])
+    assert (b["status"][others] & _lib.STATUS_NONFINITE == 0).all()
+    for t in range(6, 12):  # the env is alive again
+        env.step(st, acts[t])
+    torch.cuda.synchronize()
+    b = P.buffers_to_numpy(st)
+    assert np.isfinite(b["data"][victim]).all() and np.isfinite(b["obs"][victim]).all() and np.isfinite(b["reward"][victim])
+    assert b["info"][victim, _lib.INFO["STEPS"]] == 6
+    # the bare env (no wrappers) keeps MJX's behaviour: NaN stays, only the status bit reports it
+    bare = AirbotPlayBase(kind, num_envs=4, episode_length=0)
+    sb = bare.reset(prng.split(prng.PRNGKey(1), 4))
+    sb._buf["data"][1, L.qvel] = float("nan")
+    bare.step(sb, acts[0][:4])
+    torch.cuda.synchronize()
+    assert int(sb._buf["status"][1]) & _lib.STATUS_NONFINITE and not np.isfinite(sb._buf["data"][1].cpu().numpy()).all()
+
+
 @pytest.mark.parametrize("kind,N", [("sf", 8192), ("T", 8192)])
 def test_full_size_properties(kind, N):
     """BASELINE sizes: finite, no status flags, deterministic, env i independent of the batch it runs in"""
