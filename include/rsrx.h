@@ -68,7 +68,10 @@ typedef struct rsrx_layout {
 #define RSRX_INFO_STRIDE 20
 
 /* per-env status bits written by the kernels (no host sync needed to keep going) */
-#define RSRX_STATUS_NONFINITE 1      /* a non-finite value reached qpos/qvel */
+#define RSRX_STATUS_NONFINITE 1      /* a non-finite value reached qpos/qvel.  rsrx_env_step on a wrapped env
+                                      * (episode_length > 0) then ends the env's episode in that step: done = 1,
+                                      * reward 0, state / obs auto-reset, info / metrics back to their reset values
+                                      * (MJX would carry the NaN to the end of the episode); sticky, informational */
 #define RSRX_STATUS_CONTACT_OVERFLOW 2 /* contacts were dropped.  Cannot happen in reset / step / physics_step: an env
                                         * whose substep has more active contacts than the fast kernel's arena holds
                                         * (rsrx_max_contacts()) is re-run by the large-capacity kernel, which keeps every
