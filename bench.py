@@ -316,7 +316,7 @@ def random_action_rollout(kind, dev, n=51, seed=5):
     return np.stack(obs), np.stack(act)
 
 
-def ppo_sub_record(dev, rank, world, training_steps=5):
+def ppo_sub_record(dev, rank, world, training_steps=9):
     """BASELINE config 3 + 4: PPO exactly as ppo_train/airbot_training/train.py:45-55 (1024 envs globally, unroll 10,
     32 x 256 minibatches, 8 updates per batch, lr 1e-4, gamma 0.96, entropy 2e-2, reward scaling 0.1, obs normalisation,
     domain randomisation) WITH the RSR term (past_data, RSR/losses.py:186-195); `training/sps` of RSR/train.py:378-385 =
